@@ -1,0 +1,211 @@
+"""Parity cases: small versions of BASELINE.json's configs plus edge cases.
+
+Each builder returns a tests.scenario.Scenario.  oracle/gen_golden.py replays them on the real
+reference (oracle/_ref/ref_driver) and commits the outcome under tests/golden/; the tests replay
+them on the oracle and on the CUDA engine.  Test infrastructure only.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from scenario import Scenario
+
+
+def cavity(nx, ny, nz, steps, dyn="BGK", q=19, prec="f64", blocks=(1, 1, 1), every=None, model="local",
+           dumps=True):
+    """3D lid-driven cavity of jlabos/src/testing/test_cylinder.py:100-119 (BASELINE configs[0], [1]):
+    uMax=0.02, Re=100, nu=uMax*ny/Re, omega=1/(3nu+0.5); regularized velocity BC on all faces,
+    edges, corners; lid z=nz-1 interior moves with (uMax,0,0); rho=1, u=0 initially."""
+    u_max, re = 0.02, 100.0
+    nu = u_max * ny / re
+    omega = 1.0 / (3 * nu + 0.5)
+    sc = Scenario(q, prec, nx, ny, nz, dyn, omega, 0.14 if dyn == "SMAGO" else 0.0, blocks)
+    sc.bc_box(model)
+    sc.set_velocity(sc.box, (0, 0, 0))
+    sc.set_velocity((1, nx - 2, 1, ny - 2, nz - 1, nz - 1), (u_max, 0, 0))
+    sc.init_eq(sc.box, 1.0, (0, 0, 0))
+    sc.initialize()
+    if dumps:
+        sc.dump("f_init")
+    done = 0
+    if every:
+        while done + every <= steps:
+            sc.run(every).stats()
+            done += every
+    if steps > done:
+        sc.run(steps - done)
+    sc.stats()
+    if dumps:
+        sc.dump("f_end").dump_rho_u("rho_u_end")
+    return sc
+
+
+def poiseuille_profile(nx, ny, nz, u_max, axis_wall=1, perturb=0.0):
+    """rho=1, parabolic u_x(y) between walls at y=0 and y=ny-1, optional deterministic sinusoidal
+    perturbation."""
+    x, y, z = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    yy = (y - 0.5) / (ny - 2.0)
+    ux = 4.0 * u_max * yy * (1.0 - yy)
+    ux[(y == 0) | (y == ny - 1)] = 0.0
+    ru = np.zeros((nx, ny, nz, 4))
+    ru[..., 0] = 1.0
+    ru[..., 1] = ux
+    if perturb:
+        ru[..., 1] += perturb * np.sin(2 * np.pi * (y + 0.5) / ny) * np.cos(2 * np.pi * (z + 0.25) / nz)
+        ru[..., 2] += perturb * np.sin(2 * np.pi * (x + 0.5) / nx) * np.sin(2 * np.pi * (z + 0.75) / nz)
+        ru[..., 3] += perturb * np.cos(2 * np.pi * (x + 0.25) / nx) * np.sin(2 * np.pi * (y + 0.5) / ny)
+        ru[..., 0] += 0.1 * perturb * np.cos(2 * np.pi * x / nx)
+    return ru
+
+
+def channel(nx, ny, nz, steps, dyn="TRT", omega=1.2, q=19, prec="f64", cs=0.0, perturb=0.0, u_max=0.05,
+            blocks=(1, 1, 1), every=None):
+    """Periodic channel (BASELINE configs[2] with TRT; configs[4] with D3Q27 Smagorinsky): periodic in
+    x and z, BounceBack walls at y=0 and y=ny-1, parabolic initial profile."""
+    sc = Scenario(q, prec, nx, ny, nz, dyn, omega, cs, blocks)
+    sc.periodic(1, 0, 1)
+    sc.dynamics((0, nx - 1, 0, 0, 0, nz - 1), "BB", 1.0)
+    sc.dynamics((0, nx - 1, ny - 1, ny - 1, 0, nz - 1), "BB", 1.0)
+    sc.init_eq_field(sc.box, poiseuille_profile(nx, ny, nz, u_max, perturb=perturb))
+    sc.initialize()
+    sc.dump("f_init")
+    done = 0
+    if every:
+        while done + every <= steps:
+            sc.run(every).stats()
+            done += every
+    if steps > done:
+        sc.run(steps - done)
+    sc.stats().dump("f_end").dump_rho_u("rho_u_end")
+    return sc
+
+
+def sphere_mask(nx, ny, nz, cx, cy, cz, r):
+    x, y, z = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    return (((x - cx) ** 2 + (y - cy) ** 2 + (z - cz) ** 2) <= r * r).astype(np.int32)
+
+
+def obstacle(nx, ny, nz, steps, dyn="BGK", omega=1.5, model="zouhe", q=19, prec="f64", u_in=0.03, mask=None,
+             blocks=(1, 1, 1)):
+    """Flow past a voxelised obstacle (BASELINE configs[3]): velocity inlet x=0 and pressure outlet
+    x=nx-1 (Zou-He or regularized), BounceBack on the four side walls and on the flagged voxels."""
+    sc = Scenario(q, prec, nx, ny, nz, dyn, omega, 0.0, blocks)
+    sc.bc_vel(model, 0, -1, (0, 0, 1, ny - 2, 1, nz - 2))
+    sc.bc_pres(model, 0, +1, (nx - 1, nx - 1, 1, ny - 2, 1, nz - 2))
+    sc.dynamics((0, nx - 1, 0, 0, 0, nz - 1), "BB", 1.0)
+    sc.dynamics((0, nx - 1, ny - 1, ny - 1, 0, nz - 1), "BB", 1.0)
+    sc.dynamics((0, nx - 1, 0, ny - 1, 0, 0), "BB", 1.0)
+    sc.dynamics((0, nx - 1, 0, ny - 1, nz - 1, nz - 1), "BB", 1.0)
+    if mask is None:
+        mask = sphere_mask(nx, ny, nz, nx // 3, ny / 2 - 0.5, nz / 2 - 0.5, min(ny, nz) / 5.0)
+    sc.dynamics_mask(mask, 1, "BB", 1.0)
+    sc.set_velocity(sc.box, (u_in, 0, 0))
+    sc.set_density(sc.box, 1.0)
+    sc.init_eq(sc.box, 1.0, (u_in, 0, 0))
+    sc.initialize()
+    sc.dump("f_init")
+    sc.run(steps).stats().dump("f_end").dump_rho_u("rho_u_end")
+    return sc
+
+
+def periodic_box(nx, ny, nz, steps, dyn, omega, q=19, prec="f64", cs=0.0, perturb=0.02, blocks=(1, 1, 1)):
+    """Fully periodic box with a deterministic perturbation; optional region of different omega."""
+    sc = Scenario(q, prec, nx, ny, nz, dyn, omega, cs, blocks)
+    sc.periodic(1, 1, 1)
+    ru = poiseuille_profile(nx, ny, nz, 0.0, perturb=perturb)
+    ru[..., 1] += 0.03
+    sc.init_eq_field(sc.box, ru)
+    sc.initialize()
+    sc.run(steps).stats().dump("f_end").dump_rho_u("rho_u_end")
+    return sc
+
+
+def mixed_omega(nx, ny, nz, steps):
+    """BGK with a sub-box at a different omega, a NoDynamics block and half-open boundaries: exercises the
+    dynamics table, the on-site rule at non-periodic domain edges and partial periodicity."""
+    sc = Scenario(19, "f64", nx, ny, nz, "BGK", 1.3)
+    sc.periodic(0, 1, 0)
+    sc.dynamics((2, nx // 2, 1, ny - 2, 2, nz - 3), "BGK", 1.7)
+    sc.dynamics((nx - 3, nx - 2, 2, 3, 1, 2), "NODYN", 1.0)
+    sc.dynamics((1, 2, 1, 2, nz - 2, nz - 2), "RLB", 1.1)
+    ru = poiseuille_profile(nx, ny, nz, 0.0, perturb=0.02)
+    sc.init_eq_field(sc.box, ru)
+    sc.initialize()
+    sc.run(steps).stats().dump("f_end").dump_rho_u("rho_u_end")
+    return sc
+
+
+def inlet_outlet_local(nx, ny, nz, steps):
+    """Regularized velocity inlet + regularized pressure outlet + velocity side walls with their outer
+    edges/corners restricted to a sub-domain (applicationDomain != block)."""
+    sc = Scenario(19, "f64", nx, ny, nz, "BGK", 1.6)
+    sc.bc_box("local", sc.box, (0, nx - 2, 0, ny - 1, 0, nz - 1))          # everything but the x=nx-1 face
+    sc.bc_pres("local", 0, +1, (nx - 1, nx - 1, 1, ny - 2, 1, nz - 2))
+    sc.dynamics((nx - 1, nx - 1, 0, 0, 0, nz - 1), "BB", 1.0)
+    sc.dynamics((nx - 1, nx - 1, ny - 1, ny - 1, 0, nz - 1), "BB", 1.0)
+    sc.dynamics((nx - 1, nx - 1, 0, ny - 1, 0, 0), "BB", 1.0)
+    sc.dynamics((nx - 1, nx - 1, 0, ny - 1, nz - 1, nz - 1), "BB", 1.0)
+    sc.set_velocity(sc.box, (0, 0, 0))
+    sc.set_velocity((0, 0, 1, ny - 2, 1, nz - 2), (0.02, 0.001, -0.002))
+    sc.set_density(sc.box, 1.01)
+    sc.init_eq(sc.box, 1.0, (0.01, 0, 0))
+    sc.initialize()
+    sc.dump("f_init")
+    sc.run(steps).stats().dump("f_end").dump_rho_u("rho_u_end")
+    return sc
+
+
+# name -> (builder, how to store the reference outcome: "full" dumps, or "probe" = sha256 + sampled cells)
+CASES = {
+    # configs[0]-style cavity, all dynamics on the path
+    "cavity_bgk_10x9x8":        (lambda: cavity(10, 9, 8, 60, every=20), "full"),
+    "cavity_rlb_10x9x8":        (lambda: cavity(10, 9, 8, 40, dyn="RLB"), "full"),
+    "cavity_trt_9x8x10":        (lambda: cavity(9, 8, 10, 40, dyn="TRT"), "full"),
+    "cavity_smago_8x9x10":      (lambda: cavity(8, 9, 10, 40, dyn="SMAGO"), "full"),
+    "cavity_bgk_f32_10x9x8":    (lambda: cavity(10, 9, 8, 40, prec="f32"), "full"),
+    "cavity_bgk_q27_8x8x9":     (lambda: cavity(8, 8, 9, 30, q=27), "full"),
+    "cavity_zouhe_10x9x8":      (lambda: cavity(10, 9, 8, 40, model="zouhe"), "full"),
+    # the reference's own known-answer sizes (test_cylinder.py:85-97), 30 steps
+    "cavity_bgk_20":            (lambda: cavity(20, 20, 20, 30), "probe"),
+    "cavity_bgk_39":            (lambda: cavity(39, 39, 39, 30), "probe"),
+    "cavity_bgk_58":            (lambda: cavity(58, 58, 58, 30), "probe"),
+    "cavity_bgk_20x31x42":      (lambda: cavity(20, 31, 42, 30), "probe"),
+    "cavity_bgk_f32_20x31x42":  (lambda: cavity(20, 31, 42, 30, prec="f32"), "probe"),
+    # decomposition invariance of the reference itself: same case, 8 blocks
+    "cavity_bgk_12_blocks222":  (lambda: cavity(12, 12, 12, 30, blocks=(2, 2, 2)), "full"),
+    "cavity_bgk_12":            (lambda: cavity(12, 12, 12, 30), "full"),
+    # configs[0] proper: 64^3, 1000 steps (the 1e-10 pin of north_star)
+    "cavity_bgk_64_1000":       (lambda: cavity(64, 64, 64, 1000, every=250, dumps=True), "probe"),
+    # configs[2]: periodic TRT channel
+    "channel_trt_16x12x10":     (lambda: channel(16, 12, 10, 50, every=25), "full"),
+    "channel_trt_blocks":       (lambda: channel(16, 12, 10, 50, blocks=(4, 1, 1)), "full"),
+    "channel_trt_q27_8x8x8":    (lambda: channel(8, 8, 8, 30, q=27), "full"),
+    # configs[3]: obstacle with Zou-He inlet/outlet
+    "obstacle_zouhe_24x12x10":  (lambda: obstacle(24, 12, 10, 50), "full"),
+    "obstacle_local_rlb":       (lambda: obstacle(20, 10, 9, 40, dyn="RLB", omega=1.4, model="local"), "full"),
+    # configs[4]: D3Q27 Smagorinsky channel, fp64 and fp32
+    "channel_smago_q27_f64":    (lambda: channel(12, 10, 8, 50, dyn="SMAGO", omega=1.9, q=27, cs=0.14, perturb=0.01), "full"),
+    "channel_smago_q27_f32":    (lambda: channel(12, 10, 8, 50, dyn="SMAGO", omega=1.9, q=27, cs=0.14, perturb=0.01, prec="f32"), "full"),
+    "periodic_smago_q19_f32":   (lambda: periodic_box(9, 8, 7, 30, "SMAGO", 1.8, cs=0.17, prec="f32"), "full"),
+    "periodic_bgk_q27_f32":     (lambda: periodic_box(8, 7, 9, 30, "BGK", 1.5, q=27, prec="f32"), "full"),
+    "periodic_rlb_q27":         (lambda: periodic_box(8, 7, 9, 30, "RLB", 1.5, q=27), "full"),
+    "periodic_trt_f32":         (lambda: periodic_box(8, 7, 9, 30, "TRT", 1.5, prec="f32"), "full"),
+    # edge cases
+    "mixed_omega_11x8x9":       (lambda: mixed_omega(11, 8, 9, 40), "full"),
+    "inlet_outlet_local":       (lambda: inlet_outlet_local(12, 9, 8, 40), "full"),
+    "thin_4x5x3":               (lambda: cavity(4, 5, 3, 10), "full"),
+}
+
+PROBE_CELLS = 97  # cells sampled (deterministically) from large dumps
+
+
+def probe_index(shape, n=PROBE_CELLS):
+    """Deterministic sample of cells: corners, a face/edge walk and an LCG scatter."""
+    nx, ny, nz = shape[:3]
+    total = nx * ny * nz
+    idx = {0, total - 1, nz - 1, (ny - 1) * nz, (nx - 1) * ny * nz, (nx // 2 * ny + ny // 2) * nz + nz // 2}
+    s = 12345
+    while len(idx) < min(n, total):
+        s = (1103515245 * s + 12345) % (1 << 31)
+        idx.add(s % total)
+    return np.array(sorted(idx), dtype=np.int64)
