@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS of the collide-and-stream hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- 3D lid-driven cavity, D3Q19 BGK fp64, 512^3
+per GPU, regularized velocity boundaries on all faces / edges / corners (Palabos cavity3d), synthetic
+initial state rho=1, u=0.  With N GPUs the cavity is (512 N) x 512 x 512, one x-slab per rank
+(weak scaling, NCCL send/recv of the face-crossing populations between neighbours).
+
+One JSON line on rank 0:
+  value     whole-job MLUPS, state resident in HBM, CUDA events, max over ranks
+  e2e       the same job through the public C-ABI from HOST buffers: upload of the initial
+            populations (pinned host memory), K x {setBoundaryVelocity on the lid, collideAndStream,
+            read the stored statistics}, download of the final populations -- all inside the timed
+            region
+  roofline  sweep kernel: 2*q*sizeof(T) algorithmic bytes per cell / its CUDA-event duration,
+            against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own CPU code (oracle/_ref/ref_driver, or the C port when that binary
+            is absent) on a bounded sample of the same workload, rank 0, N=1 only
+--impl reference times that CPU implementation with as many host processes as there are cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+Q, PREC, BYTES_PER_LU = 19, "f64", 2 * 19 * 8
+U_MAX, RE = 0.02, 100.0
+
+
+def cavity_omega(ny):
+    nu = U_MAX * ny / RE
+    return 1.0 / (3 * nu + 0.5)
+
+
+# ----------------------------------------------------------------------------------- reference arm
+
+
+def cpu_reference_run(n, steps, procs):
+    """MLUPS of the reference's CPU implementation on an n^3 cavity, `procs` independent serial
+    processes side by side (the reference has no threads; its MPI build is not available here)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cases import cavity
+    import scenario
+    sc = cavity(n, n, n, 0, dumps=False)
+    sc.ops = [op for op in sc.ops if op[0] not in ("stats",)]
+    if scenario.have_reference_driver("f64"):
+        kind = "reference"
+
+        def one(out, k):
+            out[k] = scenario.run_reference(sc, timed_steps=steps)["time"]
+    else:
+        kind = "port"
+
+        def one(out, k):
+            eng = scenario.OracleEngine(sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2)
+            scenario.replay(sc, eng)
+            t0 = time.perf_counter()
+            eng.collide_and_stream(steps)
+            dt = time.perf_counter() - t0
+            out[k] = (steps, dt, n ** 3 * steps / dt / 1e6)
+            eng.close()
+    out = [None] * procs
+    t0 = time.perf_counter()
+    if kind == "reference":
+        th = [threading.Thread(target=one, args=(out, k)) for k in range(procs)]   # each thread waits on a subprocess
+        [t.start() for t in th]
+        [t.join() for t in th]
+    else:
+        # the ctypes port holds no GIL while in C, threads are enough
+        th = [threading.Thread(target=one, args=(out, k)) for k in range(procs)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+    wall = time.perf_counter() - t0
+    slowest = max(o[1] for o in out)
+    mlups = procs * n ** 3 * steps / slowest / 1e6
+    return {"value": mlups, "unit": "MLUPS", "cores": procs, "kind": kind,
+            "sample": "%d^3 lid-driven cavity D3Q19 BGK fp64, %d steps, %d serial process(es) of the reference side by side, "
+                      "slowest process %.2f s (wall incl. set-up %.1f s)" % (n, steps, procs, slowest, wall)}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    t0 = time.perf_counter()
+    runs = []
+    for k in range(args.warmup + args.steps):
+        # a "step" of this arm = a bounded sample: 96^3 cavity, 10 time steps per process
+        r = cpu_reference_run(96, 10, procs)
+        if k >= args.warmup:
+            runs.append(r)
+        if time.perf_counter() - t0 > 240 and runs:
+            break
+    v = statistics.median(r["value"] for r in runs)
+    base = dict(runs[-1]); base["value"] = v
+    line = {"impl": "reference", "metric": "MLUPS", "value": v, "unit": "MLUPS", "n_gpus": args.gpus, "steps": len(runs),
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D lid-driven cavity D3Q19 BGK fp64, regularized velocity BC (reference CPU code, bounded sample 96^3)"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- our arm
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc = None
+        self.path = tempfile.NamedTemporaryFile(delete=False, suffix=".csv").name
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            w = [x.strip() for x in ln.split(",")]
+            if len(w) < 7:
+                continue
+            try:
+                sm.append(float(w[0])); mx.append(float(w[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, w[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.path)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def our_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import palabos_b200 as pb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the engine has no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = args.n
+    nx, ny, nz = n * world, n, n
+    omega = cavity_omega(ny)
+    lat = pb.Lattice(Q, PREC, nx, ny, nz, "BGK", omega, rank=rank, n_ranks=world, slabs_per_rank=1)
+    if world > 1:
+        uid = [pb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        lat.comm_init(uid[0])
+    box = lat.box
+    lid = (1, nx - 2, 1, ny - 2, nz - 1, nz - 1)
+    lat.set_velocity_condition_on_block_boundaries("local", box, box)
+    lat.set_boundary_velocity(box, (0, 0, 0))
+    lat.set_boundary_velocity(lid, (U_MAX, 0, 0))
+    lat.initialize_at_equilibrium(box, 1.0, (0, 0, 0))
+    lat.initialize()
+    lat.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cells_global = nx * ny * nz
+    cells_local = lat.local_cells()
+
+    # ---- value: state resident in HBM ----------------------------------------------------------
+    lat.collide_and_stream(args.warmup)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lat.launch_count()
+    lat.profile_sweeps(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lat.collide_and_stream(args.steps)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sweep_ms, sweep_n = lat.profile_read()
+    lat.profile_sweeps(False)
+    launches = lat.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = cells_global * args.steps / (ms * 1e-3) / 1e6
+    stats = lat.stored_statistics()
+
+    # ---- roofline of the sweep kernel ----------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    achieved = cells_local * BYTES_PER_LU / (sweep_ms / max(sweep_n, 1) * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch_512")
+        if n != 512:
+            traffic = None
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "sweep_kernel<double,19,BGK> (even/odd AA halves averaged)", "peak_source": peak_src,
+                "algorithmic_bytes_per_cell": BYTES_PER_LU, "cells_per_launch": cells_local,
+                "kernel_ms": sweep_ms / max(sweep_n, 1), "kernel_share_of_step": sweep_ms / ms}
+
+    # ---- e2e: the same job from host buffers through the C-ABI ----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        nbytes = cells_local * Q * 8
+        try:
+            host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            pinned = True
+        except Exception:
+            host = torch.empty(nbytes, dtype=torch.uint8)
+            pinned = False
+        lat.download_ptr(host.data_ptr(), nbytes)       # a valid initial state to upload (outside the timed region)
+        k2 = args.e2e_steps or args.steps
+        barrier()
+        launches_e0 = lat.launch_count()
+        t0 = time.perf_counter()
+        lat.upload_ptr(host.data_ptr(), nbytes)
+        for it in range(k2):
+            lat.set_boundary_velocity(lid, (U_MAX * min(1.0, (it + 1) / 50.0), 0, 0))
+            lat.collide_and_stream(1)
+            lat.stored_statistics()
+        lat.download_ptr(host.data_ptr(), nbytes)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        lid_records = (nx - 2) * (ny - 2) if world == 1 else None
+        e2e = {"value": cells_global * k2 / dt / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": (nbytes * world) / k2 + (48 * (nx - 2) * (ny - 2)),
+               "d2h_bytes_per_step": (nbytes * world) / k2 + 32 * world,
+               "steps": k2, "seconds": dt, "pinned_host": pinned,
+               "what": "upload initial populations + K x {setBoundaryVelocity(lid), collideAndStream, getStored statistics} + download final populations",
+               "launches": lat.launch_count() - launches_e0}
+        del host
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference_run(128, 10, 1)
+
+    if rank == 0:
+        line = {"metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "3D lid-driven cavity D3Q19 BGK fp64, %dx%dx%d (%d^3 per GPU), regularized velocity BC on faces/edges/corners"
+                                       % (nx, ny, nz, n),
+                           "parallelism": "x-slabs, %d rank(s)" % world, "streaming": "in-place AA pattern",
+                           "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed" % (cells_local * Q * 8 / 1e9),
+                           "omega": omega, "stored_avg_energy": 0.5 * stats[1], "stored_avg_density": stats[0] + 1.0},
+                "mlups_per_gpu": value / world,
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    lat.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="cavity edge per GPU (default: the configs[1] size)")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        our_arm(args)
+
+
+if __name__ == "__main__":
+    main()

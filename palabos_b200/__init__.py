@@ -1,0 +1,296 @@
+"""palabos_b200 -- ctypes binding of libplb_b200.so (include/plb_b200.h).
+
+The product is the C-ABI shared library (hand-written sm_100a CUDA behind the Palabos API for
+MultiBlockLattice3D::collideAndStream and its boundary processors / envelope exchange /
+statistics); the C++ mirror of the reference's classes is include/palabos_b200/.  This module is
+the thin Python view of the same ABI used by tests/ and bench.py: :class:`Lattice` has one method
+per C entry point, named after the reference wrapper it replaces.
+
+There is no CPU fallback: creating a lattice without the built library or without a CUDA device
+raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(ROOT, "libplb_b200.so")
+CSRC = os.path.join(ROOT, "csrc")
+
+DYN = {"BGK": 0, "RLB": 1, "TRT": 2, "SMAGO": 3, "BB": 4, "NODYN": 5}
+BC = {"local": 0, "zouhe": 1}
+
+#: every symbol include/plb_b200.h declares (tests check the library exports them all)
+SYMBOLS = [
+    "plb_b200_create", "plb_b200_create_distributed", "plb_b200_destroy", "plb_b200_last_error",
+    "plb_b200_abi_version", "plb_b200_comm_unique_id", "plb_b200_comm_init", "plb_b200_slab_range",
+    "plb_b200_set_stream", "plb_b200_set_periodicity", "plb_b200_toggle_internal_statistics",
+    "plb_b200_define_dynamics_box", "plb_b200_define_dynamics_mask", "plb_b200_add_velocity_boundary",
+    "plb_b200_add_pressure_boundary", "plb_b200_add_external_velocity_edge",
+    "plb_b200_add_external_velocity_corner", "plb_b200_set_velocity_condition_on_block_boundaries",
+    "plb_b200_set_boundary_velocity", "plb_b200_set_boundary_density", "plb_b200_initialize_at_equilibrium",
+    "plb_b200_initialize_at_equilibrium_field", "plb_b200_initialize", "plb_b200_upload", "plb_b200_download",
+    "plb_b200_local_bytes", "plb_b200_collide_and_stream", "plb_b200_synchronize",
+    "plb_b200_get_stored_statistics", "plb_b200_compute_average_energy", "plb_b200_compute_average_density",
+    "plb_b200_compute_density_velocity", "plb_b200_launch_count", "plb_b200_device_bytes",
+    "plb_b200_boundary_stages", "plb_b200_profile_sweeps", "plb_b200_profile_read", "plb_b200_coproc_add_domain", "plb_b200_coproc_send",
+    "plb_b200_coproc_receive", "plb_b200_coproc_collide_and_stream", "plb_b200_coproc_remove_domain",
+]
+
+
+def build(verbose=False):
+    """Compile libplb_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    jobs = str(min(8, os.cpu_count() or 1))
+    r = subprocess.run(["make", "-C", CSRC, "-j", jobs], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libplb_b200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("palabos_b200/libplb_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+        L.plb_b200_create.restype = vp
+        L.plb_b200_create.argtypes = [ci] * 6 + [cd] * 2
+        L.plb_b200_create_distributed.restype = vp
+        L.plb_b200_create_distributed.argtypes = [ci] * 6 + [cd] * 2 + [ci] * 3
+        L.plb_b200_destroy.restype = None
+        L.plb_b200_destroy.argtypes = [vp]
+        L.plb_b200_last_error.restype = ctypes.c_char_p
+        L.plb_b200_local_bytes.restype = ctypes.c_size_t
+        L.plb_b200_local_bytes.argtypes = [vp, vp]
+        L.plb_b200_launch_count.restype = ctypes.c_uint64
+        L.plb_b200_launch_count.argtypes = [vp]
+        L.plb_b200_device_bytes.restype = ctypes.c_size_t
+        L.plb_b200_device_bytes.argtypes = [vp]
+        L.plb_b200_comm_unique_id.argtypes = [vp]
+        L.plb_b200_comm_init.argtypes = [vp, vp]
+        L.plb_b200_set_stream.argtypes = [vp, vp]
+        L.plb_b200_set_periodicity.argtypes = [vp, ci, ci, ci]
+        L.plb_b200_toggle_internal_statistics.argtypes = [vp, ci]
+        L.plb_b200_define_dynamics_box.argtypes = [vp, vp, ci, cd, cd]
+        L.plb_b200_define_dynamics_mask.argtypes = [vp, vp, ci, ci, cd, cd]
+        L.plb_b200_add_velocity_boundary.argtypes = [vp, ci, ci, ci, vp]
+        L.plb_b200_add_pressure_boundary.argtypes = [vp, ci, ci, ci, vp]
+        L.plb_b200_add_external_velocity_edge.argtypes = [vp, ci, ci, ci, ci, vp]
+        L.plb_b200_add_external_velocity_corner.argtypes = [vp] + [ci] * 7
+        L.plb_b200_set_velocity_condition_on_block_boundaries.argtypes = [vp, ci, vp, vp]
+        L.plb_b200_set_boundary_velocity.argtypes = [vp, vp, vp]
+        L.plb_b200_set_boundary_density.argtypes = [vp, vp, cd]
+        L.plb_b200_initialize_at_equilibrium.argtypes = [vp, vp, cd, vp]
+        L.plb_b200_initialize_at_equilibrium_field.argtypes = [vp, vp, vp]
+        L.plb_b200_initialize.argtypes = [vp]
+        L.plb_b200_upload.argtypes = [vp, vp, vp, ctypes.c_size_t]
+        L.plb_b200_download.argtypes = [vp, vp, vp, ctypes.c_size_t]
+        L.plb_b200_collide_and_stream.argtypes = [vp, ci]
+        L.plb_b200_synchronize.argtypes = [vp]
+        L.plb_b200_get_stored_statistics.argtypes = [vp, vp, vp]
+        L.plb_b200_compute_average_energy.argtypes = [vp, vp, vp]
+        L.plb_b200_compute_average_density.argtypes = [vp, vp, vp]
+        L.plb_b200_compute_density_velocity.argtypes = [vp, vp, vp, ctypes.c_size_t]
+        L.plb_b200_boundary_stages.argtypes = [vp, vp, vp]
+        L.plb_b200_profile_sweeps.argtypes = [vp, ci]
+        L.plb_b200_profile_read.argtypes = [vp, vp, vp]
+        L.plb_b200_slab_range.argtypes = [ci, ci, ci, vp, vp]
+        L.plb_b200_coproc_add_domain.argtypes = [ci, ci, ci, ci, cd, vp]
+        L.plb_b200_coproc_send.argtypes = [ci, vp, vp, ctypes.c_size_t]
+        L.plb_b200_coproc_receive.argtypes = [ci, vp, vp, ctypes.c_size_t]
+        L.plb_b200_coproc_collide_and_stream.argtypes = [ci]
+        L.plb_b200_coproc_remove_domain.argtypes = [ci]
+        _lib = L
+    return _lib
+
+
+class PlbError(RuntimeError):
+    """A C-ABI call returned 0 (the shim's equivalent of the reference's PlbLogicException)."""
+
+
+def _box(b):
+    return (ctypes.c_int * 6)(*[int(v) for v in b])
+
+
+def _vec(u):
+    return (ctypes.c_double * 3)(*[float(v) for v in u])
+
+
+def slab_range(nx, n_slabs, slab):
+    x0, x1 = ctypes.c_int(), ctypes.c_int()
+    if not lib().plb_b200_slab_range(nx, n_slabs, slab, ctypes.byref(x0), ctypes.byref(x1)):
+        raise PlbError(lib().plb_b200_last_error().decode())
+    return x0.value, x1.value
+
+
+def comm_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    if not lib().plb_b200_comm_unique_id(buf):
+        raise PlbError(lib().plb_b200_last_error().decode())
+    return buf.raw
+
+
+class Lattice:
+    """One MultiBlockLattice3D<T,Descriptor> on the GPU(s), through the C-ABI."""
+
+    def __init__(self, q, prec, nx, ny, nz, dyn, p1, p2=0.0, rank=0, n_ranks=1, slabs_per_rank=1):
+        self.lib = lib()
+        self.q, self.prec, self.nx, self.ny, self.nz = q, prec, nx, ny, nz
+        self.rank, self.n_ranks, self.slabs_per_rank = rank, n_ranks, slabs_per_rank
+        self.dtype = np.float64 if prec == "f64" else np.float32
+        self.h = ctypes.c_void_p(self.lib.plb_b200_create_distributed(
+            q, 8 if prec == "f64" else 4, nx, ny, nz, DYN[dyn], p1, p2, rank, n_ranks, slabs_per_rank))
+        if not self.h:
+            raise PlbError(self.lib.plb_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.plb_b200_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, ok):
+        if not ok:
+            raise PlbError(self.lib.plb_b200_last_error().decode())
+
+    @property
+    def box(self):
+        return (0, self.nx - 1, 0, self.ny - 1, 0, self.nz - 1)
+
+    def comm_init(self, uid: bytes):
+        self._ck(self.lib.plb_b200_comm_init(self.h, ctypes.c_char_p(uid)))
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.plb_b200_set_stream(self.h, ctypes.c_void_p(int(cuda_stream))))
+
+    def set_periodicity(self, px, py, pz):
+        self._ck(self.lib.plb_b200_set_periodicity(self.h, int(px), int(py), int(pz)))
+
+    def toggle_internal_statistics(self, on):
+        self._ck(self.lib.plb_b200_toggle_internal_statistics(self.h, int(bool(on))))
+
+    def define_dynamics(self, box, kind, p1, p2=0.0):
+        self._ck(self.lib.plb_b200_define_dynamics_box(self.h, _box(box), DYN[kind], p1, p2))
+
+    def define_dynamics_mask(self, mask, flag, kind, p1, p2=0.0):
+        mask = np.ascontiguousarray(mask, dtype=np.int32)
+        assert mask.shape == (self.nx, self.ny, self.nz)
+        self._ck(self.lib.plb_b200_define_dynamics_mask(self.h, mask.ctypes.data_as(ctypes.c_void_p), int(flag), DYN[kind], p1, p2))
+
+    def set_velocity_condition_on_block_boundaries(self, model, block=None, app=None):
+        block = block or self.box
+        self._ck(self.lib.plb_b200_set_velocity_condition_on_block_boundaries(self.h, BC[model], _box(block), _box(app or block)))
+
+    def add_velocity_boundary(self, model, d, o, box):
+        self._ck(self.lib.plb_b200_add_velocity_boundary(self.h, BC[model], d, o, _box(box)))
+
+    def add_pressure_boundary(self, model, d, o, box):
+        self._ck(self.lib.plb_b200_add_pressure_boundary(self.h, BC[model], d, o, _box(box)))
+
+    def add_external_velocity_edge(self, model, plane, n1, n2, box):
+        self._ck(self.lib.plb_b200_add_external_velocity_edge(self.h, BC[model], plane, n1, n2, _box(box)))
+
+    def add_external_velocity_corner(self, model, xn, yn, zn, x, y, z):
+        self._ck(self.lib.plb_b200_add_external_velocity_corner(self.h, BC[model], xn, yn, zn, x, y, z))
+
+    def set_boundary_velocity(self, box, u):
+        self._ck(self.lib.plb_b200_set_boundary_velocity(self.h, _box(box), _vec(u)))
+
+    def set_boundary_density(self, box, rho):
+        self._ck(self.lib.plb_b200_set_boundary_density(self.h, _box(box), rho))
+
+    def initialize_at_equilibrium(self, box, rho, u):
+        self._ck(self.lib.plb_b200_initialize_at_equilibrium(self.h, _box(box), rho, _vec(u)))
+
+    def initialize_at_equilibrium_field(self, box, rho_u):
+        rho_u = np.ascontiguousarray(rho_u, dtype=np.float64)
+        self._ck(self.lib.plb_b200_initialize_at_equilibrium_field(self.h, _box(box), rho_u.ctypes.data_as(ctypes.c_void_p)))
+
+    def initialize(self):
+        self._ck(self.lib.plb_b200_initialize(self.h))
+
+    def local_cells(self, box=None):
+        n = self.lib.plb_b200_local_bytes(self.h, _box(box or self.box))
+        return n // (self.q * np.dtype(self.dtype).itemsize)
+
+    def upload(self, pops, box=None):
+        """pops: the cells of `box` this rank owns, [cells..., q] in x,y,z order (wire format)."""
+        pops = np.ascontiguousarray(pops, dtype=self.dtype)
+        self._ck(self.lib.plb_b200_upload(self.h, _box(box or self.box), pops.ctypes.data_as(ctypes.c_void_p), pops.nbytes))
+
+    def upload_ptr(self, ptr, nbytes, box=None):
+        self._ck(self.lib.plb_b200_upload(self.h, _box(box or self.box), ctypes.c_void_p(ptr), nbytes))
+
+    def download_ptr(self, ptr, nbytes, box=None):
+        self._ck(self.lib.plb_b200_download(self.h, _box(box or self.box), ctypes.c_void_p(ptr), nbytes))
+
+    def download(self, box=None):
+        box = box or self.box
+        if self.n_ranks == 1:
+            shape = (box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1, self.q)
+        else:
+            shape = (self.local_cells(box), self.q)
+        out = np.empty(shape, dtype=self.dtype)
+        self._ck(self.lib.plb_b200_download(self.h, _box(box), out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
+        return out
+
+    def collide_and_stream(self, n=1):
+        self._ck(self.lib.plb_b200_collide_and_stream(self.h, int(n)))
+
+    def synchronize(self):
+        self._ck(self.lib.plb_b200_synchronize(self.h))
+
+    def stored_statistics(self):
+        out = (ctypes.c_double * 3)()
+        n = ctypes.c_uint64()
+        self._ck(self.lib.plb_b200_get_stored_statistics(self.h, out, ctypes.byref(n)))
+        return out[0], out[1], out[2], n.value
+
+    def compute_average_energy(self, box=None):
+        out = ctypes.c_double()
+        self._ck(self.lib.plb_b200_compute_average_energy(self.h, _box(box or self.box), ctypes.byref(out)))
+        return out.value
+
+    def compute_average_density(self, box=None):
+        out = ctypes.c_double()
+        self._ck(self.lib.plb_b200_compute_average_density(self.h, _box(box or self.box), ctypes.byref(out)))
+        return out.value
+
+    def compute_density_velocity(self, box=None):
+        box = box or self.box
+        if self.n_ranks == 1:
+            shape = (box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1, 4)
+        else:
+            shape = (self.local_cells(box), 4)
+        out = np.empty(shape, dtype=self.dtype)
+        self._ck(self.lib.plb_b200_compute_density_velocity(self.h, _box(box), out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
+        return out
+
+    def launch_count(self):
+        return int(self.lib.plb_b200_launch_count(self.h))
+
+    def device_bytes(self):
+        return int(self.lib.plb_b200_device_bytes(self.h))
+
+    def profile_sweeps(self, on):
+        self._ck(self.lib.plb_b200_profile_sweeps(self.h, int(bool(on))))
+
+    def profile_read(self):
+        ms, n = ctypes.c_double(), ctypes.c_int()
+        self._ck(self.lib.plb_b200_profile_read(self.h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def boundary_stages(self):
+        ns, ni = ctypes.c_int(), ctypes.c_int64()
+        self._ck(self.lib.plb_b200_boundary_stages(self.h, ctypes.byref(ns), ctypes.byref(ni)))
+        return ns.value, ni.value

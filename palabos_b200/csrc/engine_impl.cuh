@@ -1,0 +1,928 @@
+// palabos_b200/csrc/engine_impl.cuh -- LatticeImpl<T,Q>: the host side of the engine.
+//
+// Mirrors MultiBlockLattice3D (multiBlock/multiBlockLattice3D.hh) for the hot path only: it owns
+// the x-slabs of this process (the reference's per-block BlockLattice3D, allocated
+// multiBlockLattice3D.hh:383-400), keeps the set-up state the reference keeps inside per-cell
+// Dynamics objects (a 1-byte dynamics index per cell + sparse boundary records), orders the level-0
+// data processors into concurrent stages, and sequences one time step as the reference does
+// (multiBlockLattice3D.hh:318-360): sweep -> envelope exchange -> processors -> statistics.
+// Citations are relative to /root/reference/src.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+#include "engine.h"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+namespace plb200 {
+
+struct Proc {           ///< one data processor added by the boundary-condition set-up
+    int cls;
+    int box[6];
+    int a, b, c;
+};
+
+template <class T, int Q>
+class LatticeImpl : public LatticeBase {
+    using L = LB<T, Q>;
+
+    struct BcRec { int cell; Bc<T> b; bool alive; };
+    struct Group { int box[6]; int first, count; };   ///< records appended by one add_*_boundary call
+
+    struct Slab {
+        int g = 0;                 ///< global slab index
+        int gx0 = 0, nxl = 0;      ///< owned global planes [gx0, gx0+nxl)
+        long long cellsStore = 0;  ///< (nxl+2)*P
+        T* F = nullptr;
+        uint8_t* dKind = nullptr;
+        int* dBcIdx = nullptr;
+        Bc<T>* dBcs = nullptr; size_t dBcsCap = 0;
+        Item* dItems = nullptr; size_t dItemsCap = 0;
+        double* dPartials = nullptr; int partialsCap = 0;
+        double* dStats = nullptr;          ///< [4]
+        unsigned int* dTicket = nullptr;
+        std::vector<uint8_t> hKind;
+        std::vector<BcRec> recs;
+        std::vector<Group> groups;
+        std::unordered_map<int, int> cellToRec;
+        std::vector<int> stageOffsets;     ///< items of stage s are [stageOffsets[s], stageOffsets[s+1])
+        size_t nItems = 0;
+        bool dirtyKind = true, dirtyBcIndex = true, dirtySched = true;
+        int bcDirtyLo = 0, bcDirtyHi = 0;  ///< record range whose values must be re-uploaded
+    };
+
+    CreateDesc desc_;
+    int nx_, ny_, nz_, P_;
+    int per_[3] = {0, 0, 0};
+    int G_;                                  ///< total number of slabs over all ranks
+    std::vector<Slab> slabs_;
+    std::vector<Dyn<T>> dyns_;
+    std::vector<T> dynCs_;                   ///< cSmago of each entry (identity of a Smagorinsky entry)
+    Dyn<T>* dDyns_ = nullptr;
+    bool dirtyDyns_ = true;
+    std::vector<Proc> procs_;
+    bool swapped_ = false;
+    bool statsOn_ = true;
+    bool anySetup_ = false;
+    bool stepped_ = false;
+    cudaStream_t stream_ = 0;
+    uint64_t launches_ = 0;
+    size_t devBytes_ = 0;
+    int numSMs_ = 0;
+    void* dStage_ = nullptr; size_t stageCap_ = 0;
+    double* dReduce_ = nullptr;              ///< small device scratch for cross-rank reductions
+    ncclComm_t comm_ = nullptr;
+    int sweepOcc_[5][2][2];                  ///< cached occupancy per (MAIN, GENERIC, ODD)
+    bool profiling_ = false;                 ///< CUDA events around every sweep launch (bench.py's roofline leg)
+    std::vector<cudaEvent_t> profEvents_;    ///< pairs (before, after)
+    size_t profUsed_ = 0;
+
+    static constexpr size_t STAGE_BYTES = size_t(256) << 20;
+
+public:
+    explicit LatticeImpl(const CreateDesc& d) : desc_(d), nx_(d.nx), ny_(d.ny), nz_(d.nz), P_(d.ny * d.nz) {
+        std::memset(sweepOcc_, 0, sizeof sweepOcc_);
+        int dev = 0, nDev = 0;
+        if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+            throw PlbError("no CUDA device: libplb_b200 has no CPU fallback");
+        PLB_CUDA(cudaGetDevice(&dev));
+        PLB_CUDA(cudaDeviceGetAttribute(&numSMs_, cudaDevAttrMultiProcessorCount, dev));
+        if (d.nRanks < 1 || d.slabsPerRank < 1 || d.rank < 0 || d.rank >= d.nRanks) throw PlbError("bad rank / slab counts");
+        G_ = d.nRanks * d.slabsPerRank;
+        if (G_ > nx_) throw PlbError("more slabs than x-planes");
+        if ((long long)ny_ * nz_ >= (1ll << 30)) throw PlbError("y-z plane too large");
+        add_dyn(d.dynamics, d.p1, d.p2);     // entry 0: the background dynamics
+        for (int s = 0; s < d.slabsPerRank; ++s) {
+            Slab sl;
+            sl.g = d.rank * d.slabsPerRank + s;
+            int x0, x1;
+            slab_range(nx_, G_, sl.g, x0, x1);
+            sl.gx0 = x0; sl.nxl = x1 - x0 + 1;
+            sl.cellsStore = (long long)(sl.nxl + 2) * P_;
+            if (sl.cellsStore >= (1ll << 31)) throw PlbError("slab exceeds 2^31 cells: use more slabs");
+            slabs_.push_back(std::move(sl));
+        }
+        for (Slab& sl : slabs_) {
+            const size_t nF = (size_t)Q * sl.cellsStore;
+            sl.F = (T*)dev_alloc(nF * sizeof(T));
+            PLB_CUDA(cudaMemsetAsync(sl.F, 0, nF * sizeof(T), stream_));
+            sl.dKind = (uint8_t*)dev_alloc(sl.cellsStore);
+            sl.dBcIdx = (int*)dev_alloc(sl.cellsStore * sizeof(int));
+            sl.dStats = (double*)dev_alloc(4 * sizeof(double));
+            sl.dTicket = (unsigned int*)dev_alloc(sizeof(unsigned int));
+            PLB_CUDA(cudaMemsetAsync(sl.dTicket, 0, sizeof(unsigned int), stream_));
+            sl.hKind.assign((size_t)sl.cellsStore, 0);
+        }
+        dDyns_ = (Dyn<T>*)dev_alloc(256 * sizeof(Dyn<T>));
+        dReduce_ = (double*)dev_alloc(8 * sizeof(double));
+    }
+
+    ~LatticeImpl() override {
+        cudaStreamSynchronize(stream_);
+        for (Slab& sl : slabs_) {
+            cudaFree(sl.F); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems);
+            cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket);
+        }
+        cudaFree(dDyns_); cudaFree(dStage_); cudaFree(dReduce_);
+        if (comm_) NcclApi::get().CommDestroy(comm_);
+        for (cudaEvent_t e : profEvents_) cudaEventDestroy(e);
+    }
+
+    // ------------------------------------------------------------------------------ plumbing
+
+    void comm_init(const char id[128]) override {
+        if (desc_.nRanks == 1) return;
+        NcclApi& n = NcclApi::get();
+        ncclUniqueId uid;
+        static_assert(sizeof(uid) == 128, "ncclUniqueId is 128 bytes");
+        std::memcpy(&uid, id, 128);
+        n.check(n.CommInitRank(&comm_, desc_.nRanks, uid, desc_.rank), "ncclCommInitRank");
+    }
+    void set_stream(cudaStream_t s) override { PLB_CUDA(cudaStreamSynchronize(stream_)); stream_ = s; }
+    void synchronize() override { PLB_CUDA(cudaStreamSynchronize(stream_)); }
+    uint64_t launch_count() const override { return launches_; }
+    size_t device_bytes() const override { return devBytes_; }
+    void toggle_statistics(bool on) override { statsOn_ = on; }
+
+    void profile_sweeps(bool on) override { profiling_ = on; profUsed_ = 0; }
+    void profile_read(double* totalMs, int* nLaunches) override {
+        PLB_CUDA(cudaStreamSynchronize(stream_));
+        double ms = 0.;
+        for (size_t k = 0; k + 1 < profUsed_; k += 2) {
+            float t = 0.f;
+            PLB_CUDA(cudaEventElapsedTime(&t, profEvents_[k], profEvents_[k + 1]));
+            ms += t;
+        }
+        if (totalMs) *totalMs = ms;
+        if (nLaunches) *nLaunches = (int)(profUsed_ / 2);
+    }
+
+    void set_periodicity(int px, int py, int pz) override {
+        if (G_ > 1 && (px != 0) != (per_[0] != 0) && anySetup_)
+            throw PlbError("decomposed lattice: toggle x-periodicity before defining dynamics or boundaries");
+        per_[0] = px != 0; per_[1] = py != 0; per_[2] = pz != 0;
+        for (Slab& sl : slabs_) sl.dirtySched = true;
+    }
+
+    // -------------------------------------------------------------------------------- set-up
+
+    void define_dynamics_box(const int box[6], int dynamics, double p1, double p2) override {
+        check_box(box);
+        const int idx = add_dyn(dynamics, p1, p2);
+        anySetup_ = true;
+        for (Slab& sl : slabs_) {
+            bool touched = false;
+            for (int X = 0; X <= sl.nxl + 1; ++X) {
+                const int gx = global_x(sl, X);
+                if (gx < box[0] || gx > box[1]) continue;
+                touched = true;
+                for (int y = box[2]; y <= box[3]; ++y)
+                    std::memset(&sl.hKind[((size_t)X * ny_ + y) * nz_ + box[4]], idx, (size_t)(box[5] - box[4] + 1));
+            }
+            if (!touched) continue;
+            sl.dirtyKind = sl.dirtySched = true;
+            // defineDynamics replaces the whole dynamics object: a boundary composite on the cell goes away
+            for (size_t r = 0; r < sl.recs.size(); ++r) {
+                BcRec& rec = sl.recs[r];
+                if (!rec.alive) continue;
+                int gx, y, z;
+                decode(sl, rec.cell, gx, y, z);
+                if (in_box(box, gx, y, z)) { rec.alive = false; sl.cellToRec.erase(rec.cell); sl.dirtyBcIndex = true; }
+            }
+        }
+    }
+
+    void define_dynamics_mask(const int32_t* mask, int flag, int dynamics, double p1, double p2) override {
+        if (!mask) throw PlbError("null mask");
+        const int idx = add_dyn(dynamics, p1, p2);
+        anySetup_ = true;
+        for (Slab& sl : slabs_) {
+            for (int X = 0; X <= sl.nxl + 1; ++X) {
+                const int gx = global_x(sl, X);
+                if (gx < 0) continue;
+                const int32_t* m = mask + (size_t)gx * P_;
+                uint8_t* k = &sl.hKind[(size_t)X * P_];
+                for (int r = 0; r < P_; ++r) {
+                    if (m[r] != flag) continue;
+                    k[r] = (uint8_t)idx;
+                    if (!sl.cellToRec.empty()) {
+                        auto it = sl.cellToRec.find(X * P_ + r);
+                        if (it != sl.cellToRec.end()) { sl.recs[it->second].alive = false; sl.cellToRec.erase(it); sl.dirtyBcIndex = true; }
+                    }
+                }
+            }
+            sl.dirtyKind = sl.dirtySched = true;
+        }
+    }
+
+    /// BoundaryConditionInstantiator3D::addVelocityBoundary boundaryInstantiator3D.h:1016-1070 with the
+    /// Wrapped{Regularized,ZouHe}BoundaryManager3D (boundaryCondition3D.hh:825-840, zouHeBoundary3D.hh):
+    /// composite dynamics on the cells, then WrappedLocalBoundaryFunctional3D at level 0 (dirichlet only).
+    void add_velocity_boundary(int model, int dir, int ori, const int box[6]) override {
+        check_box(box);
+        check_dir_ori(dir, ori);
+        add_bc(model == 1 ? BC_VEL_ZH : BC_VEL_REG, dir, ori, box);
+        add_proc(PROC_PLANE, box, 0, 0, 0);
+    }
+    void add_pressure_boundary(int model, int dir, int ori, const int box[6]) override {
+        check_box(box);
+        check_dir_ori(dir, ori);
+        add_bc(model == 1 ? BC_RHO_ZH : BC_RHO_REG, dir, ori, box);
+        add_proc(PROC_PLANE, box, 0, 0, 0);
+    }
+    /// addExternalVelocityEdge / Corner: StoreVelocityDynamics + Outer{Edge,Corner}Functional3D
+    /// (boundaryCondition3D.hh:861-877, :899-915; the Zou-He manager does the same)
+    void add_external_velocity_edge(int, int plane, int n1, int n2, const int box[6]) override {
+        check_box(box);
+        if (plane < 0 || plane > 2 || (n1 != 1 && n1 != -1) || (n2 != 1 && n2 != -1)) throw PlbError("bad edge plane/normals");
+        add_bc(BC_STORE_VEL, 0, 0, box);
+        add_proc(PROC_EDGE, box, plane, n1, n2);
+    }
+    void add_external_velocity_corner(int, int xn, int yn, int zn, int x, int y, int z) override {
+        const int box[6] = {x, x, y, y, z, z};
+        check_box(box);
+        if ((xn != 1 && xn != -1) || (yn != 1 && yn != -1) || (zn != 1 && zn != -1)) throw PlbError("bad corner normals");
+        add_bc(BC_STORE_VEL, 0, 0, box);
+        add_proc(PROC_CORNER, box, xn, yn, zn);
+    }
+
+    /// OnLatticeBoundaryCondition3D::setVelocityConditionOnBlockBoundaries boundaryCondition3D.hh:64-162
+    /// with BlockSurface3D(block, 1) (core/blockSurface3D.cpp:38-200): 6 faces, 12 edges, 8 corners, in that order.
+    void set_velocity_condition_on_block_boundaries(int model, const int d[6], const int app[6]) override {
+        check_box(d);
+        const int x0 = d[0], x1 = d[1], y0 = d[2], y1 = d[3], z0 = d[4], z1 = d[5];
+        const int faces[6][8] = {
+            {0, -1, x0, x0, y0 + 1, y1 - 1, z0 + 1, z1 - 1}, {0, +1, x1, x1, y0 + 1, y1 - 1, z0 + 1, z1 - 1},
+            {1, -1, x0 + 1, x1 - 1, y0, y0, z0 + 1, z1 - 1}, {1, +1, x0 + 1, x1 - 1, y1, y1, z0 + 1, z1 - 1},
+            {2, -1, x0 + 1, x1 - 1, y0 + 1, y1 - 1, z0, z0}, {2, +1, x0 + 1, x1 - 1, y0 + 1, y1 - 1, z1, z1}};
+        const int edges[12][9] = {
+            {0, -1, -1, x0 + 1, x1 - 1, y0, y0, z0, z0}, {0, -1, +1, x0 + 1, x1 - 1, y0, y0, z1, z1},
+            {0, +1, -1, x0 + 1, x1 - 1, y1, y1, z0, z0}, {0, +1, +1, x0 + 1, x1 - 1, y1, y1, z1, z1},
+            {1, -1, -1, x0, x0, y0 + 1, y1 - 1, z0, z0}, {1, -1, +1, x1, x1, y0 + 1, y1 - 1, z0, z0},
+            {1, +1, -1, x0, x0, y0 + 1, y1 - 1, z1, z1}, {1, +1, +1, x1, x1, y0 + 1, y1 - 1, z1, z1},
+            {2, -1, -1, x0, x0, y0, y0, z0 + 1, z1 - 1}, {2, -1, +1, x0, x0, y1, y1, z0 + 1, z1 - 1},
+            {2, +1, -1, x1, x1, y0, y0, z0 + 1, z1 - 1}, {2, +1, +1, x1, x1, y1, y1, z0 + 1, z1 - 1}};
+        int in[6];
+        for (int k = 0; k < 6; ++k)
+            if (intersect(&faces[k][2], app, in)) add_velocity_boundary(model, faces[k][0], faces[k][1], in);
+        for (int k = 0; k < 12; ++k)
+            if (intersect(&edges[k][3], app, in)) add_external_velocity_edge(model, edges[k][0], edges[k][1], edges[k][2], in);
+        for (int k = 0; k < 8; ++k) {
+            const int xn = (k & 4) ? 1 : -1, yn = (k & 2) ? 1 : -1, zn = (k & 1) ? 1 : -1;
+            const int cb[6] = {xn < 0 ? x0 : x1, xn < 0 ? x0 : x1, yn < 0 ? y0 : y1, yn < 0 ? y0 : y1,
+                               zn < 0 ? z0 : z1, zn < 0 ? z0 : z1};
+            if (intersect(cb, app, in)) add_external_velocity_corner(model, xn, yn, zn, in[0], in[2], in[4]);
+        }
+    }
+
+    /// setBoundaryVelocity dataInitializerFunctional3D.hh:830-845 -> Cell::defineVelocity: only the
+    /// StoreVelocity-type dynamics keep it (boundaryDynamics.hh:333-339); no-op elsewhere.
+    void set_boundary_velocity(const int box[6], const double u[3]) override {
+        check_box(box);
+        const T v[3] = {(T)u[0], (T)u[1], (T)u[2]};
+        for_records_in(box, [&](Bc<T>& b) {
+            if (L::is_rho_plane(b.kind)) return false;
+            b.u[0] = v[0]; b.u[1] = v[1]; b.u[2] = v[2];
+            return true;
+        });
+    }
+    /// setBoundaryDensity -> StoreDensityDynamics::defineDensity boundaryDynamics.hh:239-243
+    void set_boundary_density(const int box[6], double rho) override {
+        check_box(box);
+        const T rb = (T)rho - (T)1;
+        for_records_in(box, [&](Bc<T>& b) {
+            if (!L::is_rho_plane(b.kind)) return false;
+            b.rhoBar = rb;
+            return true;
+        });
+    }
+
+    void initialize_at_equilibrium(const int box[6], double rho, const double u[3]) override {
+        check_box(box);
+        sync_setup();
+        for (Slab& sl : slabs_) {
+            BoxL b;
+            if (!local_box(sl, box, b)) continue;
+            const long long n = b.cells();
+            init_equilibrium_kernel<T, Q><<<(unsigned)((n + 255) / 256), 256, 0, stream_>>>(
+                ctx(sl), sl.F, b, (T)rho, (T)u[0], (T)u[1], (T)u[2], nullptr);
+            launched();
+        }
+    }
+
+    void initialize_at_equilibrium_field(const int box[6], const double* ru) override {
+        check_box(box);
+        if (!ru) throw PlbError("null field");
+        sync_setup();
+        const long long rowCells = (long long)(box[3] - box[2] + 1) * (box[5] - box[4] + 1);
+        for (Slab& sl : slabs_) {
+            BoxL b;
+            if (!local_box(sl, box, b)) continue;
+            const size_t planeBytes = (size_t)rowCells * 4 * sizeof(double);
+            const int planesPerChunk = (int)std::max<size_t>(1, STAGE_BYTES / planeBytes);
+            for (int X = b.X0; X <= b.X1; X += planesPerChunk) {
+                BoxL cb = b;
+                cb.X0 = X; cb.X1 = std::min(b.X1, X + planesPerChunk - 1);
+                const size_t bytes = (size_t)cb.cells() * 4 * sizeof(double);
+                double* st = (double*)stage(bytes);
+                const long long firstCell = (long long)(global_x(sl, cb.X0) - box[0]) * rowCells;
+                PLB_CUDA(cudaMemcpyAsync(st, ru + 4 * firstCell, bytes, cudaMemcpyHostToDevice, stream_));
+                init_equilibrium_kernel<T, Q><<<(unsigned)((cb.cells() + 255) / 256), 256, 0, stream_>>>(
+                    ctx(sl), sl.F, cb, (T)0, (T)0, (T)0, (T)0, st);
+                launched();
+                PLB_CUDA(cudaStreamSynchronize(stream_));   // the staging buffer is reused
+            }
+        }
+    }
+
+    /// lattice.initialize(): MultiBlock3D::initialize -> executeInternalProcessors (multiBlock/multiBlock3D.cpp:486-510)
+    void initialize() override {
+        sync_setup();
+        run_processors();
+    }
+
+    // ---------------------------------------------------------------------------- data in/out
+
+    size_t local_bytes(const int box[6]) override {
+        check_box(box);
+        size_t n = 0;
+        for (Slab& sl : slabs_) { BoxL b; if (local_box(sl, box, b)) n += (size_t)b.cells(); }
+        return n * Q * sizeof(T);
+    }
+
+    void upload(const int box[6], const void* data, size_t bytes) override { transfer(box, const_cast<void*>(data), bytes, true); }
+    void download(const int box[6], void* data, size_t bytes) override { transfer(box, data, bytes, false); }
+
+    void density_velocity(const int box[6], void* out, size_t bytes) override {
+        check_box(box);
+        if (bytes != local_bytes(box) / Q * 4) throw PlbError("buffer size does not match the box");
+        sync_setup();
+        char* host = (char*)out;
+        for (Slab& sl : slabs_) {
+            BoxL b;
+            if (!local_box(sl, box, b)) continue;
+            const size_t planeBytes = (size_t)b.ny() * b.nz() * 4 * sizeof(T);
+            const int planesPerChunk = (int)std::max<size_t>(1, STAGE_BYTES / planeBytes);
+            for (int X = b.X0; X <= b.X1; X += planesPerChunk) {
+                BoxL cb = b;
+                cb.X0 = X; cb.X1 = std::min(b.X1, X + planesPerChunk - 1);
+                const size_t nb = (size_t)cb.cells() * 4 * sizeof(T);
+                T* st = (T*)stage(nb);
+                density_velocity_kernel<T, Q><<<(unsigned)((cb.cells() + 127) / 128), 128, 0, stream_>>>(ctx(sl), cb, st);
+                launched();
+                PLB_CUDA(cudaMemcpyAsync(host, st, nb, cudaMemcpyDeviceToHost, stream_));
+                PLB_CUDA(cudaStreamSynchronize(stream_));
+                host += nb;
+            }
+        }
+    }
+
+    // --------------------------------------------------------------------------- the hot path
+
+    /// n x MultiBlockLattice3D::collideAndStream() (multiBlock/multiBlockLattice3D.hh:318-360)
+    void collide_and_stream(int n) override {
+        if (n < 0) throw PlbError("negative step count");
+        if (desc_.nRanks > 1 && !comm_) throw PlbError("plb_b200_comm_init must be called before stepping a multi-rank lattice");
+        sync_setup();
+        for (int s = 0; s < n; ++s) {
+            for (Slab& sl : slabs_) launch_sweep(sl);
+            swapped_ = !swapped_;
+            exchange();
+            run_processors();
+            stepped_ = true;
+        }
+    }
+
+    /// BlockStatistics::evaluate core/blockStatistics.cpp:77-120 + CombinedStatistics::combine
+    /// multiBlock/combinedStatistics.cpp:108-133 (+ ParallelCombinedStatistics over ranks,
+    /// parallelism/parallelStatistics.cpp:41-83).
+    void stored_statistics(double out3[3], uint64_t* nCells) override {
+        double sum[3] = {0., 0., 0.}, mx = -DBL_MAX;
+        if (stepped_ && statsOn_) {
+            PLB_CUDA(cudaStreamSynchronize(stream_));
+            for (Slab& sl : slabs_) {
+                double h[4];
+                PLB_CUDA(cudaMemcpy(h, sl.dStats, sizeof h, cudaMemcpyDeviceToHost));
+                sum[0] += h[0]; sum[1] += h[1]; sum[2] += h[3];
+                mx = std::max(mx, h[2]);
+            }
+        }
+        if (desc_.nRanks > 1) {
+            all_reduce(sum, 3, false);
+            all_reduce(&mx, 1, true);
+        }
+        if (sum[2] == 0.) { out3[0] = 0.; out3[1] = 0.; }
+        else { out3[0] = sum[0] / sum[2]; out3[1] = sum[1] / sum[2]; }
+        out3[2] = mx;
+        if (nCells) *nCells = (uint64_t)sum[2];
+    }
+
+    /// computeAverageEnergy dataAnalysisWrapper3D.hh:1252-1257 (+ BoxSumEnergyFunctional3D)
+    double average_energy(const int box[6]) override {
+        const double sum = box_sum(box, 0);
+        const long long n = box_cells(box);
+        const T sumEnergy = (T)(sum / (T)2);
+        return (double)(sumEnergy / (T)n);
+    }
+    /// computeAverageDensity dataAnalysisWrapper3D.hh:1226-1230 (+ BoxSumRhoBarFunctional3D)
+    double average_density(const int box[6]) override {
+        const double sum = box_sum(box, 1);
+        const long long n = box_cells(box);
+        const T s = (T)sum;
+        return (double)L::fullRho(s / (T)n);
+    }
+
+    void boundary_stages(int* nStages, int64_t* nItems) override {
+        sync_setup();
+        int st = 0; int64_t it = 0;
+        for (Slab& sl : slabs_) { st = std::max(st, (int)sl.stageOffsets.size() - 1); it += (int64_t)sl.nItems; }
+        if (nStages) *nStages = st;
+        if (nItems) *nItems = it;
+    }
+
+private:
+    // -------------------------------------------------------------------------------- helpers
+
+    void* dev_alloc(size_t bytes) {
+        void* p = nullptr;
+        PLB_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        devBytes_ += bytes;
+        return p;
+    }
+    void launched() {
+        ++launches_;
+        PLB_CUDA(cudaGetLastError());
+    }
+    void* stage(size_t bytes) {
+        if (bytes > stageCap_) {
+            PLB_CUDA(cudaStreamSynchronize(stream_));
+            if (dStage_) { cudaFree(dStage_); devBytes_ -= stageCap_; }
+            dStage_ = dev_alloc(bytes);
+            stageCap_ = bytes;
+        }
+        return dStage_;
+    }
+
+    void check_box(const int b[6]) const {
+        if (!(b[0] >= 0 && b[1] < nx_ && b[2] >= 0 && b[3] < ny_ && b[4] >= 0 && b[5] < nz_ &&
+              b[0] <= b[1] && b[2] <= b[3] && b[4] <= b[5]))
+            throw PlbError("box outside the lattice");
+    }
+    static void check_dir_ori(int dir, int ori) {
+        if (dir < 0 || dir > 2 || (ori != 1 && ori != -1)) throw PlbError("bad direction/orientation");
+    }
+    static bool in_box(const int b[6], int x, int y, int z) {
+        return x >= b[0] && x <= b[1] && y >= b[2] && y <= b[3] && z >= b[4] && z <= b[5];
+    }
+    static long long box_cells(const int b[6]) {
+        return (long long)(b[1] - b[0] + 1) * (b[3] - b[2] + 1) * (b[5] - b[4] + 1);
+    }
+    static bool intersect(const int a[6], const int b[6], int out[6]) {
+        for (int k = 0; k < 3; ++k) {
+            out[2 * k] = std::max(a[2 * k], b[2 * k]);
+            out[2 * k + 1] = std::min(a[2 * k + 1], b[2 * k + 1]);
+            if (out[2 * k] > out[2 * k + 1]) return false;
+        }
+        return true;
+    }
+
+    /// global x of storage plane X of a slab (ghost planes wrap in a periodic lattice), or -1
+    int global_x(const Slab& sl, int X) const {
+        int gx = sl.gx0 - 1 + X;
+        if (gx < 0 || gx >= nx_) {
+            if (!per_[0] || G_ == 1) return -1;     // one slab wraps in the kernel: its ghost planes are unused
+            gx = (gx + nx_) % nx_;
+        }
+        return gx;
+    }
+    void decode(const Slab& sl, int cell, int& gx, int& y, int& z) const {
+        const int X = cell / P_;
+        const int r = cell - X * P_;
+        y = r / nz_; z = r - y * nz_;
+        gx = global_x(sl, X);
+    }
+    /// owned part of a global box in storage coordinates
+    bool local_box(const Slab& sl, const int box[6], BoxL& b) const {
+        const int x0 = std::max(box[0], sl.gx0), x1 = std::min(box[1], sl.gx0 + sl.nxl - 1);
+        if (x0 > x1) return false;
+        b.X0 = x0 - sl.gx0 + 1; b.X1 = x1 - sl.gx0 + 1;
+        b.y0 = box[2]; b.y1 = box[3]; b.z0 = box[4]; b.z1 = box[5];
+        return true;
+    }
+
+    Geo geo(const Slab& sl) const {
+        Geo g;
+        g.nxl = sl.nxl; g.ny = ny_; g.nz = nz_; g.P = P_; g.S = sl.cellsStore;
+        g.perY = per_[1]; g.perZ = per_[2];
+        g.lowMode = sl.g > 0 ? XMODE_GHOST : (per_[0] ? (G_ == 1 ? XMODE_WRAP : XMODE_GHOST) : XMODE_EDGE);
+        g.highMode = sl.g < G_ - 1 ? XMODE_GHOST : (per_[0] ? (G_ == 1 ? XMODE_WRAP : XMODE_GHOST) : XMODE_EDGE);
+        return g;
+    }
+    CellCtx<T> ctx(const Slab& sl) const {
+        CellCtx<T> c;
+        c.F = sl.F; c.kind = sl.dKind; c.bcIdx = sl.dBcIdx; c.dyns = dDyns_; c.bcs = sl.dBcs;
+        c.g = geo(sl); c.swapped = swapped_;
+        return c;
+    }
+
+    int add_dyn(int type, double p1, double p2) {
+        if (type < DYN_BGK || type > DYN_NODYNAMICS) throw PlbError("unknown dynamics id");
+        Dyn<T> d;
+        std::memset(&d, 0, sizeof d);
+        d.type = type;
+        T cs = (T)0;
+        if (type == DYN_BOUNCEBACK || type == DYN_NODYNAMICS) d.rho = (T)p1;
+        else d.omega = (T)p1;
+        if (type == DYN_SMAGO) { cs = (T)p2; d.preFactor = L::smago_prefactor(d.omega, cs); }
+        for (size_t k = 0; k < dyns_.size(); ++k)
+            if (std::memcmp(&dyns_[k], &d, sizeof d) == 0 && dynCs_[k] == cs) return (int)k;
+        if (dyns_.size() >= 256) throw PlbError("too many distinct dynamics (256)");
+        dyns_.push_back(d);
+        dynCs_.push_back(cs);
+        dirtyDyns_ = true;
+        for (Slab& sl : slabs_) sl.dirtySched = true;
+        return (int)dyns_.size() - 1;
+    }
+
+    void add_bc(int kind, int dir, int ori, const int box[6]) {
+        anySetup_ = true;
+        for (Slab& sl : slabs_) {
+            Group grp;
+            std::memcpy(grp.box, box, sizeof grp.box);
+            grp.first = (int)sl.recs.size();
+            for (int X = 0; X <= sl.nxl + 1; ++X) {
+                const int gx = global_x(sl, X);
+                if (gx < box[0] || gx > box[1]) continue;
+                for (int y = box[2]; y <= box[3]; ++y)
+                    for (int z = box[4]; z <= box[5]; ++z) {
+                        const int cell = (X * ny_ + y) * nz_ + z;
+                        if (sl.cellToRec.count(cell)) throw PlbError("cell already carries a boundary dynamics");
+                        BcRec rec;
+                        rec.cell = cell; rec.alive = true;
+                        std::memset(&rec.b, 0, sizeof rec.b);
+                        rec.b.kind = kind; rec.b.dir = dir; rec.b.ori = ori;
+                        rec.b.rhoBar = L::rhoBarOf((T)1);          // StoreDensityDynamics ctor boundaryDynamics.hh:200-205
+                        sl.cellToRec.emplace(cell, (int)sl.recs.size());
+                        sl.recs.push_back(rec);
+                    }
+            }
+            grp.count = (int)sl.recs.size() - grp.first;
+            if (grp.count) { sl.groups.push_back(grp); sl.dirtyBcIndex = sl.dirtySched = true; }
+        }
+    }
+    void add_proc(int cls, const int box[6], int a, int b, int c) {
+        Proc p;
+        p.cls = cls; std::memcpy(p.box, box, sizeof p.box); p.a = a; p.b = b; p.c = c;
+        procs_.push_back(p);
+        for (Slab& sl : slabs_) sl.dirtySched = true;
+    }
+
+    template <class Fn>
+    void for_records_in(const int box[6], Fn fn) {
+        for (Slab& sl : slabs_)
+            for (const Group& grp : sl.groups) {
+                int tmp[6];
+                if (!intersect(grp.box, box, tmp)) continue;
+                for (int r = grp.first; r < grp.first + grp.count; ++r) {
+                    BcRec& rec = sl.recs[r];
+                    if (!rec.alive) continue;
+                    int gx, y, z;
+                    decode(sl, rec.cell, gx, y, z);
+                    if (!in_box(box, gx, y, z)) continue;
+                    if (fn(rec.b)) {
+                        if (sl.bcDirtyLo == sl.bcDirtyHi) { sl.bcDirtyLo = r; sl.bcDirtyHi = r + 1; }
+                        else { sl.bcDirtyLo = std::min(sl.bcDirtyLo, r); sl.bcDirtyHi = std::max(sl.bcDirtyHi, r + 1); }
+                    }
+                }
+            }
+    }
+
+    // ------------------------------------------------------------ set-up state -> device
+
+    struct View { int dynType; bool hasBc; int bcKind; };
+    View view(const Slab& sl, int cell) const {
+        View v;
+        v.dynType = dyns_[sl.hKind[cell]].type;
+        auto it = sl.cellToRec.find(cell);
+        v.hasBc = it != sl.cellToRec.end();
+        v.bcKind = v.hasBc ? sl.recs[it->second].b.kind : -1;
+        return v;
+    }
+
+    /// Order the level-0 processors of a slab into stages.  The reference runs them sequentially, in
+    /// insertion order, each over its box in x,y,z order (atomicBlock/atomicBlock3D.cpp:195-222); an item
+    /// goes to the earliest stage that keeps every read-after-write, write-after-read and
+    /// write-after-write relation of that sequential order, so items of one stage are independent.
+    void build_schedule(Slab& sl) {
+        std::vector<Item> items;
+        std::vector<int> stageOf;
+        std::unordered_map<int, int> lastWrite, lastRead;
+        const int strideOf[3] = {P_, nz_, 1};
+        auto wr = [&](int cell) { auto it = lastWrite.find(cell); return it == lastWrite.end() ? -1 : it->second; };
+        auto rd = [&](int cell) { auto it = lastRead.find(cell); return it == lastRead.end() ? -1 : it->second; };
+        for (const Proc& p : procs_) {
+            BoxL b;
+            if (!local_box(sl, p.box, b)) continue;
+            for (int X = b.X0; X <= b.X1; ++X) for (int y = b.y0; y <= b.y1; ++y) for (int z = b.z0; z <= b.z1; ++z) {
+                const int cell = (X * ny_ + y) * nz_ + z;
+                int reads[8], nReads = 0;
+                const int pos[3] = {X, y, z};
+                auto neighbour = [&](int dir, int step) -> int {
+                    // neighbours along y / z must exist in the lattice; along x they may be ghost cells
+                    const int v = pos[dir] + step;
+                    if (dir == 0) { if (global_x(sl, v) < 0) throw PlbError("boundary processor reaches outside the lattice"); }
+                    else if (v < 0 || v >= (dir == 1 ? ny_ : nz_)) throw PlbError("boundary processor reaches outside the lattice");
+                    return cell + step * strideOf[dir];
+                };
+                auto need_pops = [&](int c2, bool density, bool velocity) {
+                    const View v = view(sl, c2);
+                    const bool need = (density && L::density_reads_pops(v.dynType, v.hasBc, v.bcKind))
+                                   || (velocity && L::velocity_reads_pops(v.dynType, v.hasBc, v.bcKind));
+                    if (!need) return;
+                    const int X2 = c2 / P_;
+                    if (X2 < 1 || X2 > sl.nxl)
+                        throw PlbError("a boundary edge/corner processor needs populations of a cell owned by another slab (unsupported decomposition)");
+                    reads[nReads++] = c2;
+                };
+                if (p.cls == PROC_PLANE) {
+                    if (!sl.cellToRec.count(cell)) continue;
+                } else if (p.cls == PROC_EDGE) {
+                    const int d1 = (p.a + 1) % 3, d2 = (p.a + 2) % 3;
+                    need_pops(neighbour(d1, -p.b), true, false);
+                    need_pops(neighbour(d2, -p.c), true, false);
+                    need_pops(neighbour(p.a, +1), false, true);
+                    need_pops(neighbour(p.a, -1), false, true);
+                    need_pops(neighbour(d1, -p.b), false, true);
+                    need_pops(neighbour(d2, -p.c), false, true);
+                    need_pops(cell, false, true);
+                } else {
+                    const int nrm[3] = {p.a, p.b, p.c};
+                    for (int d = 0; d < 3; ++d) need_pops(neighbour(d, -nrm[d]), true, true);
+                    need_pops(cell, false, true);
+                }
+                int st = std::max(wr(cell), rd(cell)) + 1;
+                for (int k = 0; k < nReads; ++k) st = std::max(st, wr(reads[k]) + 1);
+                for (int k = 0; k < nReads; ++k) { int& r = lastRead[reads[k]]; r = std::max(rd(reads[k]), st); }
+                lastWrite[cell] = st;
+                Item it;
+                it.cell = cell; it.cls = (signed char)p.cls; it.a = (signed char)p.a; it.b = (signed char)p.b; it.c = (signed char)p.c;
+                items.push_back(it);
+                stageOf.push_back(st);
+            }
+        }
+        int nStages = 0;
+        for (int s : stageOf) nStages = std::max(nStages, s + 1);
+        std::vector<int> count(nStages + 1, 0);
+        for (int s : stageOf) ++count[s + 1];
+        for (int s = 0; s < nStages; ++s) count[s + 1] += count[s];
+        sl.stageOffsets = count;
+        std::vector<Item> sorted(items.size());
+        std::vector<int> cursor(count.begin(), count.begin() + nStages);
+        for (size_t k = 0; k < items.size(); ++k) sorted[cursor[stageOf[k]]++] = items[k];
+        sl.nItems = sorted.size();
+        if (sl.nItems > sl.dItemsCap) {
+            if (sl.dItems) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dItems); devBytes_ -= sl.dItemsCap * sizeof(Item); }
+            sl.dItems = (Item*)dev_alloc(sl.nItems * sizeof(Item));
+            sl.dItemsCap = sl.nItems;
+        }
+        if (sl.nItems) {
+            PLB_CUDA(cudaMemcpyAsync(sl.dItems, sorted.data(), sl.nItems * sizeof(Item), cudaMemcpyHostToDevice, stream_));
+            PLB_CUDA(cudaStreamSynchronize(stream_));
+        }
+        if (sl.stageOffsets.empty()) sl.stageOffsets.push_back(0);
+    }
+
+    void sync_setup() {
+        if (dirtyDyns_) {
+            PLB_CUDA(cudaMemcpyAsync(dDyns_, dyns_.data(), dyns_.size() * sizeof(Dyn<T>), cudaMemcpyHostToDevice, stream_));
+            PLB_CUDA(cudaStreamSynchronize(stream_));
+            dirtyDyns_ = false;
+        }
+        for (Slab& sl : slabs_) {
+            if (sl.dirtyKind) {
+                PLB_CUDA(cudaMemcpyAsync(sl.dKind, sl.hKind.data(), (size_t)sl.cellsStore, cudaMemcpyHostToDevice, stream_));
+                PLB_CUDA(cudaStreamSynchronize(stream_));
+                sl.dirtyKind = false;
+            }
+            if (sl.dirtyBcIndex) {
+                // records keep their position (dead ones are simply not indexed)
+                const size_t n = sl.recs.size();
+                if (n > sl.dBcsCap) {
+                    if (sl.dBcs) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dBcs); devBytes_ -= sl.dBcsCap * sizeof(Bc<T>); }
+                    sl.dBcsCap = n + n / 2 + 16;
+                    sl.dBcs = (Bc<T>*)dev_alloc(sl.dBcsCap * sizeof(Bc<T>));
+                }
+                PLB_CUDA(cudaMemsetAsync(sl.dBcIdx, 0xFF, (size_t)sl.cellsStore * sizeof(int), stream_));
+                if (n) {
+                    std::vector<int> cells(n);
+                    std::vector<Bc<T>> vals(n);
+                    for (size_t r = 0; r < n; ++r) { cells[r] = sl.recs[r].alive ? sl.recs[r].cell : -1; vals[r] = sl.recs[r].b; }
+                    int* dCells = (int*)stage(n * sizeof(int));
+                    PLB_CUDA(cudaMemcpyAsync(dCells, cells.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+                    PLB_CUDA(cudaMemcpyAsync(sl.dBcs, vals.data(), n * sizeof(Bc<T>), cudaMemcpyHostToDevice, stream_));
+                    scatter_bc_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream_>>>(dCells, (int)n, sl.dBcIdx);
+                    launched();
+                    PLB_CUDA(cudaStreamSynchronize(stream_));
+                }
+                sl.dirtyBcIndex = false;
+                sl.bcDirtyLo = sl.bcDirtyHi = 0;
+            }
+            if (sl.bcDirtyHi > sl.bcDirtyLo) {
+                const int n = sl.bcDirtyHi - sl.bcDirtyLo;
+                std::vector<Bc<T>> vals(n);
+                for (int r = 0; r < n; ++r) vals[r] = sl.recs[sl.bcDirtyLo + r].b;
+                PLB_CUDA(cudaMemcpyAsync(sl.dBcs + sl.bcDirtyLo, vals.data(), n * sizeof(Bc<T>), cudaMemcpyHostToDevice, stream_));
+                PLB_CUDA(cudaStreamSynchronize(stream_));
+                sl.bcDirtyLo = sl.bcDirtyHi = 0;
+            }
+            if (sl.dirtySched) { build_schedule(sl); sl.dirtySched = false; }
+        }
+    }
+
+    // ------------------------------------------------------------------------------ the step
+
+    template <int MAIN, bool GEN, bool ODD>
+    void launch_sweep_as(Slab& sl, SweepArgs<T>& a, int mainIdx) {
+        auto kern = sweep_kernel<T, Q, MAIN, GEN, ODD>;
+        int& occ = sweepOcc_[mainIdx][GEN][ODD];
+        if (!occ) {
+            PLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SWEEP_THREADS, 0));
+            if (occ < 1) occ = 1;
+        }
+        const int nTiles = (a.cellEnd - a.cellBegin + SWEEP_THREADS - 1) / SWEEP_THREADS;
+        const int grid = std::max(1, std::min(nTiles, numSMs_ * occ));
+        if (grid > sl.partialsCap) {
+            if (sl.dPartials) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dPartials); devBytes_ -= (size_t)sl.partialsCap * 4 * sizeof(double); }
+            sl.partialsCap = std::max(grid, numSMs_ * 16);
+            sl.dPartials = (double*)dev_alloc((size_t)sl.partialsCap * 4 * sizeof(double));
+        }
+        a.partials = sl.dPartials;
+        const bool prof = profiling_ && profUsed_ < 2 * 8192;
+        if (prof) {
+            while (profEvents_.size() < profUsed_ + 2) { cudaEvent_t e; PLB_CUDA(cudaEventCreate(&e)); profEvents_.push_back(e); }
+            PLB_CUDA(cudaEventRecord(profEvents_[profUsed_], stream_));
+        }
+        kern<<<grid, SWEEP_THREADS, 0, stream_>>>(a);
+        launched();
+        if (prof) { PLB_CUDA(cudaEventRecord(profEvents_[profUsed_ + 1], stream_)); profUsed_ += 2; }
+    }
+
+    void launch_sweep(Slab& sl) {
+        SweepArgs<T> a;
+        a.F = sl.F; a.kind = sl.dKind; a.dyns = dDyns_; a.g = geo(sl);
+        a.cellBegin = P_; a.cellEnd = (sl.nxl + 1) * P_;
+        a.omega = dyns_[0].omega; a.preFactor = dyns_[0].preFactor;
+        a.gatherStats = statsOn_ ? 1 : 0;
+        a.partials = nullptr; a.ticket = sl.dTicket; a.statsOut = sl.dStats;
+        bool generic = L::is_inert(dyns_[0].type);
+        for (size_t k = 1; k < dyns_.size(); ++k) if (!L::is_inert(dyns_[k].type)) generic = true;
+        const bool odd = swapped_;
+        if (generic) {
+            if (odd) launch_sweep_as<DYN_BGK, true, true>(sl, a, 4); else launch_sweep_as<DYN_BGK, true, false>(sl, a, 4);
+            return;
+        }
+        switch (dyns_[0].type) {
+        case DYN_BGK:   if (odd) launch_sweep_as<DYN_BGK, false, true>(sl, a, 0);   else launch_sweep_as<DYN_BGK, false, false>(sl, a, 0); break;
+        case DYN_RLB:   if (odd) launch_sweep_as<DYN_RLB, false, true>(sl, a, 1);   else launch_sweep_as<DYN_RLB, false, false>(sl, a, 1); break;
+        case DYN_TRT:   if (odd) launch_sweep_as<DYN_TRT, false, true>(sl, a, 2);   else launch_sweep_as<DYN_TRT, false, false>(sl, a, 2); break;
+        default:        if (odd) launch_sweep_as<DYN_SMAGO, false, true>(sl, a, 3); else launch_sweep_as<DYN_SMAGO, false, false>(sl, a, 3); break;
+        }
+    }
+
+    void run_processors() {
+        for (Slab& sl : slabs_) {
+            const int nStages = (int)sl.stageOffsets.size() - 1;
+            for (int s = 0; s < nStages; ++s) {
+                const int first = sl.stageOffsets[s], n = sl.stageOffsets[s + 1] - first;
+                if (n <= 0) continue;
+                boundary_stage_kernel<T, Q><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
+                launched();
+            }
+        }
+    }
+
+    /// Envelope exchange (replaces BlockCommunicator3D::duplicateOverlaps, multiBlock/serialBlockCommunicator3D.cpp:44-95
+    /// and parallelism/parallelBlockCommunicator3D.cpp:251-297).  Only the populations that cross the slab
+    /// face travel -- those with c_x = -1 or c_x = +1 (5 of 19, 9 of 27) -- and each is one contiguous
+    /// y-z plane of one slot of the SoA storage, so nothing is packed.  Across the face between slab g
+    /// (below) and slab g+1 (above):
+    ///   after an even step (layout SWAPPED):  g's last plane, slots c_x=-1   -> low ghost plane of g+1
+    ///                                         g+1's first plane, slots c_x=+1 -> high ghost plane of g
+    ///   after an odd step (layout NORMAL):    high ghost of g, slots c_x=+1   -> first plane of g+1
+    ///                                         low ghost of g+1, slots c_x=-1  -> last plane of g
+    void exchange() {
+        if (G_ == 1) return;
+        const int nFaces = per_[0] ? G_ : G_ - 1;
+        const size_t planeBytes = (size_t)P_ * sizeof(T);
+        const bool remote = desc_.nRanks > 1;
+        NcclApi* n = remote ? &NcclApi::get() : nullptr;
+        if (remote) n->check(n->GroupStart(), "ncclGroupStart");
+        for (int face = 0; face < nFaces; ++face) {
+            const int gLo = face, gHi = (face + 1) % G_;
+            for (int part = 0; part < 2; ++part) {
+                // part 0 carries the slots with c_x = -1, part 1 those with c_x = +1
+                const int cxSel = part == 0 ? -1 : +1;
+                int srcG, dstG, srcPlane, dstPlane;     // plane: 0 low ghost, 1 first, 2 last, 3 high ghost
+                if (swapped_) {
+                    if (part == 0) { srcG = gLo; srcPlane = 2; dstG = gHi; dstPlane = 0; }
+                    else           { srcG = gHi; srcPlane = 1; dstG = gLo; dstPlane = 3; }
+                } else {
+                    if (part == 1) { srcG = gLo; srcPlane = 3; dstG = gHi; dstPlane = 1; }
+                    else           { srcG = gHi; srcPlane = 0; dstG = gLo; dstPlane = 2; }
+                }
+                Slab* src = find_slab(srcG);
+                Slab* dst = find_slab(dstG);
+                if (!src && !dst) continue;
+                for (int i = 1; i < Q; ++i) {
+                    if (c_of(i, 0) != cxSel) continue;
+                    T* sp = src ? plane_ptr(*src, i, srcPlane) : nullptr;
+                    T* dp = dst ? plane_ptr(*dst, i, dstPlane) : nullptr;
+                    if (src && dst) {
+                        PLB_CUDA(cudaMemcpyAsync(dp, sp, planeBytes, cudaMemcpyDeviceToDevice, stream_));
+                    } else if (src) {
+                        n->check(n->Send(sp, planeBytes, ncclInt8, dstG / desc_.slabsPerRank, comm_, stream_), "ncclSend");
+                    } else {
+                        n->check(n->Recv(dp, planeBytes, ncclInt8, srcG / desc_.slabsPerRank, comm_, stream_), "ncclRecv");
+                    }
+                }
+            }
+        }
+        if (remote) n->check(n->GroupEnd(), "ncclGroupEnd");
+    }
+
+    static int c_of(int i, int d) { return Q == 19 ? c19(i, d) : c27(i, d); }
+    Slab* find_slab(int g) {
+        for (Slab& sl : slabs_) if (sl.g == g) return &sl;
+        return nullptr;
+    }
+    T* plane_ptr(Slab& sl, int slot, int which) {
+        const int X = which == 0 ? 0 : (which == 1 ? 1 : (which == 2 ? sl.nxl : sl.nxl + 1));
+        return sl.F + (size_t)slot * sl.cellsStore + (size_t)X * P_;
+    }
+
+    void all_reduce(double* v, int n, bool isMax) {
+        NcclApi& nc = NcclApi::get();
+        if (!comm_) throw PlbError("plb_b200_comm_init has not been called");
+        PLB_CUDA(cudaMemcpyAsync(dReduce_, v, n * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        nc.check(nc.AllReduce(dReduce_, dReduce_, n, ncclDouble, isMax ? ncclMax : ncclSum, comm_, stream_), "ncclAllReduce");
+        PLB_CUDA(cudaMemcpyAsync(v, dReduce_, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        PLB_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    // ----------------------------------------------------------------------- transfer, analysis
+
+    void transfer(const int box[6], void* data, size_t bytes, bool up) {
+        check_box(box);
+        if (bytes != local_bytes(box)) throw PlbError("buffer size does not match the box");
+        if (!data && bytes) throw PlbError("null buffer");
+        sync_setup();
+        char* host = (char*)data;
+        for (Slab& sl : slabs_) {
+            BoxL b;
+            if (!local_box(sl, box, b)) continue;
+            const size_t planeBytes = (size_t)b.ny() * b.nz() * Q * sizeof(T);
+            const int planesPerChunk = (int)std::max<size_t>(1, STAGE_BYTES / planeBytes);
+            for (int X = b.X0; X <= b.X1; X += planesPerChunk) {
+                BoxL cb = b;
+                cb.X0 = X; cb.X1 = std::min(b.X1, X + planesPerChunk - 1);
+                const size_t nb = (size_t)cb.cells() * Q * sizeof(T);
+                T* st = (T*)stage(nb);
+                const unsigned grid = (unsigned)((cb.cells() + 127) / 128);
+                if (up) {
+                    PLB_CUDA(cudaMemcpyAsync(st, host, nb, cudaMemcpyHostToDevice, stream_));
+                    transfer_kernel<T, Q, true><<<grid, 128, 0, stream_>>>(ctx(sl), sl.F, cb, st);
+                } else {
+                    transfer_kernel<T, Q, false><<<grid, 128, 0, stream_>>>(ctx(sl), sl.F, cb, st);
+                    PLB_CUDA(cudaMemcpyAsync(host, st, nb, cudaMemcpyDeviceToHost, stream_));
+                }
+                launched();
+                PLB_CUDA(cudaStreamSynchronize(stream_));
+                host += nb;
+            }
+        }
+    }
+
+    double box_sum(const int box[6], int what) {
+        check_box(box);
+        sync_setup();
+        double total = 0.;
+        for (Slab& sl : slabs_) {
+            BoxL b;
+            if (!local_box(sl, box, b)) continue;
+            const int grid = (int)std::min<long long>((b.cells() + 255) / 256, 1024);
+            double* part = (double*)stage(grid * sizeof(double));
+            box_sum_kernel<T, Q><<<grid, 256, 0, stream_>>>(ctx(sl), b, what, part);
+            launched();
+            std::vector<double> h(grid);
+            PLB_CUDA(cudaMemcpyAsync(h.data(), part, grid * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            PLB_CUDA(cudaStreamSynchronize(stream_));
+            for (double v : h) total += v;
+        }
+        if (desc_.nRanks > 1) all_reduce(&total, 1, false);
+        return total;
+    }
+};
+
+}  // namespace plb200

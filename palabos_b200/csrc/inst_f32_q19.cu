@@ -1,0 +1,8 @@
+// palabos_b200/csrc/inst_f32_q19.cu -- explicit instantiation of the engine for T = float, D3Q19
+// (one translation unit per (T, Q) so that the four compile in parallel).
+#include "engine_impl.cuh"
+
+namespace plb200 {
+template class LatticeImpl<float, 19>;
+LatticeBase* make_lattice_f32_q19(const CreateDesc& d) { return new LatticeImpl<float, 19>(d); }
+}  // namespace plb200

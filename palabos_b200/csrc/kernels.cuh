@@ -1,0 +1,545 @@
+// palabos_b200/csrc/kernels.cuh -- device kernels of the collide-and-stream path.
+//
+// Storage (per slab, all in HBM): structure-of-arrays populations  F[slot][X][y][z]  with z fastest
+// (the reference's index order, atomicBlock/blockLattice3D.hh:342-349), X = local x + 1 so that
+// planes X = 0 and X = nxl+1 are the ghost planes towards the neighbouring slabs; one byte per cell
+// with the index of its dynamics; one int32 per cell with the index of its boundary record or -1.
+//
+// Streaming is IN PLACE with the AA pattern (one read and one write per population per step):
+//   even step  (layout NORMAL -> SWAPPED): read slot i of the own cell, collide, write f*_i into
+//              slot opp(i) of the own cell.  Purely local.
+//   odd step   (layout SWAPPED -> NORMAL): population i that arrives at cell x sits in slot opp(i)
+//              of cell x - c_i; read it there, collide, write f*_i into slot i of cell x + c_i.
+//              Each storage location is read and written by exactly one thread.
+// A population whose neighbour lies outside a non-periodic edge of the global domain stays on its
+// cell in the opposite slot -- the reference's rule for the rim of the sweep domain (collide()+revert()
+// followed by the bounds-checked swaps of boundaryStream(), atomicBlock/blockLattice3D.hh:173-185,
+// :403-427).  In the SWAPPED layout the post-stream population (i, x) of the reference is therefore found at
+//   valid(x - c_i) ? (slot opp(i), cell x - c_i) : (slot i, cell x)             ("accessor")
+// which is how the boundary, transfer and analysis kernels address populations after an even step.
+#pragma once
+#include <cfloat>
+#include <cuda_runtime.h>
+#include "lb_core.cuh"
+
+namespace plb200 {
+
+enum XMode : int { XMODE_EDGE = 0, XMODE_GHOST = 1, XMODE_WRAP = 2 };
+
+struct Geo {
+    int nxl, ny, nz;      ///< owned planes, rows, columns
+    int P;                ///< ny*nz cells per x-plane
+    long long S;          ///< slot stride in elements = (nxl+2)*P
+    int perY, perZ;       ///< in-kernel index wrap along y / z
+    int lowMode, highMode;///< what lies beyond X = 1 / X = nxl (XMode)
+};
+
+struct Nbr {
+    int oxm, oxp, oym, oyp, ozm, ozp;
+    bool vxm, vxp, vym, vyp, vzm, vzp;
+};
+
+__device__ __forceinline__ Nbr make_nbr(const Geo& g, int X, int y, int z) {
+    Nbr n;
+    n.vzm = (z > 0) || g.perZ;          n.ozm = (z > 0) ? -1 : (g.nz - 1);
+    n.vzp = (z < g.nz - 1) || g.perZ;   n.ozp = (z < g.nz - 1) ? 1 : -(g.nz - 1);
+    n.vym = (y > 0) || g.perY;          n.oym = (y > 0) ? -g.nz : (g.ny - 1) * g.nz;
+    n.vyp = (y < g.ny - 1) || g.perY;   n.oyp = (y < g.ny - 1) ? g.nz : -(g.ny - 1) * g.nz;
+    if (X > 1) { n.vxm = true; n.oxm = -g.P; }
+    else { n.vxm = g.lowMode != XMODE_EDGE; n.oxm = g.lowMode == XMODE_WRAP ? (g.nxl - 1) * g.P : -g.P; }
+    if (X < g.nxl) { n.vxp = true; n.oxp = g.P; }
+    else { n.vxp = g.highMode != XMODE_EDGE; n.oxp = g.highMode == XMODE_WRAP ? -(g.nxl - 1) * g.P : g.P; }
+    return n;
+}
+
+template <int SX, int SY, int SZ>
+__device__ __forceinline__ bool nbr_valid(const Nbr& n) {
+    bool v = true;
+    if (SX > 0) v = v && n.vxp;
+    if (SX < 0) v = v && n.vxm;
+    if (SY > 0) v = v && n.vyp;
+    if (SY < 0) v = v && n.vym;
+    if (SZ > 0) v = v && n.vzp;
+    if (SZ < 0) v = v && n.vzm;
+    return v;
+}
+template <int SX, int SY, int SZ>
+__device__ __forceinline__ int nbr_off(const Nbr& n) {
+    int o = 0;
+    if (SX > 0) o += n.oxp;
+    if (SX < 0) o += n.oxm;
+    if (SY > 0) o += n.oyp;
+    if (SY < 0) o += n.oym;
+    if (SZ > 0) o += n.ozp;
+    if (SZ < 0) o += n.ozm;
+    return o;
+}
+
+/// Storage index to which f*_I of cell c streams (odd step), i.e. where the reference's post-stream
+/// population (I, c + c_I) lives in the NORMAL layout -- or the opposite slot of c at a domain edge.
+template <class T, int Q, int I>
+__device__ __forceinline__ long long stream_target(const Geo& g, const Nbr& n, int c) {
+    using L = LB<T, Q>;
+    constexpr int sx = L::c(I, 0), sy = L::c(I, 1), sz = L::c(I, 2);
+    return nbr_valid<sx, sy, sz>(n) ? (long long)I * g.S + (c + nbr_off<sx, sy, sz>(n))
+                                    : (long long)L::opp(I) * g.S + c;
+}
+
+/// Storage index of the reference's population (I, c) in the given layout (see file header).
+template <class T, int Q, int I>
+__device__ __forceinline__ long long pop_index(const Geo& g, const Nbr& n, int c, bool swapped) {
+    using L = LB<T, Q>;
+    if (!swapped || I == 0) return (long long)I * g.S + c;
+    return stream_target<T, Q, L::opp(I)>(g, n, c);
+}
+
+template <class T, int Q, int I = 0>
+struct CellIO {
+    __device__ __forceinline__ static void load(const T* __restrict__ F, const Geo& g, const Nbr& n, int c, bool swapped, T* f) {
+        f[I] = F[pop_index<T, Q, I>(g, n, c, swapped)];
+        CellIO<T, Q, I + 1>::load(F, g, n, c, swapped, f);
+    }
+    __device__ __forceinline__ static void store(T* __restrict__ F, const Geo& g, const Nbr& n, int c, bool swapped, const T* f) {
+        F[pop_index<T, Q, I>(g, n, c, swapped)] = f[I];
+        CellIO<T, Q, I + 1>::store(F, g, n, c, swapped, f);
+    }
+    // the sweep's own forms
+    __device__ __forceinline__ static void load_local(const T* __restrict__ F, const Geo& g, int c, T* f) {
+        f[I] = F[(long long)I * g.S + c];
+        CellIO<T, Q, I + 1>::load_local(F, g, c, f);
+    }
+    __device__ __forceinline__ static void store_local_swapped(T* __restrict__ F, const Geo& g, int c, const T* f) {
+        F[(long long)LB<T, Q>::opp(I) * g.S + c] = f[I];
+        CellIO<T, Q, I + 1>::store_local_swapped(F, g, c, f);
+    }
+    __device__ __forceinline__ static void load_pull(const T* __restrict__ F, const Geo& g, const Nbr& n, int c, T* f) {
+        f[I] = F[stream_target<T, Q, LB<T, Q>::opp(I)>(g, n, c)];
+        CellIO<T, Q, I + 1>::load_pull(F, g, n, c, f);
+    }
+    __device__ __forceinline__ static void store_push(T* __restrict__ F, const Geo& g, const Nbr& n, int c, const T* f) {
+        F[stream_target<T, Q, I>(g, n, c)] = f[I];
+        CellIO<T, Q, I + 1>::store_push(F, g, n, c, f);
+    }
+};
+template <class T, int Q>
+struct CellIO<T, Q, Q> {
+    __device__ __forceinline__ static void load(const T*, const Geo&, const Nbr&, int, bool, T*) {}
+    __device__ __forceinline__ static void store(T*, const Geo&, const Nbr&, int, bool, const T*) {}
+    __device__ __forceinline__ static void load_local(const T*, const Geo&, int, T*) {}
+    __device__ __forceinline__ static void store_local_swapped(T*, const Geo&, int, const T*) {}
+    __device__ __forceinline__ static void load_pull(const T*, const Geo&, const Nbr&, int, T*) {}
+    __device__ __forceinline__ static void store_push(T*, const Geo&, const Nbr&, int, const T*) {}
+};
+
+// ---------------------------------------------------------------------------------- the sweep
+
+constexpr int SWEEP_THREADS = 256;
+
+template <class T>
+struct SweepArgs {
+    T* F;
+    const uint8_t* kind;
+    const Dyn<T>* dyns;       ///< dynamics table in global memory
+    Geo g;
+    int cellBegin, cellEnd;   ///< storage cell range [begin, end) swept by this launch
+    T omega, preFactor;       ///< parameters of dynamics-table entry 0 (the lattice's background dynamics)
+    int gatherStats;          ///< BlockStatistics on/off (MultiBlock3D::toggleInternalStatistics)
+    double* partials;         ///< [gridDim.x][4] per-block partial sums
+    unsigned int* ticket;     ///< arrival counter for the last-block reduction
+    double* statsOut;         ///< [4] sum rhoBar, sum uSqr, max uSqr, cell count of this launch
+};
+
+/// Deterministic block reduction of the BlockStatistics accumulators (core/blockStatistics.cpp:205-229:
+/// gatherAverage / gatherMax / incrementStats, always in double) followed by a fixed-order reduction
+/// over blocks done by whichever block arrives last.
+__device__ __forceinline__ void reduce_stats(double sRho, double sU, double mU, double cnt,
+                                             double* partials, unsigned int* ticket, double* out) {
+    __shared__ double sh[4][SWEEP_THREADS / 32];
+    __shared__ bool isLast;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sRho += __shfl_down_sync(0xffffffffu, sRho, o);
+        sU += __shfl_down_sync(0xffffffffu, sU, o);
+        mU = fmax(mU, __shfl_down_sync(0xffffffffu, mU, o));
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) { sh[0][warp] = sRho; sh[1][warp] = sU; sh[2][warp] = mU; sh[3][warp] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = sh[0][0], b = sh[1][0], m = sh[2][0], n = sh[3][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; m = fmax(m, sh[2][w]); n += sh[3][w]; }
+        double* p = partials + 4 * (size_t)blockIdx.x;
+        p[0] = a; p[1] = b; p[2] = m; p[3] = n;
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        isLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    // fixed order: thread k sums blocks k, k+B, k+2B, ...; then the same tree as above
+    double a = 0., b = 0., m = -DBL_MAX, n = 0.;
+    for (unsigned int blk = threadIdx.x; blk < gridDim.x; blk += blockDim.x) {
+        const volatile double* p = partials + 4 * (size_t)blk;
+        a += p[0]; b += p[1]; m = fmax(m, p[2]); n += p[3];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+        m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+        n += __shfl_down_sync(0xffffffffu, n, o);
+    }
+    __syncthreads();
+    if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; sh[2][warp] = m; sh[3][warp] = n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = sh[0][0]; b = sh[1][0]; m = sh[2][0]; n = sh[3][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; m = fmax(m, sh[2][w]); n += sh[3][w]; }
+        out[0] = a; out[1] = b; out[2] = m; out[3] = n;
+        *ticket = 0u;
+    }
+}
+
+/// The fused collide-and-stream sweep (BlockLattice3D::collideAndStream, atomicBlock/blockLattice3D.hh:253-312,
+/// with Cell::collide -> Dynamics::collide inlined as a device functor and gatherStatistics,
+/// core/latticeStatistics.h:36-45, reduced per block).
+///   MAIN     dynamics type of table entry 0, compiled in
+///   GENERIC  false: every cell is entry 0, BounceBack or NoDynamics; true: any table entry per cell
+///   ODD      which half of the AA pattern (see file header)
+template <class T, int Q, int MAIN, bool GENERIC, bool ODD>
+__global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepArgs<T> a) {
+    using L = LB<T, Q>;
+    const Geo& g = a.g;
+    double sRho = 0., sU = 0., mU = -DBL_MAX, cnt = 0.;
+    const int nTiles = (a.cellEnd - a.cellBegin + SWEEP_THREADS - 1) / SWEEP_THREADS;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const int c = a.cellBegin + tile * SWEEP_THREADS + threadIdx.x;
+        if (c >= a.cellEnd) continue;
+        T f[Q];
+        Nbr n;
+        if (ODD) {
+            const int X = c / g.P;
+            const int r = c - X * g.P;
+            const int y = r / g.nz;
+            const int z = r - y * g.nz;
+            n = make_nbr(g, X, y, z);
+            CellIO<T, Q>::load_pull(a.F, g, n, c, f);
+        } else {
+            CellIO<T, Q>::load_local(a.F, g, c, f);
+        }
+        const int k = a.kind[c];
+        T rhoBar = (T)0, uSqr = (T)0;
+        bool took;
+        if (!GENERIC) {
+            if (k == 0) {
+                took = L::template collide_as<MAIN>(f, a.omega, a.preFactor, rhoBar, uSqr);
+            } else {
+                took = false;
+                if (a.dyns[k].type == DYN_BOUNCEBACK) L::collide_bounceback(f);
+            }
+        } else {
+            const Dyn<T> d = a.dyns[k];
+            took = L::collide_any(d, f, rhoBar, uSqr);
+        }
+        if (ODD) CellIO<T, Q>::store_push(a.F, g, n, c, f);
+        else CellIO<T, Q>::store_local_swapped(a.F, g, c, f);
+        if (took) {
+            sRho += (double)rhoBar;
+            sU += (double)uSqr;
+            mU = fmax(mU, (double)uSqr);
+            cnt += 1.;
+        }
+    }
+    if (a.gatherStats) reduce_stats(sRho, sU, mU, cnt, a.partials, a.ticket, a.statsOut);
+}
+
+// ------------------------------------------------------------------- boundary processors
+
+struct Item {
+    int cell;            ///< storage cell index
+    signed char cls;     ///< ProcClass
+    signed char a, b, c; ///< edge: plane, normal1, normal2; corner: xNormal, yNormal, zNormal
+};
+
+template <class T>
+struct CellCtx {
+    const T* F;
+    const uint8_t* kind;
+    const int* bcIdx;
+    const Dyn<T>* dyns;
+    const Bc<T>* bcs;
+    Geo g;
+    bool swapped;
+};
+
+__device__ __forceinline__ void decode_cell(const Geo& g, int c, int& X, int& y, int& z) {
+    X = c / g.P;
+    const int r = c - X * g.P;
+    y = r / g.nz;
+    z = r - y * g.nz;
+}
+
+template <class T, int Q>
+struct CellView {
+    Dyn<T> d;
+    Bc<T> b;
+    bool hasBc;
+    T f[Q];
+};
+
+/// Dynamics and boundary record of a cell; populations only if `needPops`.
+template <class T, int Q>
+__device__ __forceinline__ void fetch_cell(const CellCtx<T>& cx, int c, bool needDensityPops, bool needVelocityPops, CellView<T, Q>& v) {
+    using L = LB<T, Q>;
+    v.d = cx.dyns[cx.kind[c]];
+    const int bi = cx.bcIdx[c];
+    v.hasBc = bi >= 0;
+    if (v.hasBc) v.b = cx.bcs[bi];
+    else { v.b.kind = -1; v.b.dir = 0; v.b.ori = 1; v.b.u[0] = v.b.u[1] = v.b.u[2] = (T)0; v.b.rhoBar = (T)0; }
+    const bool need = (needDensityPops && L::density_reads_pops(v.d.type, v.hasBc, v.b.kind))
+                   || (needVelocityPops && L::velocity_reads_pops(v.d.type, v.hasBc, v.b.kind));
+    if (need) {
+        int X, y, z;
+        decode_cell(cx.g, c, X, y, z);
+        const Nbr n = make_nbr(cx.g, X, y, z);
+        CellIO<T, Q>::load(cx.F, cx.g, n, c, cx.swapped, v.f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) v.f[i] = (T)0;
+    }
+}
+
+template <class T, int Q>
+__device__ __forceinline__ T density_at(const CellCtx<T>& cx, int c) {
+    CellView<T, Q> v;
+    fetch_cell<T, Q>(cx, c, true, false, v);
+    return LB<T, Q>::cell_density(v.d, v.hasBc, v.b, v.f);
+}
+template <class T, int Q>
+__device__ __forceinline__ void velocity_at(const CellCtx<T>& cx, int c, T u[3]) {
+    CellView<T, Q> v;
+    fetch_cell<T, Q>(cx, c, false, true, v);
+    LB<T, Q>::cell_velocity(v.d, v.hasBc, v.b, v.f, u);
+}
+
+__device__ __forceinline__ int axis_stride(const Geo& g, int dir) { return dir == 0 ? g.P : (dir == 1 ? g.nz : 1); }
+
+/// fd::DirectedGradients3D<..,orthogonal=true>::o1_velocityDerivative finiteDifference/finiteDifference3D.h:64-82
+template <class T, int Q>
+__device__ __forceinline__ void grad_normal(const CellCtx<T>& cx, int c, int dir, int ori, T out[3]) {
+    T u0[3], u1[3];
+    velocity_at<T, Q>(cx, c, u0);
+    velocity_at<T, Q>(cx, c - ori * axis_stride(cx.g, dir), u1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[k] = -ori * (-u0[k] + u1[k]);
+}
+/// ..orthogonal=false: central difference finiteDifference3D.h:158-178
+template <class T, int Q>
+__device__ __forceinline__ void grad_tangent(const CellCtx<T>& cx, int c, int dir, T out[3]) {
+    T up[3], um[3];
+    velocity_at<T, Q>(cx, c + axis_stride(cx.g, dir), up);
+    velocity_at<T, Q>(cx, c - axis_stride(cx.g, dir), um);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[k] = (up[k] - um[k]) / (T)2;
+}
+
+/// common tail of Outer{Edge,Corner}Functional3D::processCell
+/// (boundaryCondition/finiteDifferenceBoundaryProcessor3D.hh:189-221, :287-313)
+template <class T, int Q>
+__device__ __forceinline__ void fd_regularize(const CellCtx<T>& cx, T* F, int c, T rho, T (*dA_uB)[3]) {
+    using L = LB<T, Q>;
+    CellView<T, Q> v;
+    fetch_cell<T, Q>(cx, c, false, true, v);
+    const T omega = L::is_inert(v.d.type) ? (T)0 : v.d.omega;
+    const T sToPi = -rho / L::invCs2() / omega;
+    T pi[6], vel[3], j[3];
+    pi[0] = (T)2 * dA_uB[0][0] * sToPi;
+    pi[3] = (T)2 * dA_uB[1][1] * sToPi;
+    pi[5] = (T)2 * dA_uB[2][2] * sToPi;
+    pi[1] = (dA_uB[0][1] + dA_uB[1][0]) * sToPi;
+    pi[2] = (dA_uB[0][2] + dA_uB[2][0]) * sToPi;
+    pi[4] = (dA_uB[1][2] + dA_uB[2][1]) * sToPi;
+    L::cell_velocity(v.d, v.hasBc, v.b, v.f, vel);
+    j[0] = rho * vel[0]; j[1] = rho * vel[1]; j[2] = rho * vel[2];
+    const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+    if (L::is_inert(v.d.type)) return;      // regularize is a no-op there: the populations stay
+    L::regularize(v.d.type, v.f, L::rhoBarOf(rho), j, jSqr, pi);
+    int X, y, z;
+    decode_cell(cx.g, c, X, y, z);
+    const Nbr n = make_nbr(cx.g, X, y, z);
+    CellIO<T, Q>::store(F, cx.g, n, c, cx.swapped, v.f);
+}
+
+/// One stage of the level-0 data processors (AtomicBlock3D::executeInternalProcessors,
+/// atomicBlock/atomicBlock3D.cpp:195-222).  The host has ordered the (processor, cell) pairs into
+/// stages such that running a stage's items concurrently equals the reference's sequential order.
+template <class T, int Q>
+__global__ void __launch_bounds__(128) boundary_stage_kernel(CellCtx<T> cx, T* F, const Item* items, int nItems) {
+    using L = LB<T, Q>;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nItems) return;
+    const Item it = items[t];
+    const int c = it.cell;
+    if (it.cls == PROC_PLANE) {
+        // WrappedLocalBoundaryFunctional3D::process boundaryCondition/wrappedLocalBoundaryProcessor3D.hh:42-62
+        const int bi = cx.bcIdx[c];
+        if (bi < 0) return;
+        const Bc<T> b = cx.bcs[bi];
+        const int baseType = cx.dyns[cx.kind[c]].type;
+        int X, y, z;
+        decode_cell(cx.g, c, X, y, z);
+        const Nbr n = make_nbr(cx.g, X, y, z);
+        T f[Q];
+        CellIO<T, Q>::load(F, cx.g, n, c, cx.swapped, f);
+        L::complete_populations(baseType, b, f);
+        CellIO<T, Q>::store(F, cx.g, n, c, cx.swapped, f);
+    } else if (it.cls == PROC_EDGE) {
+        // OuterVelocityEdgeFunctional3D::processCell finiteDifferenceBoundaryProcessor3D.hh:164-226
+        const int plane = it.a, n1 = it.b, n2 = it.c;
+        const int d1 = (plane + 1) % 3, d2 = (plane + 2) % 3;
+        const T rho10 = density_at<T, Q>(cx, c - n1 * axis_stride(cx.g, d1));
+        const T rho01 = density_at<T, Q>(cx, c - n2 * axis_stride(cx.g, d2));
+        const T rho = (T)0.5 * (rho01 + rho10);
+        T g0[3], g1[3], g2[3], dA_uB[3][3];
+        grad_tangent<T, Q>(cx, c, plane, g0);
+        grad_normal<T, Q>(cx, c, d1, n1, g1);
+        grad_normal<T, Q>(cx, c, d2, n2, g2);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            dA_uB[0][k] = plane == 0 ? g0[k] : (d1 == 0 ? g1[k] : g2[k]);
+            dA_uB[1][k] = plane == 1 ? g0[k] : (d1 == 1 ? g1[k] : g2[k]);
+            dA_uB[2][k] = plane == 2 ? g0[k] : (d1 == 2 ? g1[k] : g2[k]);
+        }
+        fd_regularize<T, Q>(cx, F, c, rho, dA_uB);
+    } else {
+        // OuterVelocityCornerFunctional3D::processCell finiteDifferenceBoundaryProcessor3D.hh:264-318
+        const int xn = it.a, yn = it.b, zn = it.c;
+        const T rho100 = density_at<T, Q>(cx, c - xn * cx.g.P);
+        const T rho010 = density_at<T, Q>(cx, c - yn * cx.g.nz);
+        const T rho001 = density_at<T, Q>(cx, c - zn);
+        const T rho = (T)1 / (T)3 * (rho001 + rho010 + rho100);
+        T dA_uB[3][3];
+        grad_normal<T, Q>(cx, c, 0, xn, dA_uB[0]);
+        grad_normal<T, Q>(cx, c, 1, yn, dA_uB[1]);
+        grad_normal<T, Q>(cx, c, 2, zn, dA_uB[2]);
+        fd_regularize<T, Q>(cx, F, c, rho, dA_uB);
+    }
+}
+
+// ------------------------------------------------------------- set-up, transfer, analysis
+
+struct BoxL {             ///< a box in storage coordinates of one slab: X in [X0,X1], y, z inclusive
+    int X0, X1, y0, y1, z0, z1;
+    __host__ __device__ int ny() const { return y1 - y0 + 1; }
+    __host__ __device__ int nz() const { return z1 - z0 + 1; }
+    __host__ __device__ long long cells() const { return (long long)(X1 - X0 + 1) * ny() * nz(); }
+};
+
+__device__ __forceinline__ int box_cell(const Geo& g, const BoxL& b, long long k, int& X, int& y, int& z) {
+    const int bz = b.nz(), by = b.ny();
+    const int kz = (int)(k % bz);
+    const long long r = k / bz;
+    const int ky = (int)(r % by);
+    const int kx = (int)(r / by);
+    X = b.X0 + kx; y = b.y0 + ky; z = b.z0 + kz;
+    return (X * g.ny + y) * g.nz + z;
+}
+
+/// initializeAtEquilibrium(lattice, box, rho, u) -> iniCellAtEquilibrium core/cell.hh:124-132.
+/// field == nullptr: constant (rho, u); otherwise field = [cells of the box][rho,ux,uy,uz] in double
+/// (converted to T like the reference's functional overload does).
+template <class T, int Q>
+__global__ void init_equilibrium_kernel(CellCtx<T> cx, T* F, BoxL box, T rho, T ux, T uy, T uz, const double* field) {
+    using L = LB<T, Q>;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= box.cells()) return;
+    int X, y, z;
+    const int c = box_cell(cx.g, box, k, X, y, z);
+    T u[3] = { ux, uy, uz };
+    if (field) { rho = (T)field[4 * k]; u[0] = (T)field[4 * k + 1]; u[1] = (T)field[4 * k + 2]; u[2] = (T)field[4 * k + 3]; }
+    T f[Q];
+    L::ini_equilibrium(cx.dyns[cx.kind[c]].type, f, rho, u);
+    const Nbr n = make_nbr(cx.g, X, y, z);
+    CellIO<T, Q>::store(F, cx.g, n, c, cx.swapped, f);
+}
+
+/// CoProcessor3D::send / receive wire format (coProcessors/coProcessor3D.h:79-92): raw T,
+/// [x][y][z][q], values as stored (f - t_i, Cell::serialize core/cell.hh:103-111).
+template <class T, int Q, bool UP>
+__global__ void transfer_kernel(CellCtx<T> cx, T* F, BoxL box, T* wire) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= box.cells()) return;
+    int X, y, z;
+    const int c = box_cell(cx.g, box, k, X, y, z);
+    const Nbr n = make_nbr(cx.g, X, y, z);
+    T f[Q];
+    if (UP) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) f[i] = wire[k * Q + i];
+        CellIO<T, Q>::store(F, cx.g, n, c, cx.swapped, f);
+    } else {
+        CellIO<T, Q>::load(F, cx.g, n, c, cx.swapped, f);
+#pragma unroll
+        for (int i = 0; i < Q; ++i) wire[k * Q + i] = f[i];
+    }
+}
+
+/// rho and u of every cell of a box through Cell::computeDensity / computeVelocity; out = [cells][4] in T
+template <class T, int Q>
+__global__ void density_velocity_kernel(CellCtx<T> cx, BoxL box, T* out) {
+    using L = LB<T, Q>;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= box.cells()) return;
+    int X, y, z;
+    const int c = box_cell(cx.g, box, k, X, y, z);
+    CellView<T, Q> v;
+    fetch_cell<T, Q>(cx, c, true, true, v);
+    T u[3];
+    out[4 * k] = L::cell_density(v.d, v.hasBc, v.b, v.f);
+    L::cell_velocity(v.d, v.hasBc, v.b, v.f, u);
+    out[4 * k + 1] = u[0]; out[4 * k + 2] = u[1]; out[4 * k + 3] = u[2];
+}
+
+/// BoxSumEnergyFunctional3D (dataProcessors/dataAnalysisFunctional3D.hh:97-123: sum of |u|^2, double
+/// accumulator) and BoxSumRhoBarFunctional3D (:62-76).  what: 0 = |u|^2, 1 = rhoBar.
+/// partials[blockIdx.x] = block sum; the host adds the partials in order.
+template <class T, int Q>
+__global__ void __launch_bounds__(256) box_sum_kernel(CellCtx<T> cx, BoxL box, int what, double* partials) {
+    using L = LB<T, Q>;
+    __shared__ double sh[8];
+    double s = 0.;
+    const long long total = box.cells();
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        int X, y, z;
+        const int c = box_cell(cx.g, box, k, X, y, z);
+        CellView<T, Q> v;
+        fetch_cell<T, Q>(cx, c, what == 1, what == 0, v);
+        if (what == 0) {
+            T u[3];
+            L::cell_velocity(v.d, v.hasBc, v.b, v.f, u);
+            const T uNormSqr = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+            s += (double)uNormSqr;
+        } else {
+            s += (double)L::cell_rhoBar(v.d, v.hasBc, v.b, v.f);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = sh[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) a += sh[w];
+        partials[blockIdx.x] = a;
+    }
+}
+
+/// Scatter the sparse (cell -> boundary record) map into the dense per-cell index.
+static __global__ void scatter_bc_index_kernel(const int* cells, int n, int* bcIdx) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) bcIdx[cells[t]] = t;
+}
+
+}  // namespace plb200

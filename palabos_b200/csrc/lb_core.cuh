@@ -1,0 +1,656 @@
+// palabos_b200/csrc/lb_core.cuh -- velocity sets and per-cell arithmetic of the hot path.
+//
+// Everything here is a __host__ __device__ function template on <T, Q> that works on ONE cell
+// held in registers (T f[Q], indices known at compile time after unrolling).  The expression
+// shapes (association order, which literals are T and which are bare doubles) follow the
+// reference, because the parity contract is bit-exact populations: the library is compiled with
+// -fmad=false and IEEE division / square root.  Citations are relative to /root/reference/src.
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+#define PLB_HD __host__ __device__ __forceinline__
+
+namespace plb200 {
+
+enum DynType : int { DYN_BGK = 0, DYN_RLB = 1, DYN_TRT = 2, DYN_SMAGO = 3, DYN_BOUNCEBACK = 4, DYN_NODYNAMICS = 5 };
+enum BcKind : int { BC_VEL_REG = 0, BC_RHO_REG = 1, BC_VEL_ZH = 2, BC_RHO_ZH = 3, BC_STORE_VEL = 4 };
+enum ProcClass : int { PROC_PLANE = 0, PROC_EDGE = 1, PROC_CORNER = 2 };
+
+/// One entry of the per-lattice dynamics table (a cell stores the 1-byte index of its entry).
+template <class T>
+struct Dyn {
+    int type;
+    T omega;      ///< relaxation parameter (omega0 for Smagorinsky)
+    T preFactor;  ///< Smagorinsky: 0.5*(cSmago*omega0*invCs2)^2, complexDynamics/smagorinskyDynamics.hh:45-48
+    T rho;        ///< BounceBack / NoDynamics: the density they report, core/dynamics.hh:813-815
+};
+
+/// Data of the boundary composite dynamics sitting on a cell (boundaryCondition/boundaryDynamics.hh):
+/// stored wall velocity (StoreVelocityDynamics :324-339) or stored rhoBar (StoreDensityDynamics :239-257).
+template <class T>
+struct Bc {
+    int kind, dir, ori;
+    T u[3];
+    T rhoBar;
+};
+
+// ------------------------------------------------------------------------------ descriptors
+
+/// latticeBoltzmann/nearestNeighborLattices3D.hh:165-177 (D3Q19 c), :225-239 (D3Q27 c)
+PLB_HD constexpr int c19(int i, int d) {
+    constexpr int tab[19][3] = {
+        { 0, 0, 0},
+        {-1, 0, 0}, { 0,-1, 0}, { 0, 0,-1},
+        {-1,-1, 0}, {-1, 1, 0}, {-1, 0,-1},
+        {-1, 0, 1}, { 0,-1,-1}, { 0,-1, 1},
+        { 1, 0, 0}, { 0, 1, 0}, { 0, 0, 1},
+        { 1, 1, 0}, { 1,-1, 0}, { 1, 0, 1},
+        { 1, 0,-1}, { 0, 1, 1}, { 0, 1,-1} };
+    return tab[i][d];
+}
+PLB_HD constexpr int c27(int i, int d) {
+    constexpr int tab[27][3] = {
+        { 0, 0, 0},
+        {-1, 0, 0}, { 0,-1, 0}, { 0, 0,-1},
+        {-1,-1, 0}, {-1, 1, 0}, {-1, 0,-1},
+        {-1, 0, 1}, { 0,-1,-1}, { 0,-1, 1},
+        {-1,-1,-1}, {-1,-1, 1}, {-1, 1,-1}, {-1, 1, 1},
+        { 1, 0, 0}, { 0, 1, 0}, { 0, 0, 1},
+        { 1, 1, 0}, { 1,-1, 0}, { 1, 0, 1},
+        { 1, 0,-1}, { 0, 1, 1}, { 0, 1,-1},
+        { 1, 1, 1}, { 1, 1,-1}, { 1,-1, 1}, { 1,-1,-1} };
+    return tab[i][d];
+}
+
+template <class T, int Q>
+struct LB {
+    static_assert(Q == 19 || Q == 27, "D3Q19 or D3Q27");
+    static constexpr int q = Q;
+    static constexpr int H = Q / 2;
+
+    PLB_HD static constexpr int c(int i, int d) { return Q == 19 ? c19(i, d) : c27(i, d); }
+    /// indexTemplates::opposite latticeBoltzmann/indexTemplates.h:41-46
+    PLB_HD static constexpr int opp(int i) { return i == 0 ? 0 : (i <= H ? i + H : i - H); }
+    PLB_HD static constexpr int nn(int i) {
+        return (c(i, 0) != 0) + (c(i, 1) != 0) + (c(i, 2) != 0);
+    }
+    /// weights: nearestNeighborLattices3D.hh:176-196 (D3Q19), :263-277 (D3Q27)
+    PLB_HD static constexpr T t(int i) {
+        return Q == 19
+            ? (nn(i) == 0 ? (T)1 / (T)3 : nn(i) == 1 ? (T)1 / (T)18 : (T)1 / (T)36)
+            : (nn(i) == 0 ? (T)8 / (T)27 : nn(i) == 1 ? (T)2 / (T)27 : nn(i) == 2 ? (T)1 / (T)54 : (T)1 / (T)216);
+    }
+    PLB_HD static constexpr T cs2() { return (T)1 / (T)3; }
+    PLB_HD static constexpr T invCs2() { return (T)3; }
+
+    /// latticeBoltzmann/roundOffPolicy.h:74-90 (DefaultRoundOffPolicy)
+    PLB_HD static T rhoBarOf(T rho) { return rho - (T)1; }
+    PLB_HD static T fullRho(T rhoBar) { return rhoBar + (T)1; }
+    PLB_HD static T invRhoOf(T rhoBar) { return (T)1 / (rhoBar + (T)1); }
+
+    // ------------------------------------------------------------------------------ moments
+
+    struct Partial { T xm, x0, xp, ym, yp, zm, zp; };
+
+    /// momentTemplates3D.h:351-373 (D3Q19 partial_rho), :43-72 (D3Q27)
+    PLB_HD static Partial partial_rho(const T* f) {
+        Partial p;
+        if constexpr (Q == 19) {
+            p.xm = f[1] + f[4] + f[5] + f[6] + f[7];
+            p.xp = f[10] + f[13] + f[14] + f[15] + f[16];
+            p.ym = f[2] + f[4] + f[8] + f[9] + f[14];
+            p.yp = f[5] + f[11] + f[13] + f[17] + f[18];
+            p.zm = f[3] + f[6] + f[8] + f[16] + f[18];
+            p.zp = f[7] + f[9] + f[12] + f[15] + f[17];
+            p.x0 = f[0] + f[2] + f[3] + f[8] + f[9] + f[11] + f[12] + f[17] + f[18];
+        } else {
+            p.xm = f[1] + f[4] + f[5] + f[6] + f[7] + f[10] + f[11] + f[12] + f[13];
+            p.xp = f[14] + f[17] + f[18] + f[19] + f[20] + f[23] + f[24] + f[25] + f[26];
+            p.ym = f[2] + f[4] + f[8] + f[9] + f[10] + f[11] + f[18] + f[25] + f[26];
+            p.yp = f[5] + f[12] + f[13] + f[15] + f[17] + f[21] + f[22] + f[23] + f[24];
+            p.zm = f[3] + f[6] + f[8] + f[10] + f[12] + f[20] + f[22] + f[24] + f[26];
+            p.zp = f[7] + f[9] + f[11] + f[13] + f[16] + f[19] + f[21] + f[23] + f[25];
+            p.x0 = f[0] + f[2] + f[3] + f[8] + f[9] + f[15] + f[16] + f[21] + f[22];
+        }
+        return p;
+    }
+
+    /// momentTemplates3D.h:375-382 (D3Q19 get_rhoBar), :74-83 (D3Q27): plain left-to-right sum
+    PLB_HD static T get_rhoBar(const T* f) {
+        T rhoBar = f[0] + f[1];
+#pragma unroll
+        for (int i = 2; i < Q; ++i) rhoBar = rhoBar + f[i];
+        return rhoBar;
+    }
+
+    /// momentTemplates3D.h:384-402 (get_j)
+    PLB_HD static void get_j(const T* f, T j[3]) {
+        Partial p = partial_rho(f);
+        j[0] = (p.xp - p.xm); j[1] = (p.yp - p.ym); j[2] = (p.zp - p.zm);
+    }
+
+    /// momentTemplates3D.h:411-423 (D3Q19 get_rhoBar_j), :118-132 (D3Q27)
+    PLB_HD static void get_rhoBar_j(const T* f, T& rhoBar, T j[3]) {
+        Partial p = partial_rho(f);
+        rhoBar = p.xm + p.x0 + p.xp;
+        j[0] = (p.xp - p.xm); j[1] = (p.yp - p.ym); j[2] = (p.zp - p.zm);
+    }
+
+    /// momentTemplates3D.h:517-539 (D3Q19 compute_rhoBar_j_PiNeq), :239-267 (D3Q27).
+    /// Tensor index order xx,xy,xz,yy,yz,zz (geometricOperationTemplates.h:246-248).
+    PLB_HD static void rhoBar_j_PiNeq(const T* f, T& rhoBar, T j[3], T PiNeq[6]) {
+        Partial p = partial_rho(f);
+        rhoBar = p.xm + p.x0 + p.xp;
+        j[0] = (p.xp - p.xm); j[1] = (p.yp - p.ym); j[2] = (p.zp - p.zm);
+        const T invRho = invRhoOf(rhoBar);
+        PiNeq[0] = p.xp + p.xm - cs2() * rhoBar - invRho * j[0] * j[0];
+        PiNeq[3] = p.yp + p.ym - cs2() * rhoBar - invRho * j[1] * j[1];
+        PiNeq[5] = p.zp + p.zm - cs2() * rhoBar - invRho * j[2] * j[2];
+        if constexpr (Q == 19) {
+            PiNeq[1] = f[4] - f[5] + f[13] - f[14] - invRho * j[0] * j[1];
+            PiNeq[2] = f[6] - f[7] + f[15] - f[16] - invRho * j[0] * j[2];
+            PiNeq[4] = f[8] - f[9] + f[17] - f[18] - invRho * j[1] * j[2];
+        } else {
+            PiNeq[1] = f[4] - f[5] + f[10] + f[11] - f[12] - f[13]
+                     + f[17] - f[18] + f[23] + f[24] - f[25] - f[26]
+                     - invRho * j[0] * j[1];
+            PiNeq[2] = f[6] - f[7] + f[10] - f[11] + f[12] - f[13]
+                     + f[19] - f[20] + f[23] - f[24] + f[25] - f[26]
+                     - invRho * j[0] * j[2];
+            PiNeq[4] = f[8] - f[9] + f[10] - f[11] - f[12] + f[13]
+                     + f[21] - f[22] + f[23] - f[24] - f[25] + f[26]
+                     - invRho * j[1] * j[2];
+        }
+    }
+
+    // ------------------------------------------------------------------------------ equilibria
+
+    /// dynamicsTemplates3D.h:1994-1997 (D3Q19: literals are (T)-cast) and :167-170 (D3Q27: bare
+    /// double literals, so a float lattice evaluates this in double -- SURVEY.md section 7).
+    PLB_HD static T bgk_ma2_equilibrium(int i, T rhoBar, T invRho, const T j[3], T jSqr) {
+        T c_j = c(i, 0) * j[0] + c(i, 1) * j[1] + c(i, 2) * j[2];
+        if (Q == 19)
+            return t(i) * (rhoBar + (T)3. * c_j + invRho * ((T)4.5 * c_j * c_j - (T)1.5 * jSqr));
+        return t(i) * (rhoBar + 3. * c_j + invRho * (4.5 * c_j * c_j - 1.5 * jSqr));
+    }
+
+    /// dynamicsTemplates3D.h:1999-2076 (D3Q19 bgk_ma2_equilibria), :264-365 (D3Q27)
+    PLB_HD static void bgk_ma2_equilibria(T rhoBar, T invRho, const T j[3], T jSqr, T* eq) {
+        constexpr int h = H;
+        const T t0 = t(0), t1 = t(1), t4 = t(4);
+        const T kx = (T)3 * j[0], ky = (T)3 * j[1], kz = (T)3 * j[2];
+        const T kxSqr_ = invRho / (T)2 * kx * kx;
+        const T kySqr_ = invRho / (T)2 * ky * ky;
+        const T kzSqr_ = invRho / (T)2 * kz * kz;
+        const T kxky_ = invRho * kx * ky;
+        const T kxkz_ = invRho * kx * kz;
+        const T kykz_ = invRho * ky * kz;
+        const T C1 = rhoBar + invRho * (T)3 * jSqr;
+        T C2, C3;
+        C3 = -kxSqr_ - kySqr_ - kzSqr_;           eq[0] = t0 * (C1 + C3);
+        C2 = -kx;       C3 = -kySqr_ - kzSqr_;    eq[1] = t1 * (C1 + C2 + C3); eq[1 + h] = t1 * (C1 - C2 + C3);
+        C2 = -ky;       C3 = -kxSqr_ - kzSqr_;    eq[2] = t1 * (C1 + C2 + C3); eq[2 + h] = t1 * (C1 - C2 + C3);
+        C2 = -kz;       C3 = -kxSqr_ - kySqr_;    eq[3] = t1 * (C1 + C2 + C3); eq[3 + h] = t1 * (C1 - C2 + C3);
+        C2 = -kx - ky;  C3 = kxky_ - kzSqr_;      eq[4] = t4 * (C1 + C2 + C3); eq[4 + h] = t4 * (C1 - C2 + C3);
+        C2 = -kx + ky;  C3 = -kxky_ - kzSqr_;     eq[5] = t4 * (C1 + C2 + C3); eq[5 + h] = t4 * (C1 - C2 + C3);
+        C2 = -kx - kz;  C3 = kxkz_ - kySqr_;      eq[6] = t4 * (C1 + C2 + C3); eq[6 + h] = t4 * (C1 - C2 + C3);
+        C2 = -kx + kz;  C3 = -kxkz_ - kySqr_;     eq[7] = t4 * (C1 + C2 + C3); eq[7 + h] = t4 * (C1 - C2 + C3);
+        C2 = -ky - kz;  C3 = kykz_ - kxSqr_;      eq[8] = t4 * (C1 + C2 + C3); eq[8 + h] = t4 * (C1 - C2 + C3);
+        C2 = -ky + kz;  C3 = -kykz_ - kxSqr_;     eq[9] = t4 * (C1 + C2 + C3); eq[9 + h] = t4 * (C1 - C2 + C3);
+        if constexpr (Q == 27) {
+            const T t10 = t(10);
+            C2 = -kx - ky - kz;  C3 = kxky_ + kxkz_ + kykz_;   eq[10] = t10 * (C1 + C2 + C3); eq[23] = t10 * (C1 - C2 + C3);
+            C2 = -kx - ky + kz;  C3 = kxky_ - kxkz_ - kykz_;   eq[11] = t10 * (C1 + C2 + C3); eq[24] = t10 * (C1 - C2 + C3);
+            C2 = -kx + ky - kz;  C3 = -kxky_ + kxkz_ - kykz_;  eq[12] = t10 * (C1 + C2 + C3); eq[25] = t10 * (C1 - C2 + C3);
+            C2 = -kx + ky + kz;  C3 = -kxky_ - kxkz_ + kykz_;  eq[13] = t10 * (C1 + C2 + C3); eq[26] = t10 * (C1 - C2 + C3);
+        }
+    }
+
+    // ------------------------------------------------------------------------------ collisions
+
+    /// D3Q19: dynamicsTemplates3D.h:2289-2368 (bgk_ma2_collision_base) via :2476-2478.
+    /// D3Q27: generic loop :1624-1634.  Returns uSqr.
+    PLB_HD static T bgk_ma2_collision(T* f, T rhoBar, const T j[3], T omega) {
+        const T invRho = invRhoOf(rhoBar);
+        if constexpr (Q == 19) {
+            const T one_m_omega = (T)1 - omega;
+            const T t0_omega = t(0) * omega;
+            const T t1_omega = t(1) * omega;
+            const T t4_omega = t(4) * omega;
+            const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+            const T kx = (T)3 * j[0];
+            const T ky = (T)3 * j[1];
+            const T kz = (T)3 * j[2];
+            const T kxSqr_ = invRho / (T)2 * kx * kx;
+            const T kySqr_ = invRho / (T)2 * ky * ky;
+            const T kzSqr_ = invRho / (T)2 * kz * kz;
+            const T kxky_ = invRho * kx * ky;
+            const T kxkz_ = invRho * kx * kz;
+            const T kykz_ = invRho * ky * kz;
+            const T C1 = rhoBar + invRho * (T)3 * jSqr;
+            T C2, C3;
+            C3 = -kxSqr_ - kySqr_ - kzSqr_;
+            f[0] *= one_m_omega; f[0] += t0_omega * (C1 + C3);
+            C2 = -kx;  C3 = -kySqr_ - kzSqr_;
+            f[1]  *= one_m_omega; f[1]  += t1_omega * (C1 + C2 + C3);
+            f[10] *= one_m_omega; f[10] += t1_omega * (C1 - C2 + C3);
+            C2 = -ky;  C3 = -kxSqr_ - kzSqr_;
+            f[2]  *= one_m_omega; f[2]  += t1_omega * (C1 + C2 + C3);
+            f[11] *= one_m_omega; f[11] += t1_omega * (C1 - C2 + C3);
+            C2 = -kz;  C3 = -kxSqr_ - kySqr_;
+            f[3]  *= one_m_omega; f[3]  += t1_omega * (C1 + C2 + C3);
+            f[12] *= one_m_omega; f[12] += t1_omega * (C1 - C2 + C3);
+            C2 = -kx - ky;  C3 = kxky_ - kzSqr_;
+            f[4]  *= one_m_omega; f[4]  += t4_omega * (C1 + C2 + C3);
+            f[13] *= one_m_omega; f[13] += t4_omega * (C1 - C2 + C3);
+            C2 = -kx + ky;  C3 = -kxky_ - kzSqr_;
+            f[5]  *= one_m_omega; f[5]  += t4_omega * (C1 + C2 + C3);
+            f[14] *= one_m_omega; f[14] += t4_omega * (C1 - C2 + C3);
+            C2 = -kx - kz;  C3 = kxkz_ - kySqr_;
+            f[6]  *= one_m_omega; f[6]  += t4_omega * (C1 + C2 + C3);
+            f[15] *= one_m_omega; f[15] += t4_omega * (C1 - C2 + C3);
+            C2 = -kx + kz;  C3 = -kxkz_ - kySqr_;
+            f[7]  *= one_m_omega; f[7]  += t4_omega * (C1 + C2 + C3);
+            f[16] *= one_m_omega; f[16] += t4_omega * (C1 - C2 + C3);
+            C2 = -ky - kz;  C3 = kykz_ - kxSqr_;
+            f[8]  *= one_m_omega; f[8]  += t4_omega * (C1 + C2 + C3);
+            f[17] *= one_m_omega; f[17] += t4_omega * (C1 - C2 + C3);
+            C2 = -ky + kz;  C3 = -kykz_ - kxSqr_;
+            f[9]  *= one_m_omega; f[9]  += t4_omega * (C1 + C2 + C3);
+            f[18] *= one_m_omega; f[18] += t4_omega * (C1 - C2 + C3);
+            return invRho * invRho * jSqr;
+        } else {
+            const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+#pragma unroll
+            for (int i = 0; i < Q; ++i) {
+                f[i] *= (T)1 - omega;
+                f[i] += omega * bgk_ma2_equilibrium(i, rhoBar, invRho, j, jSqr);
+            }
+            return jSqr * invRho * invRho;
+        }
+    }
+
+    /// neqPiD3Q19 dynamicsTemplates3D.h:1903-1975 and neqPiD3Q27 :38-135 (fromPiToFneq0..9 / 0..13)
+    PLB_HD static void neqPi(const T* pi, T* n) {
+        const T xx = pi[0], xy = pi[1], xz = pi[2], yy = pi[3], yz = pi[4], zz = pi[5];
+        if constexpr (Q == 19) {
+            n[0] = (T)3. / (T)2 * (-(T)1. / (T)3 * xx - (T)1. / (T)3 * yy - (T)1. / (T)3 * zz);
+            n[1] = (T)1. / (T)4 * ((T)2. / (T)3 * xx - (T)1. / (T)3 * yy - (T)1. / (T)3 * zz);
+            n[2] = (T)1. / (T)4 * (-(T)1. / (T)3 * xx + (T)2. / (T)3 * yy - (T)1. / (T)3 * zz);
+            n[3] = (T)1. / (T)4 * (-(T)1. / (T)3 * xx - (T)1. / (T)3 * yy + (T)2. / (T)3 * zz);
+            n[4] = (T)1. / (T)8 * ((T)2. / (T)3 * xx + (T)2. / (T)3 * yy - (T)1. / (T)3 * zz + (T)2 * xy);
+            n[5] = (T)1. / (T)8 * ((T)2. / (T)3 * xx + (T)2. / (T)3 * yy - (T)1. / (T)3 * zz - (T)2 * xy);
+            n[6] = (T)1. / (T)8 * ((T)2. / (T)3 * xx - (T)1. / (T)3 * yy + (T)2. / (T)3 * zz + (T)2 * xz);
+            n[7] = (T)1. / (T)8 * ((T)2. / (T)3 * xx - (T)1. / (T)3 * yy + (T)2. / (T)3 * zz - (T)2 * xz);
+            n[8] = (T)1. / (T)8 * (-(T)1. / (T)3 * xx + (T)2. / (T)3 * yy + (T)2. / (T)3 * zz + (T)2 * yz);
+            n[9] = (T)1. / (T)8 * (-(T)1. / (T)3 * xx + (T)2. / (T)3 * yy + (T)2. / (T)3 * zz - (T)2 * yz);
+        } else {
+            n[0] = (T)4. / (T)3 * (-(T)1. / (T)3 * xx - (T)1. / (T)3 * yy - (T)1. / (T)3 * zz);
+            n[1] = (T)1. / (T)3 * ((T)2. / (T)3 * xx - (T)1. / (T)3 * yy - (T)1. / (T)3 * zz);
+            n[2] = (T)1. / (T)3 * (-(T)1. / (T)3 * xx + (T)2. / (T)3 * yy - (T)1. / (T)3 * zz);
+            n[3] = (T)1. / (T)3 * (-(T)1. / (T)3 * xx - (T)1. / (T)3 * yy + (T)2. / (T)3 * zz);
+            n[4] = (T)1. / (T)12 * ((T)2 * xy + (T)2. / (T)3 * xx + (T)2. / (T)3 * yy - (T)1. / (T)3 * zz);
+            n[5] = (T)1. / (T)12 * (-(T)2 * xy + (T)2. / (T)3 * xx + (T)2. / (T)3 * yy - (T)1. / (T)3 * zz);
+            n[6] = (T)1. / (T)12 * ((T)2 * xz + (T)2. / (T)3 * xx - (T)1. / (T)3 * yy + (T)2. / (T)3 * zz);
+            n[7] = (T)1. / (T)12 * (-(T)2 * xz + (T)2. / (T)3 * xx - (T)1. / (T)3 * yy + (T)2. / (T)3 * zz);
+            n[8] = (T)1. / (T)12 * ((T)2 * yz - (T)1. / (T)3 * xx + (T)2. / (T)3 * yy + (T)2. / (T)3 * zz);
+            n[9] = (T)1. / (T)12 * (-(T)2 * yz - (T)1. / (T)3 * xx + (T)2. / (T)3 * yy + (T)2. / (T)3 * zz);
+            n[10] = (T)1. / (T)48 * (+(T)2 * xy + (T)2 * xz + (T)2 * yz
+                                     + (T)2. / (T)3 * xx + (T)2. / (T)3 * yy + (T)2. / (T)3 * zz);
+            n[11] = (T)1. / (T)48 * (+(T)2 * xy - (T)2 * xz - (T)2 * yz
+                                     + (T)2. / (T)3 * xx + (T)2. / (T)3 * yy + (T)2. / (T)3 * zz);
+            n[12] = (T)1. / (T)48 * (-(T)2 * xy + (T)2 * xz - (T)2 * yz
+                                     + (T)2. / (T)3 * xx + (T)2. / (T)3 * yy + (T)2. / (T)3 * zz);
+            n[13] = (T)1. / (T)48 * (-(T)2 * xy - (T)2 * xz + (T)2 * yz
+                                     + (T)2. / (T)3 * xx + (T)2. / (T)3 * yy + (T)2. / (T)3 * zz);
+        }
+    }
+
+    /// dynamicsTemplates3D.h:2500-2554 (D3Q19 rlb_collision), :1683-1760 (D3Q27)
+    PLB_HD static T rlb_collision(T* f, T rhoBar, T invRho, const T j[3], const T PiNeq[6], T omega) {
+        const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+        T n[14];
+        neqPi(PiNeq, n);
+        f[0] = bgk_ma2_equilibrium(0, rhoBar, invRho, j, jSqr) + ((T)1 - omega) * n[0];
+#pragma unroll
+        for (int i = 1; i <= H; ++i)
+            f[i] = bgk_ma2_equilibrium(i, rhoBar, invRho, j, jSqr) + ((T)1 - omega) * n[i];
+#pragma unroll
+        for (int i = 1; i <= H; ++i)
+            f[i + H] = bgk_ma2_equilibrium(i + H, rhoBar, invRho, j, jSqr) + ((T)1 - omega) * n[i];
+        return jSqr * invRho * invRho;
+    }
+
+    /// complexDynamics/smagorinskyDynamics.hh:45-48 (computePrefactor; util::sqr(x) = x*x)
+    PLB_HD static T smago_prefactor(T omega0, T cSmago) {
+        T x = cSmago * omega0 * invCs2();
+        return (T)0.5 * (x * x);
+    }
+    /// smagorinskyDynamics.hh:50-59 (computeOmega) + tensorNormSqr geometricOperationTemplates.h:254-257
+    PLB_HD static T smago_omega(T omega0, T preFactor, T rhoBar, const T m[6]) {
+        T PiNeqNormSqr = m[0] * m[0] + m[3] * m[3] + m[5] * m[5]
+                       + (T)2 * m[1] * m[1] + (T)2 * m[2] * m[2] + (T)2 * m[4] * m[4];
+        T PiNeqNorm = sqrt(PiNeqNormSqr);
+        T alpha = preFactor * invRhoOf(rhoBar);
+        T linearTerm = alpha * PiNeqNorm;
+        T squareTerm = (T)2 * alpha * alpha * PiNeqNormSqr;
+        return omega0 * (1 - linearTerm + squareTerm);
+    }
+
+    /// BGKdynamics::collide basicDynamics/isoThermalDynamics.hh:319-331
+    PLB_HD static void collide_bgk(T* f, T omega, T& rhoBar, T& uSqr) {
+        T j[3];
+        get_rhoBar_j(f, rhoBar, j);
+        uSqr = bgk_ma2_collision(f, rhoBar, j, omega);
+    }
+    /// RegularizedBGKdynamics::collide isoThermalDynamics.hh:1588-1602
+    PLB_HD static void collide_rlb(T* f, T omega, T& rhoBar, T& uSqr) {
+        T j[3], PiNeq[6];
+        rhoBar_j_PiNeq(f, rhoBar, j, PiNeq);
+        const T invRho = invRhoOf(rhoBar);
+        uSqr = rlb_collision(f, rhoBar, invRho, j, PiNeq, omega);
+    }
+    /// TRTdynamics::collide complexDynamics/trtDynamics.hh:64-99, sMinus = 1.1 (:40)
+    PLB_HD static void collide_trt(T* f, T omega, T& rhoBar, T& uSqr) {
+        const T sPlus = omega;
+        const T sMinus = (T)1.1;
+        T j[3], eq[Q];
+        get_rhoBar_j(f, rhoBar, j);
+        const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+        const T invRho = invRhoOf(rhoBar);
+        bgk_ma2_equilibria(rhoBar, invRho, j, jSqr, eq);
+        f[0] += -sPlus * f[0] + sPlus * eq[0];
+#pragma unroll
+        for (int i = 1; i <= H; ++i) {
+            const T eq_plus = 0.5 * (eq[i] + eq[i + H]);
+            const T eq_minus = 0.5 * (eq[i] - eq[i + H]);
+            const T f_plus = 0.5 * (f[i] + f[i + H]);
+            const T f_minus = 0.5 * (f[i] - f[i + H]);
+            f[i]     += -sPlus * (f_plus - eq_plus) - sMinus * (f_minus - eq_minus);
+            f[i + H] += -sPlus * (f_plus - eq_plus) + sMinus * (f_minus - eq_minus);
+        }
+        uSqr = jSqr * invRho * invRho;
+    }
+    /// SmagorinskyBGKdynamics::collide complexDynamics/smagorinskyDynamics.hh:290-304
+    PLB_HD static void collide_smago(T* f, T omega0, T preFactor, T& rhoBar, T& uSqr) {
+        T j[3], PiNeq[6];
+        rhoBar_j_PiNeq(f, rhoBar, j, PiNeq);
+        const T omega = smago_omega(omega0, preFactor, rhoBar, PiNeq);
+        uSqr = bgk_ma2_collision(f, rhoBar, j, omega);
+    }
+    /// BounceBack::collide core/dynamics.hh:783-791
+    PLB_HD static void collide_bounceback(T* f) {
+#pragma unroll
+        for (int i = 1; i <= H; ++i) { T tmp = f[i]; f[i] = f[i + H]; f[i + H] = tmp; }
+    }
+
+    /// Cell::collide -> Dynamics::collide (core/cell.h:183-186) with the dynamics type known at
+    /// compile time.  Returns true (and rhoBar, uSqr) when the dynamics gathers statistics.
+    template <int TYPE>
+    PLB_HD static bool collide_as(T* f, T omega, T preFactor, T& rhoBar, T& uSqr) {
+        if (TYPE == DYN_BGK) { collide_bgk(f, omega, rhoBar, uSqr); return true; }
+        if (TYPE == DYN_RLB) { collide_rlb(f, omega, rhoBar, uSqr); return true; }
+        if (TYPE == DYN_TRT) { collide_trt(f, omega, rhoBar, uSqr); return true; }
+        if (TYPE == DYN_SMAGO) { collide_smago(f, omega, preFactor, rhoBar, uSqr); return true; }
+        if (TYPE == DYN_BOUNCEBACK) { collide_bounceback(f); return false; }
+        return false;   // NoDynamics core/dynamics.hh:968-972
+    }
+
+    /// Same with the type read from the dynamics table at run time.
+    PLB_HD static bool collide_any(const Dyn<T>& d, T* f, T& rhoBar, T& uSqr) {
+        switch (d.type) {
+        case DYN_BGK:        collide_bgk(f, d.omega, rhoBar, uSqr); return true;
+        case DYN_RLB:        collide_rlb(f, d.omega, rhoBar, uSqr); return true;
+        case DYN_TRT:        collide_trt(f, d.omega, rhoBar, uSqr); return true;
+        case DYN_SMAGO:      collide_smago(f, d.omega, d.preFactor, rhoBar, uSqr); return true;
+        case DYN_BOUNCEBACK: collide_bounceback(f); return false;
+        default:             return false;
+        }
+    }
+
+    // ------------------------------------------------------------------------ regularization
+
+    PLB_HD static bool is_inert(int type) { return type == DYN_BOUNCEBACK || type == DYN_NODYNAMICS; }
+
+    /// Dynamics::computeEquilibrium(iPop, rhoBar, j, jSqr): identical for BGK / RLB / TRT /
+    /// Smagorinsky (isoThermalDynamics.hh:341-346, :1619-1624, trtDynamics.hh:138-143,
+    /// smagorinskyDynamics.hh:322-328); BounceBack / NoDynamics return 0 (core/dynamics.hh:800-805).
+    PLB_HD static T computeEquilibrium(int type, int i, T rhoBar, const T j[3], T jSqr) {
+        if (is_inert(type)) return (T)0;
+        const T invRho = invRhoOf(rhoBar);
+        return bgk_ma2_equilibrium(i, rhoBar, invRho, j, jSqr);
+    }
+
+    /// latticeBoltzmann/offEquilibriumTemplates.h:91-114 (generic; no 3D specialisation exists)
+    PLB_HD static T fromPiToFneq(int i, const T PiNeq[6]) {
+        T fNeq = (T)0;
+        int iPi = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            fNeq += PiNeq[iPi] * (c(i, a) * c(i, a) - cs2());
+            ++iPi;
+#pragma unroll
+            for (int b = a + 1; b < 3; ++b) {
+                fNeq += PiNeq[iPi] * (T)2 * c(i, a) * c(i, b);
+                ++iPi;
+            }
+        }
+        fNeq *= t(i) * invCs2() * invCs2() / (T)2;
+        return fNeq;
+    }
+
+    /// IsoThermalBulkDynamics::regularize basicDynamics/isoThermalDynamics.hh:54-70;
+    /// BounceBack/NoDynamics::regularize are no-ops (core/dynamics.hh:807-811, :986-990)
+    PLB_HD static void regularize(int type, T* f, T rhoBar, const T j[3], T jSqr, const T PiNeq[6]) {
+        if (is_inert(type)) return;
+        f[0] = computeEquilibrium(type, 0, rhoBar, j, jSqr) + fromPiToFneq(0, PiNeq);
+#pragma unroll
+        for (int i = 1; i <= H; ++i) {
+            f[i] = computeEquilibrium(type, i, rhoBar, j, jSqr);
+            f[i + H] = computeEquilibrium(type, i + H, rhoBar, j, jSqr);
+            const T fNeq = fromPiToFneq(i, PiNeq);
+            f[i] += fNeq;
+            f[i + H] += fNeq;
+        }
+    }
+
+    // ---------------------------------------------------------------- plane boundary dynamics
+
+    PLB_HD static int cdir(int i, int dir) { return dir == 0 ? c(i, 0) : (dir == 1 ? c(i, 1) : c(i, 2)); }
+
+    /// sums over indexTemplates::subIndex<D,direction,value>() in ascending index order
+    /// (latticeBoltzmann/indexTemplates.h:78-99)
+    PLB_HD static T sub_sum(const T* f, int dir, int value) {
+        T s = (T)0;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) if (cdir(i, dir) == value) s += f[i];
+        return s;
+    }
+
+    /// VelocityDirichletBoundaryDynamics::computeRhoBar boundaryCondition/boundaryDynamics.hh:639-668
+    /// (the descriptors on this path carry no external force: the 0.5*force terms vanish)
+    PLB_HD static T veldir_rhoBar(const Bc<T>& b, const T* f) {
+        const T rhoOnWall = sub_sum(f, b.dir, 0);
+        const T rhoNormal = sub_sum(f, b.dir, b.ori);
+        const T uN = b.dir == 0 ? b.u[0] : (b.dir == 1 ? b.u[1] : b.u[2]);
+        const T velNormal = (T)b.ori * (uN - 0.5 * (T)0);
+        return ((T)2 * rhoNormal + rhoOnWall - 1 * velNormal) / ((T)1 + velNormal);
+    }
+
+    /// DensityDirichletBoundaryDynamics::computeJ boundaryDynamics.hh:760-787
+    PLB_HD static void rhodir_j(const Bc<T>& b, const T* f, T j[3]) {
+        const T rhoOnWall = sub_sum(f, b.dir, 0);
+        const T rhoNormal = sub_sum(f, b.dir, b.ori);
+        const T jn = (T)b.ori * ((T)2 * rhoNormal + rhoOnWall - b.rhoBar);
+        j[0] = b.dir == 0 ? jn : (T)0;
+        j[1] = b.dir == 1 ? jn : (T)0;
+        j[2] = b.dir == 2 ? jn : (T)0;
+    }
+
+    PLB_HD static bool is_vel_plane(int kind) { return kind == BC_VEL_REG || kind == BC_VEL_ZH; }
+    PLB_HD static bool is_rho_plane(int kind) { return kind == BC_RHO_REG || kind == BC_RHO_ZH; }
+
+    /// computeRhoBarJ of the plane boundary dynamics: velocity boundaryDynamics.hh:680-701, density :822-828
+    PLB_HD static void plane_rhoBar_j(const Bc<T>& b, const T* f, T& rhoBar, T j[3]) {
+        if (is_vel_plane(b.kind)) {
+            rhoBar = veldir_rhoBar(b, f);
+            const T rho = fullRho(rhoBar);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) j[d] = rho * (b.u[d] - 0.5 * (T)0);
+        } else {
+            rhoBar = b.rhoBar;
+            rhodir_j(b, f, j);
+        }
+    }
+
+    /// boundaryTemplates<..>::compute_PiNeq boundaryCondition/boundaryTemplates.h:45-87
+    PLB_HD static void boundary_PiNeq(int baseType, const Bc<T>& b, const T* f, T rhoBar, const T j[3], T jSqr, T PiNeq[6]) {
+        T fNeq[Q];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const int cd = cdir(i, b.dir);
+            if (cd == 0) fNeq[i] = f[i] - computeEquilibrium(baseType, i, rhoBar, j, jSqr);
+            else if (cd == b.ori) fNeq[i] = f[i] - computeEquilibrium(baseType, i, rhoBar, j, jSqr);
+            else fNeq[i] = (T)0;
+        }
+        int iPi = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int bb = a; bb < 3; ++bb) {
+                T s = (T)0;
+#pragma unroll
+                for (int i = 0; i < Q; ++i) if (cdir(i, b.dir) == 0)
+                    s += c(i, a) * c(i, bb) * fNeq[i];
+#pragma unroll
+                for (int i = 0; i < Q; ++i) if (cdir(i, b.dir) == b.ori)
+                    s += (T)2 * c(i, a) * c(i, bb) * fNeq[i];
+                PiNeq[iPi] = s;
+                ++iPi;
+            }
+        }
+    }
+
+    /// ZouHeClosure boundaryCondition/zouHeDynamics.hh:43-115
+    PLB_HD static void zouhe_closure(int baseType, const Bc<T>& b, T* f) {
+        // missing populations = opposites of subIndex<dir,ori>; the diagonal ones (all but the single
+        // axis-aligned one) share the transverse-momentum correction: 4 for D3Q19, 8 for D3Q27.
+        constexpr int nDiag = (Q == 19) ? 4 : 8;
+        T rhoBar, j[3];
+        plane_rhoBar_j(b, f, rhoBar, j);
+        const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+#pragma unroll
+        for (int i = 1; i < Q; ++i) if (cdir(i, b.dir) == b.ori) {
+            // pop = opp(i) is missing, its opposite i is known
+            f[opp(i)] = f[i] - computeEquilibrium(baseType, i, rhoBar, j, jSqr)
+                             + computeEquilibrium(baseType, opp(i), rhoBar, j, jSqr);
+        }
+        // momentTemplates::compute_rho_uLb momentTemplates3D.h:437-445
+        T falseRhoBar, falseJ[3], falseU[3], diff[3];
+        get_rhoBar_j(f, falseRhoBar, falseJ);
+        const T invRho = invRhoOf(falseRhoBar);
+        const T falseRho = fullRho(falseRhoBar);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { falseU[d] = falseJ[d]; falseU[d] *= invRho; }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) diff[d] = (j[d] - falseRho * falseU[d]) / (T)nDiag;
+        const int d1 = (b.dir + 1) % 3, d2 = (b.dir + 2) % 3;
+        const T diff1 = d1 == 0 ? diff[0] : (d1 == 1 ? diff[1] : diff[2]);
+        const T diff2 = d2 == 0 ? diff[0] : (d2 == 1 ? diff[1] : diff[2]);
+#pragma unroll
+        for (int i = 1; i < Q; ++i) if (cdir(i, b.dir) == b.ori && nn(i) > 1) {
+            const int p = opp(i);
+            f[p] += cdir(p, d1) * diff1;
+            f[p] += cdir(p, d2) * diff2;
+        }
+    }
+
+    /// completePopulations of the four plane boundary dynamics:
+    /// RegularizedVelocity/DensityBoundaryDynamics regularizedBoundaryDynamics.hh:94-109, :166-181;
+    /// ZouHeVelocity/PressureDynamics zouHeDynamics.hh:166-169, :222-225.  StoreVelocityDynamics
+    /// (edges, corners) inherits the empty completePopulations (boundaryDynamics.hh:185-187).
+    PLB_HD static void complete_populations(int baseType, const Bc<T>& b, T* f) {
+        if (b.kind == BC_VEL_REG || b.kind == BC_RHO_REG) {
+            T rhoBar, j[3], PiNeq[6];
+            plane_rhoBar_j(b, f, rhoBar, j);
+            const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+            boundary_PiNeq(baseType, b, f, rhoBar, j, jSqr, PiNeq);
+            regularize(baseType, f, rhoBar, j, jSqr, PiNeq);
+        } else if (b.kind == BC_VEL_ZH || b.kind == BC_RHO_ZH) {
+            zouhe_closure(baseType, b, f);
+        }
+    }
+
+    // --------------------------------------------- Cell::computeDensity / Velocity / RhoBar
+
+    /// Dynamics::computeDensity of whatever sits on the cell (hasBc: a boundary composite is on top):
+    ///  bulk BasicBulkDynamics::computeDensity core/dynamics.hh:277-280; BB/NoDynamics their rho
+    ///  (:813-815, :992-994); velocity planes boundaryDynamics.hh:671-677; density planes :247-250;
+    ///  edges/corners fall through to the base dynamics (:83-87).
+    PLB_HD static T cell_density(const Dyn<T>& d, bool hasBc, const Bc<T>& b, const T* f) {
+        if (hasBc) {
+            if (is_vel_plane(b.kind)) return fullRho(veldir_rhoBar(b, f));
+            if (is_rho_plane(b.kind)) return fullRho(b.rhoBar);
+        }
+        if (is_inert(d.type)) return d.rho;
+        return fullRho(get_rhoBar(f));
+    }
+    /// True when cell_density needs the populations of the cell.
+    PLB_HD static bool density_reads_pops(int dynType, bool hasBc, int bcKind) {
+        if (hasBc) {
+            if (is_vel_plane(bcKind)) return true;
+            if (is_rho_plane(bcKind)) return false;
+        }
+        return !is_inert(dynType);
+    }
+
+    /// Dynamics::computeVelocity: bulk compute_uLb momentTemplates3D.h:429-435; BB/NoDynamics zero
+    /// (core/dynamics.hh:821-826); StoreVelocityDynamics (velocity planes, edges, corners)
+    /// boundaryDynamics.hh:324-331; density planes :790-812.
+    PLB_HD static void cell_velocity(const Dyn<T>& d, bool hasBc, const Bc<T>& b, const T* f, T u[3]) {
+        if (hasBc) {
+            if (is_rho_plane(b.kind)) {
+                const T invRho = invRhoOf(b.rhoBar);
+                rhodir_j(b, f, u);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { u[k] *= invRho; u[k] += 0.5 * (T)0; }
+                return;
+            }
+            u[0] = b.u[0]; u[1] = b.u[1]; u[2] = b.u[2];
+            return;
+        }
+        if (is_inert(d.type)) { u[0] = u[1] = u[2] = (T)0; return; }
+        get_j(f, u);
+        const T invRho = invRhoOf(get_rhoBar(f));
+        u[0] *= invRho; u[1] *= invRho; u[2] *= invRho;
+    }
+    PLB_HD static bool velocity_reads_pops(int dynType, bool hasBc, int bcKind) {
+        if (hasBc) return is_rho_plane(bcKind);
+        return !is_inert(dynType);
+    }
+
+    /// Dynamics::computeRhoBar: bulk core/dynamics.hh:351-354; BB :861-863; velocity planes
+    /// boundaryDynamics.hh:639-668; density planes :254-257; StoreVelocityDynamics :342-346.
+    PLB_HD static T cell_rhoBar(const Dyn<T>& d, bool hasBc, const Bc<T>& b, const T* f) {
+        if (hasBc) {
+            if (is_vel_plane(b.kind)) return veldir_rhoBar(b, f);
+            if (is_rho_plane(b.kind)) return b.rhoBar;
+            return rhoBarOf(cell_density(d, hasBc, b, f));
+        }
+        if (is_inert(d.type)) return rhoBarOf(d.rho);
+        return get_rhoBar(f);
+    }
+
+    /// iniCellAtEquilibrium core/cell.hh:124-132
+    PLB_HD static void ini_equilibrium(int type, T* f, T density, const T velocity[3]) {
+        T j[3];
+        j[0] = velocity[0] * density; j[1] = velocity[1] * density; j[2] = velocity[2] * density;
+        const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+        const T rhoBar = rhoBarOf(density);
+#pragma unroll
+        for (int i = 0; i < Q; ++i) f[i] = computeEquilibrium(type, i, rhoBar, j, jSqr);
+    }
+};
+
+}  // namespace plb200

@@ -1,0 +1,201 @@
+"""Parity of the CUDA engine (through the C-ABI, palabos_b200.Lattice) with the CPU oracle and with
+the dumps of the real reference under tests/golden/.
+
+Bar (BASELINE.json north_star): populations and rho/u within 1e-10 relative in fp64 -- the engine
+is in fact bit-identical, so the tests ask for equality of values (and of bytes where the sign of a
+zero cannot differ); statistics are sums over all cells in a different order: 1e-12 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES, cavity, channel, obstacle, periodic_box
+from scenario import digest, max_rel_diff, replay, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FAST = [n for n in CASES if n not in ("cavity_bgk_64_1000", "cavity_bgk_58", "cavity_bgk_39")]
+
+
+def run_gpu(sc, slabs=1):
+    import palabos_b200 as pb
+    eng = pb.Lattice(sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2, slabs_per_rank=slabs)
+    try:
+        res = replay(sc, eng)
+        res["launches"] = eng.launch_count()
+        return res
+    finally:
+        eng.close()
+
+
+def assert_same(name, got, want, prec):
+    for key, w in want.items():
+        if key in ("stats", "time", "launches"):
+            continue
+        g = got[key]
+        assert g.shape == w.shape and g.dtype == w.dtype
+        if not np.array_equal(g, w):
+            raise AssertionError("%s: %s differs, max rel diff %.3e" % (name, key, max_rel_diff(g, w)))
+    rel = 1e-12 if prec == "f64" else 1e-6
+    assert got["stats"].shape == want["stats"].shape
+    assert np.allclose(got["stats"], want["stats"], rtol=rel, atol=1e-300), (got["stats"], want["stats"])
+
+
+def check_golden(name, res):
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    keys = [k[:-7] for k in gold.files if k.endswith("_sha256")]
+    assert keys
+    for key in keys:
+        arr = res[key]
+        flat = arr.reshape(-1, arr.shape[-1])
+        assert np.array_equal(flat[gold[key + "_probe_idx"]], gold[key + "_probe"]), "%s: probe cells of %s differ" % (name, key)
+        if key + "_full" in gold.files:
+            assert np.array_equal(arr, gold[key + "_full"])
+        if digest(arr) != str(gold[key + "_sha256"]):
+            # equal values but different bytes can only be the sign of a zero
+            assert key + "_full" in gold.files, "%s: sha256 of %s differs" % (name, key)
+    rel = 1e-12 if res["stats"].dtype == np.float64 and "f32" not in name else 1e-6
+    assert np.allclose(res["stats"], gold["stats"], rtol=rel, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_engine_matches_oracle_and_reference_dump(name):
+    sc = CASES[name][0]()
+    got = run_gpu(sc)
+    assert got["launches"] > 0
+    assert_same(name, got, run_oracle(sc), sc.prec)
+    check_golden(name, got)
+
+
+@pytest.mark.parametrize("name", ["cavity_bgk_39", "cavity_bgk_58"])
+def test_engine_matches_reference_dump_known_answer_sizes(name):
+    check_golden(name, run_gpu(CASES[name][0]()))
+
+
+def test_cavity_64_1000_steps_against_reference():
+    """configs[0] proper: 64^3 cavity, 1000 steps -- the 1e-10 pin of north_star, met bit for bit."""
+    sc = CASES["cavity_bgk_64_1000"][0]()
+    got = run_gpu(sc)
+    check_golden("cavity_bgk_64_1000", got)
+    # the reference's own regression strings need 30 steps; here: sanity of the developed flow
+    assert 0.9999 < got["stats"][-1][5] < 1.0001
+
+
+# ---- decomposition invariance: k x-slabs with envelope exchange give the
+# ---- same populations as one block, bit for bit (jlabos/src/testing/testsuite:3-7 runs 1/2/4/8 ranks)
+
+SLAB_CASES = {
+    "cavity_bgk_12": 3,
+    "cavity_bgk_10x9x8": 2,
+    "cavity_zouhe_10x9x8": 5,
+    "channel_trt_16x12x10": 4,
+    "channel_trt_q27_8x8x8": 2,
+    "channel_smago_q27_f32": 3,
+    "obstacle_zouhe_24x12x10": 4,
+    "periodic_rlb_q27": 2,
+    "periodic_trt_f32": 8,
+    "mixed_omega_11x8x9": 3,
+    "inlet_outlet_local": 2,
+    "thin_4x5x3": 2,
+}
+
+
+@pytest.mark.parametrize("name", sorted(SLAB_CASES))
+def test_slab_decomposition_is_bit_identical(name):
+    sc = CASES[name][0]()
+    got = run_gpu(sc, slabs=SLAB_CASES[name])
+    assert_same(name, got, run_oracle(sc), sc.prec)
+    check_golden(name, got)
+
+
+def test_odd_and_even_step_counts_and_repeated_download():
+    """The in-place AA layout differs after odd and even step counts; download must hide that."""
+    sc = cavity(9, 10, 11, 0)
+    import palabos_b200 as pb
+    from scenario import OracleEngine
+    g = pb.Lattice(19, "f64", 9, 10, 11, sc.dyn, sc.p1)
+    o = OracleEngine(19, "f64", 9, 10, 11, sc.dyn, sc.p1)
+    for eng in (g, o):
+        eng.set_velocity_condition_on_block_boundaries("local", sc.box, sc.box)
+        eng.set_boundary_velocity(sc.box, (0, 0, 0))
+        eng.set_boundary_velocity((1, 7, 1, 8, 10, 10), (0.02, 0, 0))
+        eng.initialize_at_equilibrium(sc.box, 1.0, (0, 0, 0))
+        eng.initialize()
+    for n in (1, 1, 2, 3, 1):
+        g.collide_and_stream(n)
+        o.collide_and_stream(n)
+        assert np.array_equal(g.download(), o.download())
+        sub = (2, 5, 0, 9, 3, 10)
+        assert np.array_equal(g.download(sub), o.download(sub))
+        assert np.array_equal(g.compute_density_velocity(), o.compute_density_velocity())
+    # upload in the swapped layout, then keep going
+    pops = o.download()
+    pops2 = pops * 0.5
+    g.upload(pops2); o.upload(pops2)
+    g.collide_and_stream(3); o.collide_and_stream(3)
+    assert np.array_equal(g.download(), o.download())
+    g.close(); o.close()
+
+
+def test_time_dependent_boundary_velocity():
+    """setBoundaryVelocity between steps (only record values change: no re-scheduling)."""
+    import palabos_b200 as pb
+    from scenario import OracleEngine
+    sc = cavity(8, 8, 8, 0)
+    engines = [pb.Lattice(19, "f64", 8, 8, 8, "BGK", sc.p1, slabs_per_rank=2), OracleEngine(19, "f64", 8, 8, 8, "BGK", sc.p1)]
+    for eng in engines:
+        eng.set_velocity_condition_on_block_boundaries("local", sc.box, sc.box)
+        eng.set_boundary_velocity(sc.box, (0, 0, 0))
+        eng.initialize_at_equilibrium(sc.box, 1.0, (0, 0, 0))
+        eng.initialize()
+    for it in range(6):
+        for eng in engines:
+            eng.set_boundary_velocity((1, 6, 1, 6, 7, 7), (0.004 * (it + 1), 0, 0.001 * it))
+            eng.collide_and_stream(1)
+    assert np.array_equal(engines[0].download(), engines[1].download())
+    a, b = engines[0].stored_statistics(), engines[1].stored_statistics()
+    assert a[3] == b[3] and np.allclose(a[:3], b[:3], rtol=1e-12)
+    for eng in engines:
+        eng.close()
+
+
+def test_error_behaviour():
+    import palabos_b200 as pb
+    lat = pb.Lattice(19, "f64", 6, 6, 6, "BGK", 1.0)
+    with pytest.raises(pb.PlbError):
+        lat.define_dynamics((0, 6, 0, 5, 0, 5), "BB", 1.0)         # box outside the lattice
+    with pytest.raises(pb.PlbError):
+        lat.upload(np.zeros((6, 6, 6, 18)))                        # wrong size
+    lat.add_velocity_boundary("local", 2, 1, (1, 4, 1, 4, 5, 5))
+    with pytest.raises(pb.PlbError):
+        lat.add_velocity_boundary("local", 2, 1, (1, 4, 1, 4, 5, 5))   # nested composite dynamics
+    with pytest.raises(pb.PlbError):
+        pb.Lattice(13, "f64", 4, 4, 4, "BGK", 1.0)
+    lat.close()
+
+
+def test_coprocessor_surface_bgk_pure_block():
+    """The reference's own plug-in contract (coProcessors/coProcessor3D.h:59-116): addDomain / send /
+    collideAndStream / receive on a pure BGK block; the result is defined away from the outer layer."""
+    import ctypes
+    import palabos_b200 as pb
+    from scenario import OracleEngine
+    L = pb.lib()
+    nx, ny, nz, omega = 9, 8, 7, 1.3
+    rng = np.random.default_rng(10)
+    pops = (rng.random((nx, ny, nz, 19)) - 0.5) * 1e-2
+    h = ctypes.c_int()
+    assert L.plb_b200_coproc_add_domain(8, nx, ny, nz, omega, ctypes.byref(h)) == 1
+    box = (ctypes.c_int * 6)(0, nx - 1, 0, ny - 1, 0, nz - 1)
+    assert L.plb_b200_coproc_send(h.value, box, pops.ctypes.data_as(ctypes.c_void_p), pops.nbytes) == 1
+    assert L.plb_b200_coproc_collide_and_stream(h.value) == 1
+    out = np.empty_like(pops)
+    assert L.plb_b200_coproc_receive(h.value, box, out.ctypes.data_as(ctypes.c_void_p), out.nbytes) == 1
+    assert L.plb_b200_coproc_remove_domain(h.value) == 1
+    o = OracleEngine(19, "f64", nx, ny, nz, "BGK", omega)
+    o.upload(pops); o.collide_and_stream(1)
+    want = o.download(); o.close()
+    assert np.array_equal(out[1:-1, 1:-1, 1:-1], want[1:-1, 1:-1, 1:-1])
+    assert np.array_equal(out, want)        # we also reproduce the reference's rim rule
