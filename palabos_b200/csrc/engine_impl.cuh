@@ -47,7 +47,8 @@ class LatticeImpl : public LatticeBase {
         std::vector<BcRec> recs;
         std::vector<Group> groups;
         std::unordered_map<int, int> cellToRec;
-        std::vector<int> stageOffsets;     ///< items of stage s are [stageOffsets[s], stageOffsets[s+1])
+        std::vector<int> stageOffsets;     ///< items of stage s are [stageOffsets[s], stageOffsets[s+1]) ...
+        std::vector<int> stageSplit;       ///< ... plane items first, finite-difference items from stageSplit[s]
         size_t nItems = 0;
         bool dirtyKind = true, dirtyBcIndex = true, dirtySched = true;
         int bcDirtyLo = 0, bcDirtyHi = 0;  ///< record range whose values must be re-uploaded
@@ -74,7 +75,6 @@ class LatticeImpl : public LatticeBase {
     void* dStage_ = nullptr; size_t stageCap_ = 0;
     double* dReduce_ = nullptr;              ///< small device scratch for cross-rank reductions
     ncclComm_t comm_ = nullptr;
-    int sweepOcc_[5][2][2];                  ///< cached occupancy per (MAIN, GENERIC, ODD)
     bool profiling_ = false;                 ///< CUDA events around every sweep launch (bench.py's roofline leg)
     std::vector<cudaEvent_t> profEvents_;    ///< pairs (before, after)
     size_t profUsed_ = 0;
@@ -83,7 +83,6 @@ class LatticeImpl : public LatticeBase {
 
 public:
     explicit LatticeImpl(const CreateDesc& d) : desc_(d), nx_(d.nx), ny_(d.ny), nz_(d.nz), P_(d.ny * d.nz) {
-        std::memset(sweepOcc_, 0, sizeof sweepOcc_);
         int dev = 0, nDev = 0;
         if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
             throw PlbError("no CUDA device: libplb_b200 has no CPU fallback");
@@ -674,13 +673,18 @@ private:
         }
         int nStages = 0;
         for (int s : stageOf) nStages = std::max(nStages, s + 1);
-        std::vector<int> count(nStages + 1, 0);
-        for (int s : stageOf) ++count[s + 1];
-        for (int s = 0; s < nStages; ++s) count[s + 1] += count[s];
-        sl.stageOffsets = count;
+        // bucket = 2*stage + (0 plane | 1 edge/corner)
+        std::vector<int> count(2 * nStages + 1, 0);
+        auto bucket = [&](size_t k) { return 2 * stageOf[k] + (items[k].cls == PROC_PLANE ? 0 : 1); };
+        for (size_t k = 0; k < items.size(); ++k) ++count[bucket(k) + 1];
+        for (int b = 0; b < 2 * nStages; ++b) count[b + 1] += count[b];
         std::vector<Item> sorted(items.size());
-        std::vector<int> cursor(count.begin(), count.begin() + nStages);
-        for (size_t k = 0; k < items.size(); ++k) sorted[cursor[stageOf[k]]++] = items[k];
+        std::vector<int> cursor(count.begin(), count.begin() + 2 * nStages);
+        for (size_t k = 0; k < items.size(); ++k) sorted[cursor[bucket(k)]++] = items[k];
+        sl.stageOffsets.assign(nStages + 1, 0);
+        sl.stageSplit.assign(nStages, 0);
+        for (int st = 0; st < nStages; ++st) { sl.stageOffsets[st] = count[2 * st]; sl.stageSplit[st] = count[2 * st + 1]; }
+        sl.stageOffsets[nStages] = (int)items.size();
         sl.nItems = sorted.size();
         if (sl.nItems > sl.dItemsCap) {
             if (sl.dItems) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dItems); devBytes_ -= sl.dItemsCap * sizeof(Item); }
@@ -691,7 +695,6 @@ private:
             PLB_CUDA(cudaMemcpyAsync(sl.dItems, sorted.data(), sl.nItems * sizeof(Item), cudaMemcpyHostToDevice, stream_));
             PLB_CUDA(cudaStreamSynchronize(stream_));
         }
-        if (sl.stageOffsets.empty()) sl.stageOffsets.push_back(0);
     }
 
     void sync_setup() {
@@ -746,13 +749,10 @@ private:
     template <int MAIN, bool GEN, bool ODD>
     void launch_sweep_as(Slab& sl, SweepArgs<T>& a, int mainIdx) {
         auto kern = sweep_kernel<T, Q, MAIN, GEN, ODD>;
-        int& occ = sweepOcc_[mainIdx][GEN][ODD];
-        if (!occ) {
-            PLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SWEEP_THREADS, 0));
-            if (occ < 1) occ = 1;
-        }
-        const int nTiles = (a.cellEnd - a.cellBegin + SWEEP_THREADS - 1) / SWEEP_THREADS;
-        const int grid = std::max(1, std::min(nTiles, numSMs_ * occ));
+        constexpr int threads = sweep_threads(ODD);
+        const int nTiles = (a.cellEnd - a.cellBegin + threads - 1) / threads;
+        const int grid = std::max(1, std::min(nTiles, numSMs_ * sweep_grid_factor(ODD)));
+        (void)mainIdx;
         if (grid > sl.partialsCap) {
             if (sl.dPartials) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dPartials); devBytes_ -= (size_t)sl.partialsCap * 4 * sizeof(double); }
             sl.partialsCap = std::max(grid, numSMs_ * 16);
@@ -764,7 +764,7 @@ private:
             while (profEvents_.size() < profUsed_ + 2) { cudaEvent_t e; PLB_CUDA(cudaEventCreate(&e)); profEvents_.push_back(e); }
             PLB_CUDA(cudaEventRecord(profEvents_[profUsed_], stream_));
         }
-        kern<<<grid, SWEEP_THREADS, 0, stream_>>>(a);
+        kern<<<grid, threads, 0, stream_>>>(a);
         launched();
         if (prof) { PLB_CUDA(cudaEventRecord(profEvents_[profUsed_ + 1], stream_)); profUsed_ += 2; }
     }
@@ -795,10 +795,17 @@ private:
         for (Slab& sl : slabs_) {
             const int nStages = (int)sl.stageOffsets.size() - 1;
             for (int s = 0; s < nStages; ++s) {
-                const int first = sl.stageOffsets[s], n = sl.stageOffsets[s + 1] - first;
-                if (n <= 0) continue;
-                boundary_stage_kernel<T, Q><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
-                launched();
+                const int first = sl.stageOffsets[s], split = sl.stageSplit[s], last = sl.stageOffsets[s + 1];
+                if (split > first) {
+                    const int n = split - first;
+                    plane_stage_kernel<T, Q><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
+                    launched();
+                }
+                if (last > split) {
+                    const int n = last - split;
+                    fd_stage_kernel<T, Q><<<(n + 63) / 64, 64, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + split, n);
+                    launched();
+                }
             }
         }
     }
@@ -810,8 +817,8 @@ private:
     /// (below) and slab g+1 (above):
     ///   after an even step (layout SWAPPED):  g's last plane, slots c_x=-1   -> low ghost plane of g+1
     ///                                         g+1's first plane, slots c_x=+1 -> high ghost plane of g
-    ///   after an odd step (layout NORMAL):    high ghost of g, slots c_x=+1   -> first plane of g+1
-    ///                                         low ghost of g+1, slots c_x=-1  -> last plane of g
+    ///   after an odd step (layout NORMAL):    high ghost of g, slots c_x=+1   -> low ghost of g+1 -> (unpack) first plane of g+1
+    ///                                         low ghost of g+1, slots c_x=-1  -> high ghost of g  -> (unpack) last plane of g
     void exchange() {
         if (G_ == 1) return;
         const int nFaces = per_[0] ? G_ : G_ - 1;
@@ -829,8 +836,9 @@ private:
                     if (part == 0) { srcG = gLo; srcPlane = 2; dstG = gHi; dstPlane = 0; }
                     else           { srcG = gHi; srcPlane = 1; dstG = gLo; dstPlane = 3; }
                 } else {
-                    if (part == 1) { srcG = gLo; srcPlane = 3; dstG = gHi; dstPlane = 1; }
-                    else           { srcG = gHi; srcPlane = 0; dstG = gLo; dstPlane = 2; }
+                    // ghost -> ghost; unpack_halo_kernel then moves the valid entries onto the boundary plane
+                    if (part == 1) { srcG = gLo; srcPlane = 3; dstG = gHi; dstPlane = 0; }
+                    else           { srcG = gHi; srcPlane = 0; dstG = gLo; dstPlane = 3; }
                 }
                 Slab* src = find_slab(srcG);
                 Slab* dst = find_slab(dstG);
@@ -850,6 +858,14 @@ private:
             }
         }
         if (remote) n->check(n->GroupEnd(), "ncclGroupEnd");
+        if (!swapped_) {
+            for (Slab& sl : slabs_) {
+                const Geo g = geo(sl);
+                const unsigned grid = (unsigned)((P_ + 127) / 128);
+                if (g.lowMode == XMODE_GHOST) { unpack_halo_kernel<T, Q><<<grid, 128, 0, stream_>>>(sl.F, g, 0); launched(); }
+                if (g.highMode == XMODE_GHOST) { unpack_halo_kernel<T, Q><<<grid, 128, 0, stream_>>>(sl.F, g, 1); launched(); }
+            }
+        }
     }
 
     static int c_of(int i, int d) { return Q == 19 ? c19(i, d) : c27(i, d); }

@@ -24,6 +24,41 @@
 
 namespace plb200 {
 
+// Launch shape and cache policy of the sweep.  The defaults are the measured optimum on B200 for
+// D3Q19 fp64 at 512^3 (profiles/sweep_lab_r01.md): the even (local) half runs 512-thread blocks, the odd
+// (neighbour) half 256-thread blocks with an L2 prefetch one grid stride ahead; both use many more
+// blocks than are resident (grid = SMs x factor), which staggers the load / compute / store phases
+// of the resident blocks.  The macros exist for tools/sweep_lab.cu, which explores the alternatives.
+#ifndef PLB_SWEEP_THREADS_EVEN
+#define PLB_SWEEP_THREADS_EVEN 512
+#endif
+#ifndef PLB_SWEEP_THREADS_ODD
+#define PLB_SWEEP_THREADS_ODD 256
+#endif
+#ifndef PLB_SWEEP_PF_EVEN       // L2 prefetch distance in grid strides (0 = off)
+#define PLB_SWEEP_PF_EVEN 0
+#endif
+#ifndef PLB_SWEEP_PF_ODD
+#define PLB_SWEEP_PF_ODD 1
+#endif
+#ifndef PLB_SWEEP_GRID_EVEN     // blocks per SM in the grid
+#define PLB_SWEEP_GRID_EVEN 64
+#endif
+#ifndef PLB_SWEEP_GRID_ODD
+#define PLB_SWEEP_GRID_ODD 16
+#endif
+#ifndef PLB_SWEEP_LD
+#define PLB_SWEEP_LD(p) (*(p))
+#endif
+#ifndef PLB_SWEEP_ST
+#define PLB_SWEEP_ST(p, v) (*(p) = (v))
+#endif
+__host__ __device__ constexpr int sweep_threads(bool odd) { return odd ? PLB_SWEEP_THREADS_ODD : PLB_SWEEP_THREADS_EVEN; }
+__host__ __device__ constexpr int sweep_minblocks(bool odd) { return 512 / sweep_threads(odd) > 0 ? 512 / sweep_threads(odd) : 1; }
+__host__ __device__ constexpr int sweep_prefetch(bool odd) { return odd ? PLB_SWEEP_PF_ODD : PLB_SWEEP_PF_EVEN; }
+__host__ __device__ constexpr int sweep_grid_factor(bool odd) { return odd ? PLB_SWEEP_GRID_ODD : PLB_SWEEP_GRID_EVEN; }
+constexpr int SWEEP_MAX_THREADS = 1024;
+
 enum XMode : int { XMODE_EDGE = 0, XMODE_GHOST = 1, XMODE_WRAP = 2 };
 
 struct Geo {
@@ -105,22 +140,42 @@ struct CellIO {
     }
     // the sweep's own forms
     __device__ __forceinline__ static void load_local(const T* __restrict__ F, const Geo& g, int c, T* f) {
-        f[I] = F[(long long)I * g.S + c];
+        f[I] = PLB_SWEEP_LD(F + ((long long)I * g.S + c));
         CellIO<T, Q, I + 1>::load_local(F, g, c, f);
     }
     __device__ __forceinline__ static void store_local_swapped(T* __restrict__ F, const Geo& g, int c, const T* f) {
-        F[(long long)LB<T, Q>::opp(I) * g.S + c] = f[I];
+        const long long k = (long long)LB<T, Q>::opp(I) * g.S + c;
+        PLB_SWEEP_ST(F + k, f[I]);
         CellIO<T, Q, I + 1>::store_local_swapped(F, g, c, f);
     }
     __device__ __forceinline__ static void load_pull(const T* __restrict__ F, const Geo& g, const Nbr& n, int c, T* f) {
-        f[I] = F[stream_target<T, Q, LB<T, Q>::opp(I)>(g, n, c)];
+        const long long k = stream_target<T, Q, LB<T, Q>::opp(I)>(g, n, c);
+        f[I] = PLB_SWEEP_LD(F + k);
         CellIO<T, Q, I + 1>::load_pull(F, g, n, c, f);
     }
     __device__ __forceinline__ static void store_push(T* __restrict__ F, const Geo& g, const Nbr& n, int c, const T* f) {
-        F[stream_target<T, Q, I>(g, n, c)] = f[I];
+        const long long k = stream_target<T, Q, I>(g, n, c);
+        PLB_SWEEP_ST(F + k, f[I]);
         CellIO<T, Q, I + 1>::store_push(F, g, n, c, f);
     }
 };
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+/// L2 prefetch of the cell that this thread will process `delta` cells further on: same slots and
+/// (for the odd half) the same neighbour offsets as the current cell -- a hint, exact away from rims.
+template <class T, int Q, bool ODD, int I = 0>
+struct CellPrefetch {
+    __device__ __forceinline__ static void run(const T* __restrict__ F, const Geo& g, const Nbr& n, int c, int delta) {
+        const long long k = ODD ? stream_target<T, Q, I>(g, n, c) : (long long)I * g.S + c;
+        prefetch_l2(F + k + delta);
+        CellPrefetch<T, Q, ODD, I + 1>::run(F, g, n, c, delta);
+    }
+};
+template <class T, int Q, bool ODD>
+struct CellPrefetch<T, Q, ODD, Q> {
+    __device__ __forceinline__ static void run(const T*, const Geo&, const Nbr&, int, int) {}
+};
+
 template <class T, int Q>
 struct CellIO<T, Q, Q> {
     __device__ __forceinline__ static void load(const T*, const Geo&, const Nbr&, int, bool, T*) {}
@@ -133,7 +188,6 @@ struct CellIO<T, Q, Q> {
 
 // ---------------------------------------------------------------------------------- the sweep
 
-constexpr int SWEEP_THREADS = 256;
 
 template <class T>
 struct SweepArgs {
@@ -154,7 +208,7 @@ struct SweepArgs {
 /// over blocks done by whichever block arrives last.
 __device__ __forceinline__ void reduce_stats(double sRho, double sU, double mU, double cnt,
                                              double* partials, unsigned int* ticket, double* out) {
-    __shared__ double sh[4][SWEEP_THREADS / 32];
+    __shared__ double sh[4][SWEEP_MAX_THREADS / 32];
     __shared__ bool isLast;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -209,8 +263,9 @@ __device__ __forceinline__ void reduce_stats(double sRho, double sU, double mU, 
 ///   GENERIC  false: every cell is entry 0, BounceBack or NoDynamics; true: any table entry per cell
 ///   ODD      which half of the AA pattern (see file header)
 template <class T, int Q, int MAIN, bool GENERIC, bool ODD>
-__global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepArgs<T> a) {
+__global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) sweep_kernel(const SweepArgs<T> a) {
     using L = LB<T, Q>;
+    constexpr int SWEEP_THREADS = sweep_threads(ODD);
     const Geo& g = a.g;
     double sRho = 0., sU = 0., mU = -DBL_MAX, cnt = 0.;
     const int nTiles = (a.cellEnd - a.cellBegin + SWEEP_THREADS - 1) / SWEEP_THREADS;
@@ -228,6 +283,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepArgs<T>
             CellIO<T, Q>::load_pull(a.F, g, n, c, f);
         } else {
             CellIO<T, Q>::load_local(a.F, g, c, f);
+        }
+        if (sweep_prefetch(ODD) > 0) {
+            const long long delta = (long long)sweep_prefetch(ODD) * gridDim.x * SWEEP_THREADS;
+            if (c + delta < a.cellEnd) CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
         }
         const int k = a.kind[c];
         T rhoBar = (T)0, uSqr = (T)0;
@@ -253,6 +312,43 @@ __global__ void __launch_bounds__(SWEEP_THREADS) sweep_kernel(const SweepArgs<T>
         }
     }
     if (a.gatherStats) reduce_stats(sRho, sU, mU, cnt, a.partials, a.ticket, a.statsOut);
+}
+
+// ------------------------------------------------------------------- envelope exchange
+
+/// Second half of the envelope exchange after an odd step.  The populations that left a slab
+/// through its face were written into its ghost plane and have been copied (cudaMemcpy / NCCL) into
+/// the ghost plane of the receiving slab; this kernel moves them onto the receiver's boundary plane
+/// -- except where the sending cell does not exist (y or z rim of a non-periodic lattice): there the
+/// receiver's own cell kept the population under the on-site rule and must not be overwritten.
+///   side 0: low face,  slots with c_x = +1, ghost plane X = 0      -> plane X = 1
+///   side 1: high face, slots with c_x = -1, ghost plane X = nxl+1  -> plane X = nxl
+template <class T, int Q, int I = 1>
+struct Unpack {
+    __device__ __forceinline__ static void run(T* __restrict__ F, const Geo& g, const Nbr& n, int side, int src, int dst) {
+        using L = LB<T, Q>;
+        constexpr int cx = L::c(I, 0), cy = L::c(I, 1), cz = L::c(I, 2);
+        if ((cx == 1 && side == 0) || (cx == -1 && side == 1)) {
+            if (nbr_valid<0, -cy, -cz>(n)) F[(long long)I * g.S + dst] = F[(long long)I * g.S + src];
+        }
+        Unpack<T, Q, I + 1>::run(F, g, n, side, src, dst);
+    }
+};
+template <class T, int Q>
+struct Unpack<T, Q, Q> {
+    __device__ __forceinline__ static void run(T*, const Geo&, const Nbr&, int, int, int) {}
+};
+
+template <class T, int Q>
+__global__ void unpack_halo_kernel(T* F, Geo g, int side) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.P) return;
+    const int y = r / g.nz, z = r - y * g.nz;
+    const int X = side == 0 ? 1 : g.nxl;
+    const Nbr n = make_nbr(g, X, y, z);
+    const int dst = X * g.P + r;
+    const int src = (side == 0 ? 0 : g.nxl + 1) * g.P + r;
+    Unpack<T, Q>::run(F, g, n, side, src, dst);
 }
 
 // ------------------------------------------------------------------- boundary processors
@@ -375,27 +471,45 @@ __device__ __forceinline__ void fd_regularize(const CellCtx<T>& cx, T* F, int c,
 /// One stage of the level-0 data processors (AtomicBlock3D::executeInternalProcessors,
 /// atomicBlock/atomicBlock3D.cpp:195-222).  The host has ordered the (processor, cell) pairs into
 /// stages such that running a stage's items concurrently equals the reference's sequential order.
+/// Plane items (local completion of the populations) and finite-difference items (outer edges and
+/// corners, which read neighbours) run in separate kernels.
+///
+/// WrappedLocalBoundaryFunctional3D::process boundaryCondition/wrappedLocalBoundaryProcessor3D.hh:42-62.
+/// The switch on (direction, orientation) lets the compiler specialise completePopulations for each
+/// of the six faces, as the reference's templates <direction, orientation> do.
 template <class T, int Q>
-__global__ void __launch_bounds__(128) boundary_stage_kernel(CellCtx<T> cx, T* F, const Item* items, int nItems) {
+__global__ void __launch_bounds__(128) plane_stage_kernel(CellCtx<T> cx, T* F, const Item* items, int nItems) {
     using L = LB<T, Q>;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nItems) return;
+    const int c = items[t].cell;
+    const int bi = cx.bcIdx[c];
+    if (bi < 0) return;
+    Bc<T> b = cx.bcs[bi];
+    const int baseType = cx.dyns[cx.kind[c]].type;
+    int X, y, z;
+    decode_cell(cx.g, c, X, y, z);
+    const Nbr n = make_nbr(cx.g, X, y, z);
+    T f[Q];
+    CellIO<T, Q>::load(F, cx.g, n, c, cx.swapped, f);
+    switch (b.dir * 2 + (b.ori > 0 ? 1 : 0)) {
+    case 0: b.dir = 0; b.ori = -1; L::complete_populations(baseType, b, f); break;
+    case 1: b.dir = 0; b.ori = +1; L::complete_populations(baseType, b, f); break;
+    case 2: b.dir = 1; b.ori = -1; L::complete_populations(baseType, b, f); break;
+    case 3: b.dir = 1; b.ori = +1; L::complete_populations(baseType, b, f); break;
+    case 4: b.dir = 2; b.ori = -1; L::complete_populations(baseType, b, f); break;
+    default: b.dir = 2; b.ori = +1; L::complete_populations(baseType, b, f); break;
+    }
+    CellIO<T, Q>::store(F, cx.g, n, c, cx.swapped, f);
+}
+
+template <class T, int Q>
+__global__ void __launch_bounds__(64) fd_stage_kernel(CellCtx<T> cx, T* F, const Item* items, int nItems) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nItems) return;
     const Item it = items[t];
     const int c = it.cell;
-    if (it.cls == PROC_PLANE) {
-        // WrappedLocalBoundaryFunctional3D::process boundaryCondition/wrappedLocalBoundaryProcessor3D.hh:42-62
-        const int bi = cx.bcIdx[c];
-        if (bi < 0) return;
-        const Bc<T> b = cx.bcs[bi];
-        const int baseType = cx.dyns[cx.kind[c]].type;
-        int X, y, z;
-        decode_cell(cx.g, c, X, y, z);
-        const Nbr n = make_nbr(cx.g, X, y, z);
-        T f[Q];
-        CellIO<T, Q>::load(F, cx.g, n, c, cx.swapped, f);
-        L::complete_populations(baseType, b, f);
-        CellIO<T, Q>::store(F, cx.g, n, c, cx.swapped, f);
-    } else if (it.cls == PROC_EDGE) {
+    if (it.cls == PROC_EDGE) {
         // OuterVelocityEdgeFunctional3D::processCell finiteDifferenceBoundaryProcessor3D.hh:164-226
         const int plane = it.a, n1 = it.b, n2 = it.c;
         const int d1 = (plane + 1) % 3, d2 = (plane + 2) % 3;
