@@ -1,0 +1,436 @@
+// include/palabos_b200/palabos3D.h -- header-only C++ mirror of the Palabos classes that a user
+// touches around ONE hot path, MultiBlockLattice3D::collideAndStream(), implemented on top of the
+// C-ABI of libplb_b200.so (include/plb_b200.h).  A simulation written against the reference
+//
+//     MultiBlockLattice3D<T,DESCRIPTOR> lattice(nx, ny, nz, new BGKdynamics<T,DESCRIPTOR>(omega));
+//     OnLatticeBoundaryCondition3D<T,DESCRIPTOR>* bc = createLocalBoundaryCondition3D<T,DESCRIPTOR>();
+//     bc->setVelocityConditionOnBlockBoundaries(lattice);
+//     setBoundaryVelocity(lattice, lattice.getBoundingBox(), Array<T,3>(0.,0.,0.));
+//     initializeAtEquilibrium(lattice, lattice.getBoundingBox(), (T)1., Array<T,3>(0.,0.,0.));
+//     lattice.initialize();
+//     for (...) { lattice.collideAndStream(); }  getStoredAverageEnergy(lattice);  computeAverageEnergy(lattice);
+//
+// compiles unchanged with `#include "palabos_b200/palabos3D.h"` and `namespace plb`, and runs the
+// sweep, the boundary processors, the envelope exchange and the statistics on the B200.  Same names,
+// argument meaning and error behaviour (a failed call throws PlbLogicException, as the reference's
+// plbLogicError does, core/runTimeDiagnostics.h:58-130).  Citations: paths under /root/reference/src.
+//
+// What is NOT here, on purpose: per-cell host access (lattice.get(x,y,z) returns a Cell& in the
+// reference; populations live in HBM, use getPopulations / setPopulations on a Box3D instead), data
+// processors written by the user, multi-grid, multi-physics, particles, I/O.
+#ifndef PALABOS_B200_PALABOS3D_H
+#define PALABOS_B200_PALABOS3D_H
+
+#include <cmath>
+#include <cstddef>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../plb_b200.h"
+
+namespace plb {
+
+typedef long plint;             // core/globalDefs.h
+typedef std::size_t pluint;
+
+/// core/runTimeDiagnostics.h:80-130
+class PlbException : public std::exception {};
+class PlbLogicException : public PlbException {
+public:
+    explicit PlbLogicException(std::string const& m) : msg(m) {}
+    virtual ~PlbLogicException() throw() {}
+    virtual const char* what() const throw() { return msg.c_str(); }
+private:
+    std::string msg;
+};
+
+namespace detail {
+inline void check(int ok) { if (!ok) throw PlbLogicException(plb_b200_last_error()); }
+}
+
+/// core/array.h
+template <typename T, int n>
+class Array {
+public:
+    Array() { for (int i = 0; i < n; ++i) data[i] = T(); }
+    Array(T a, T b, T c) { static_assert(n == 3, "3-component constructor"); data[0] = a; data[1] = b; data[2] = c; }
+    T& operator[](int i) { return data[i]; }
+    T const& operator[](int i) const { return data[i]; }
+private:
+    T data[n];
+};
+
+/// core/geometry3D.h
+struct Box3D {
+    Box3D() : x0(0), x1(0), y0(0), y1(0), z0(0), z1(0) {}
+    Box3D(plint x0_, plint x1_, plint y0_, plint y1_, plint z0_, plint z1_) : x0(x0_), x1(x1_), y0(y0_), y1(y1_), z0(z0_), z1(z1_) {}
+    plint getNx() const { return x1 - x0 + 1; }
+    plint getNy() const { return y1 - y0 + 1; }
+    plint getNz() const { return z1 - z0 + 1; }
+    plint nCells() const { return getNx() * getNy() * getNz(); }
+    Box3D enlarge(plint w) const { return Box3D(x0 - w, x1 + w, y0 - w, y1 + w, z0 - w, z1 + w); }
+    plint x0, x1, y0, y1, z0, z1;
+};
+namespace detail {
+struct CBox { int v[6]; explicit CBox(Box3D const& b) { v[0] = (int)b.x0; v[1] = (int)b.x1; v[2] = (int)b.y0; v[3] = (int)b.y1; v[4] = (int)b.z0; v[5] = (int)b.z1; } };
+}
+
+/// latticeBoltzmann/nearestNeighborLattices3D.h
+namespace descriptors {
+template <typename T> struct D3Q19Descriptor { enum { d = 3, q = 19 }; static T fullRho(T rhoBar) { return rhoBar + (T)1; } };
+template <typename T> struct D3Q27Descriptor { enum { d = 3, q = 27 }; static T fullRho(T rhoBar) { return rhoBar + (T)1; } };
+}
+
+namespace boundary { enum BcType { dirichlet }; }   // boundaryCondition/boundaryCondition.h (the others are out of scope)
+
+// ----------------------------------------------------------------------------------- dynamics
+// On the device a dynamics object is an entry (kind, parameters) of the lattice's dynamics table and
+// a compiled-in functor; these classes only carry the description (core/dynamics.h:64-266).
+
+template <typename T, template <typename U> class Descriptor>
+class Dynamics {
+public:
+    virtual ~Dynamics() {}
+    virtual Dynamics<T, Descriptor>* clone() const = 0;
+    virtual int b200Kind() const = 0;
+    virtual double b200P1() const = 0;
+    virtual double b200P2() const { return 0.; }
+    virtual T getOmega() const { return T(); }
+};
+
+#define PLB_B200_OMEGA_DYNAMICS(NAME, KIND)                                                          \
+    template <typename T, template <typename U> class Descriptor>                                      \
+    class NAME : public Dynamics<T, Descriptor> {                                                     \
+    public:                                                                                            \
+        explicit NAME(T omega_) : omega(omega_) {}                                                     \
+        virtual NAME<T, Descriptor>* clone() const { return new NAME<T, Descriptor>(*this); }          \
+        virtual int b200Kind() const { return KIND; }                                                  \
+        virtual double b200P1() const { return (double)omega; }                                        \
+        virtual T getOmega() const { return omega; }                                                   \
+    private:                                                                                           \
+        T omega;                                                                                       \
+    };
+PLB_B200_OMEGA_DYNAMICS(BGKdynamics, PLB_B200_DYN_BGK)                  // basicDynamics/isoThermalDynamics.h
+PLB_B200_OMEGA_DYNAMICS(RegularizedBGKdynamics, PLB_B200_DYN_RLB)       // basicDynamics/isoThermalDynamics.h
+PLB_B200_OMEGA_DYNAMICS(TRTdynamics, PLB_B200_DYN_TRT)                  // complexDynamics/trtDynamics.h
+#undef PLB_B200_OMEGA_DYNAMICS
+
+/// complexDynamics/smagorinskyDynamics.h: SmagorinskyBGKdynamics(omega0, cSmago)
+template <typename T, template <typename U> class Descriptor>
+class SmagorinskyBGKdynamics : public Dynamics<T, Descriptor> {
+public:
+    SmagorinskyBGKdynamics(T omega0_, T cSmago_) : omega0(omega0_), cSmago(cSmago_) {}
+    virtual SmagorinskyBGKdynamics<T, Descriptor>* clone() const { return new SmagorinskyBGKdynamics<T, Descriptor>(*this); }
+    virtual int b200Kind() const { return PLB_B200_DYN_SMAGO; }
+    virtual double b200P1() const { return (double)omega0; }
+    virtual double b200P2() const { return (double)cSmago; }
+    virtual T getOmega() const { return omega0; }
+private:
+    T omega0, cSmago;
+};
+
+/// core/dynamics.h: BounceBack(rho = T()), NoDynamics(rho = 1)
+template <typename T, template <typename U> class Descriptor>
+class BounceBack : public Dynamics<T, Descriptor> {
+public:
+    explicit BounceBack(T rho_ = T()) : rho(rho_) {}
+    virtual BounceBack<T, Descriptor>* clone() const { return new BounceBack<T, Descriptor>(*this); }
+    virtual int b200Kind() const { return PLB_B200_DYN_BOUNCEBACK; }
+    virtual double b200P1() const { return (double)rho; }
+private:
+    T rho;
+};
+template <typename T, template <typename U> class Descriptor>
+class NoDynamics : public Dynamics<T, Descriptor> {
+public:
+    explicit NoDynamics(T rho_ = (T)1) : rho(rho_) {}
+    virtual NoDynamics<T, Descriptor>* clone() const { return new NoDynamics<T, Descriptor>(*this); }
+    virtual int b200Kind() const { return PLB_B200_DYN_NODYNAMICS; }
+    virtual double b200P1() const { return (double)rho; }
+private:
+    T rho;
+};
+
+// ----------------------------------------------------------------------------------- lattice
+
+template <typename T, template <typename U> class Descriptor> class MultiBlockLattice3D;
+
+/// multiBlock/multiBlock3D.h:69-90
+template <typename T, template <typename U> class Descriptor>
+class PeriodicitySwitch3D {
+public:
+    explicit PeriodicitySwitch3D(MultiBlockLattice3D<T, Descriptor>& l) : lattice(l) { per[0] = per[1] = per[2] = false; }
+    void toggle(int direction, bool on) { per[direction] = on; push(); }
+    void toggleAll(bool on) { per[0] = per[1] = per[2] = on; push(); }
+    bool get(int direction) const { return per[direction]; }
+private:
+    void push();
+    MultiBlockLattice3D<T, Descriptor>& lattice;
+    bool per[3];
+};
+
+/// multiBlock/multiBlockLattice3D.h:72-137.  The lattice takes ownership of backgroundDynamics, as
+/// the reference does.  rank / numRanks / slabsPerRank describe the x-slab decomposition over the
+/// GPUs of one box (one process per GPU); the defaults are one GPU.
+template <typename T, template <typename U> class Descriptor>
+class MultiBlockLattice3D {
+public:
+    MultiBlockLattice3D(plint nx_, plint ny_, plint nz_, Dynamics<T, Descriptor>* backgroundDynamics,
+                        int rank = 0, int numRanks = 1, int slabsPerRank = 1)
+        : nx(nx_), ny(ny_), nz(nz_), background(backgroundDynamics), periodicitySwitch(*this), statisticsOn(true) {
+        handle = plb_b200_create_distributed(Descriptor<T>::q, (int)sizeof(T), (int)nx, (int)ny, (int)nz,
+                                             background->b200Kind(), background->b200P1(), background->b200P2(),
+                                             rank, numRanks, slabsPerRank);
+        if (!handle) { std::string m = plb_b200_last_error(); delete background; throw PlbLogicException(m); }
+    }
+    ~MultiBlockLattice3D() { plb_b200_destroy(handle); delete background; }
+
+    plint getNx() const { return nx; }
+    plint getNy() const { return ny; }
+    plint getNz() const { return nz; }
+    Box3D getBoundingBox() const { return Box3D(0, nx - 1, 0, ny - 1, 0, nz - 1); }
+    Dynamics<T, Descriptor> const& getBackgroundDynamics() const { return *background; }
+    PeriodicitySwitch3D<T, Descriptor>& periodicity() { return periodicitySwitch; }
+    void toggleInternalStatistics(bool on) { statisticsOn = on; detail::check(plb_b200_toggle_internal_statistics(handle, on ? 1 : 0)); }
+    bool isInternalStatisticsOn() const { return statisticsOn; }
+
+    /// MultiBlock3D::initialize: run the internal processors once
+    void initialize() { detail::check(plb_b200_initialize(handle)); }
+    /// multiBlock/multiBlockLattice3D.hh:318-360
+    void collideAndStream() { detail::check(plb_b200_collide_and_stream(handle, 1)); }
+    /// n steps queued at once (the host does not wait)
+    void collideAndStream(plint n) { detail::check(plb_b200_collide_and_stream(handle, (int)n)); }
+    void synchronize() { detail::check(plb_b200_synchronize(handle)); }
+
+    /// NCCL communicator for numRanks > 1: rank 0 calls getCommId(), the application broadcasts the
+    /// 128 bytes (MPI_Bcast in Palabos), everybody calls initComm().
+    static void getCommId(char id128[128]) { detail::check(plb_b200_comm_unique_id(id128)); }
+    void initComm(const char id128[128]) { detail::check(plb_b200_comm_init(handle, id128)); }
+
+    /// Populations of a box in the reference's serialization order ([x][y][z][q], f_i - t_i; what
+    /// Cell::serialize / CoProcessor3D::receive produce, core/cell.hh:103-111).
+    void getPopulations(Box3D domain, std::vector<T>& data) const {
+        detail::CBox b(domain);
+        data.resize(plb_b200_local_bytes(handle, b.v) / sizeof(T));
+        detail::check(plb_b200_download(handle, b.v, data.data(), data.size() * sizeof(T)));
+    }
+    void setPopulations(Box3D domain, std::vector<T> const& data) {
+        detail::CBox b(domain);
+        detail::check(plb_b200_upload(handle, b.v, data.data(), data.size() * sizeof(T)));
+    }
+    /// density and velocity of every cell of a box ([cells][rho,ux,uy,uz]) through Cell::computeDensity / computeVelocity
+    void getDensityVelocity(Box3D domain, std::vector<T>& rhoU) const {
+        detail::CBox b(domain);
+        rhoU.resize(plb_b200_local_bytes(handle, b.v) / sizeof(T) / Descriptor<T>::q * 4);
+        detail::check(plb_b200_compute_density_velocity(handle, b.v, rhoU.data(), rhoU.size() * sizeof(T)));
+    }
+
+    plb_b200_lattice* b200Handle() const { return handle; }
+
+private:
+    MultiBlockLattice3D(MultiBlockLattice3D const&);
+    MultiBlockLattice3D& operator=(MultiBlockLattice3D const&);
+    plint nx, ny, nz;
+    Dynamics<T, Descriptor>* background;
+    plb_b200_lattice* handle;
+    PeriodicitySwitch3D<T, Descriptor> periodicitySwitch;
+    bool statisticsOn;
+};
+
+template <typename T, template <typename U> class Descriptor>
+void PeriodicitySwitch3D<T, Descriptor>::push() {
+    detail::check(plb_b200_set_periodicity(lattice.b200Handle(), per[0], per[1], per[2]));
+}
+
+/// multiBlock/multiBlockLattice3D.hh:531-548
+template <typename T, template <typename U> class Descriptor>
+double getStoredAverageDensity(MultiBlockLattice3D<T, Descriptor> const& lattice) {
+    double s[3];
+    detail::check(plb_b200_get_stored_statistics(lattice.b200Handle(), s, 0));
+    return (double)Descriptor<T>::fullRho((T)s[0]);
+}
+template <typename T, template <typename U> class Descriptor>
+double getStoredAverageEnergy(MultiBlockLattice3D<T, Descriptor> const& lattice) {
+    double s[3];
+    detail::check(plb_b200_get_stored_statistics(lattice.b200Handle(), s, 0));
+    return 0.5 * s[1];
+}
+template <typename T, template <typename U> class Descriptor>
+double getStoredMaxVelocity(MultiBlockLattice3D<T, Descriptor> const& lattice) {
+    double s[3];
+    detail::check(plb_b200_get_stored_statistics(lattice.b200Handle(), s, 0));
+    return std::sqrt(s[2]);
+}
+
+// ------------------------------------------------------- wrappers (dataProcessors/*Wrapper3D.h)
+
+/// defineDynamics(lattice, domain, dynamics): the function takes ownership of `dynamics` (dataInitializerWrapper3D.h:163-165)
+template <typename T, template <typename U> class Descriptor>
+void defineDynamics(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain, Dynamics<T, Descriptor>* dynamics) {
+    detail::CBox b(domain);
+    int ok = plb_b200_define_dynamics_box(lattice.b200Handle(), b.v, dynamics->b200Kind(), dynamics->b200P1(), dynamics->b200P2());
+    delete dynamics;
+    detail::check(ok);
+}
+/// defineDynamics(lattice, intMask, dynamics, flag) (dataInitializerWrapper3D.h:194-200); the mask is a
+/// plain int array [nx][ny][nz] here instead of a MultiScalarField3D<int>
+template <typename T, template <typename U> class Descriptor>
+void defineDynamics(MultiBlockLattice3D<T, Descriptor>& lattice, std::vector<int> const& intMask, Dynamics<T, Descriptor>* dynamics, int whichFlag) {
+    int ok = 0;
+    if ((plint)intMask.size() == lattice.getNx() * lattice.getNy() * lattice.getNz())
+        ok = plb_b200_define_dynamics_mask(lattice.b200Handle(), intMask.data(), whichFlag, dynamics->b200Kind(), dynamics->b200P1(), dynamics->b200P2());
+    delete dynamics;
+    if (!ok && (plint)intMask.size() != lattice.getNx() * lattice.getNy() * lattice.getNz()) throw PlbLogicException("mask size does not match the lattice");
+    detail::check(ok);
+}
+template <typename T, template <typename U> class Descriptor>
+void setBoundaryVelocity(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain, Array<T, 3> velocity) {
+    detail::CBox b(domain);
+    const double u[3] = {(double)velocity[0], (double)velocity[1], (double)velocity[2]};
+    detail::check(plb_b200_set_boundary_velocity(lattice.b200Handle(), b.v, u));
+}
+template <typename T, template <typename U> class Descriptor>
+void setBoundaryDensity(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain, T rho) {
+    detail::CBox b(domain);
+    detail::check(plb_b200_set_boundary_density(lattice.b200Handle(), b.v, (double)rho));
+}
+template <typename T, template <typename U> class Descriptor>
+void initializeAtEquilibrium(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain, T density, Array<T, 3> velocity) {
+    detail::CBox b(domain);
+    const double u[3] = {(double)velocity[0], (double)velocity[1], (double)velocity[2]};
+    detail::check(plb_b200_initialize_at_equilibrium(lattice.b200Handle(), b.v, (double)density, u));
+}
+/// the functional overload: f(iX, iY, iZ, rho, u) evaluated on the host, equilibrium built on the device
+template <typename T, template <typename U> class Descriptor, class RhoUFunction>
+void initializeAtEquilibrium(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain, RhoUFunction f) {
+    std::vector<double> ru((std::size_t)domain.nCells() * 4);
+    std::size_t k = 0;
+    for (plint x = domain.x0; x <= domain.x1; ++x)
+        for (plint y = domain.y0; y <= domain.y1; ++y)
+            for (plint z = domain.z0; z <= domain.z1; ++z, ++k) {
+                T rho; Array<T, 3> u;
+                f(x, y, z, rho, u);
+                ru[4 * k] = (double)rho; ru[4 * k + 1] = (double)u[0]; ru[4 * k + 2] = (double)u[1]; ru[4 * k + 3] = (double)u[2];
+            }
+    detail::CBox b(domain);
+    detail::check(plb_b200_initialize_at_equilibrium_field(lattice.b200Handle(), b.v, ru.data()));
+}
+/// dataProcessors/dataAnalysisWrapper3D.hh:1252-1262, :1226-1230
+template <typename T, template <typename U> class Descriptor>
+T computeAverageEnergy(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain) {
+    detail::CBox b(domain);
+    double out = 0.;
+    detail::check(plb_b200_compute_average_energy(lattice.b200Handle(), b.v, &out));
+    return (T)out;
+}
+template <typename T, template <typename U> class Descriptor>
+T computeAverageEnergy(MultiBlockLattice3D<T, Descriptor>& lattice) { return computeAverageEnergy(lattice, lattice.getBoundingBox()); }
+template <typename T, template <typename U> class Descriptor>
+T computeAverageDensity(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain) {
+    detail::CBox b(domain);
+    double out = 0.;
+    detail::check(plb_b200_compute_average_density(lattice.b200Handle(), b.v, &out));
+    return (T)out;
+}
+template <typename T, template <typename U> class Descriptor>
+T computeAverageDensity(MultiBlockLattice3D<T, Descriptor>& lattice) { return computeAverageDensity(lattice, lattice.getBoundingBox()); }
+
+// ------------------------------------------- boundary conditions (boundaryCondition/boundaryCondition3D.h)
+
+template <typename T, template <typename U> class Descriptor>
+class OnLatticeBoundaryCondition3D {
+public:
+    explicit OnLatticeBoundaryCondition3D(int model_) : model(model_) {}
+    virtual ~OnLatticeBoundaryCondition3D() {}
+    virtual OnLatticeBoundaryCondition3D<T, Descriptor>* clone() const { return new OnLatticeBoundaryCondition3D<T, Descriptor>(model); }
+    typedef MultiBlockLattice3D<T, Descriptor> Lattice;
+
+#define PLB_B200_PLANE(DIR, ORI, SUFFIX)                                                                        \
+    void addVelocityBoundary##SUFFIX(Box3D domain, Lattice& lattice, boundary::BcType = boundary::dirichlet) {   \
+        detail::CBox b(domain); detail::check(plb_b200_add_velocity_boundary(lattice.b200Handle(), model, DIR, ORI, b.v)); } \
+    void addPressureBoundary##SUFFIX(Box3D domain, Lattice& lattice, boundary::BcType = boundary::dirichlet) {   \
+        detail::CBox b(domain); detail::check(plb_b200_add_pressure_boundary(lattice.b200Handle(), model, DIR, ORI, b.v)); }
+    PLB_B200_PLANE(0, -1, 0N) PLB_B200_PLANE(0, +1, 0P)
+    PLB_B200_PLANE(1, -1, 1N) PLB_B200_PLANE(1, +1, 1P)
+    PLB_B200_PLANE(2, -1, 2N) PLB_B200_PLANE(2, +1, 2P)
+#undef PLB_B200_PLANE
+
+#define PLB_B200_EDGE(PLANE, N1, N2, SUFFIX)                                                                          \
+    void addExternalVelocityEdge##SUFFIX(Box3D domain, Lattice& lattice, boundary::BcType = boundary::dirichlet) {      \
+        detail::CBox b(domain); detail::check(plb_b200_add_external_velocity_edge(lattice.b200Handle(), model, PLANE, N1, N2, b.v)); }
+    PLB_B200_EDGE(0, -1, -1, 0NN) PLB_B200_EDGE(0, -1, +1, 0NP) PLB_B200_EDGE(0, +1, -1, 0PN) PLB_B200_EDGE(0, +1, +1, 0PP)
+    PLB_B200_EDGE(1, -1, -1, 1NN) PLB_B200_EDGE(1, -1, +1, 1NP) PLB_B200_EDGE(1, +1, -1, 1PN) PLB_B200_EDGE(1, +1, +1, 1PP)
+    PLB_B200_EDGE(2, -1, -1, 2NN) PLB_B200_EDGE(2, -1, +1, 2NP) PLB_B200_EDGE(2, +1, -1, 2PN) PLB_B200_EDGE(2, +1, +1, 2PP)
+#undef PLB_B200_EDGE
+
+#define PLB_B200_CORNER(XN, YN, ZN, SUFFIX)                                                                                     \
+    void addExternalVelocityCorner##SUFFIX(plint x, plint y, plint z, Lattice& lattice, boundary::BcType = boundary::dirichlet) {  \
+        detail::check(plb_b200_add_external_velocity_corner(lattice.b200Handle(), model, XN, YN, ZN, (int)x, (int)y, (int)z)); }
+    PLB_B200_CORNER(-1, -1, -1, NNN) PLB_B200_CORNER(-1, -1, +1, NNP) PLB_B200_CORNER(-1, +1, -1, NPN) PLB_B200_CORNER(-1, +1, +1, NPP)
+    PLB_B200_CORNER(+1, -1, -1, PNN) PLB_B200_CORNER(+1, -1, +1, PNP) PLB_B200_CORNER(+1, +1, -1, PPN) PLB_B200_CORNER(+1, +1, +1, PPP)
+#undef PLB_B200_CORNER
+
+    /// boundaryCondition3D.h:416-434 (three overloads), implementation boundaryCondition3D.hh:64-162
+    void setVelocityConditionOnBlockBoundaries(Lattice& lattice, boundary::BcType bcType = boundary::dirichlet) {
+        setVelocityConditionOnBlockBoundaries(lattice, lattice.getBoundingBox(), lattice.getBoundingBox(), bcType);
+    }
+    void setVelocityConditionOnBlockBoundaries(Lattice& lattice, Box3D applicationDomain, boundary::BcType bcType = boundary::dirichlet) {
+        setVelocityConditionOnBlockBoundaries(lattice, lattice.getBoundingBox(), applicationDomain, bcType);
+    }
+    void setVelocityConditionOnBlockBoundaries(Lattice& lattice, Box3D block, Box3D applicationDomain, boundary::BcType = boundary::dirichlet) {
+        detail::CBox b(block), a(applicationDomain);
+        detail::check(plb_b200_set_velocity_condition_on_block_boundaries(lattice.b200Handle(), model, b.v, a.v));
+    }
+private:
+    int model;
+};
+
+/// boundaryCondition3D.hh:1162-1167 ("Wrapped regularized") and zouHeBoundary3D.hh:338-350
+template <typename T, template <typename U> class Descriptor>
+OnLatticeBoundaryCondition3D<T, Descriptor>* createLocalBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<T, Descriptor>(PLB_B200_BC_LOCAL); }
+template <typename T, template <typename U> class Descriptor>
+OnLatticeBoundaryCondition3D<T, Descriptor>* createZouHeBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<T, Descriptor>(PLB_B200_BC_ZOUHE); }
+
+// ------------------------------------------------ the reference's plug-in (coProcessors/coProcessor3D.h)
+
+/// coProcessor3D.h:59-116, verbatim interface
+template <typename T>
+class CoProcessor3D {
+public:
+    virtual ~CoProcessor3D() {}
+    virtual int addDomain(plint nx, plint ny, plint nz, T omega, int& domainHandle) = 0;
+    virtual int send(int domainHandle, Box3D const& subDomain, std::vector<char> const& data) = 0;
+    virtual int receive(int domainHandle, Box3D const& subDomain, std::vector<char>& data) const = 0;
+    virtual int collideAndStream(int domainHandle) = 0;
+};
+
+/// What global::defaultCoProcessor3D<T>() (coProcessor3D.h:179-186) should return instead of the
+/// commented-out D3Q19CudaCoProcessor3D (coProcessor3D.hh:82-434): see INTEGRATION.md.
+template <typename T>
+class B200CoProcessor3D : public CoProcessor3D<T> {
+public:
+    virtual int addDomain(plint nx, plint ny, plint nz, T omega, int& domainHandle) {
+        return plb_b200_coproc_add_domain((int)sizeof(T), (int)nx, (int)ny, (int)nz, (double)omega, &domainHandle);
+    }
+    virtual int send(int domainHandle, Box3D const& subDomain, std::vector<char> const& data) {
+        detail::CBox b(subDomain);
+        return plb_b200_coproc_send(domainHandle, b.v, data.data(), data.size());
+    }
+    virtual int receive(int domainHandle, Box3D const& subDomain, std::vector<char>& data) const {
+        detail::CBox b(subDomain);
+        data.resize((std::size_t)subDomain.nCells() * 19 * sizeof(T));      // "it is the responsibility of the receive method to resize"
+        return plb_b200_coproc_receive(domainHandle, b.v, data.data(), data.size());
+    }
+    virtual int collideAndStream(int domainHandle) { return plb_b200_coproc_collide_and_stream(domainHandle); }
+};
+
+namespace global {
+template <typename T>
+inline CoProcessor3D<T>& defaultCoProcessor3D() {
+    static B200CoProcessor3D<T> singleton;
+    return singleton;
+}
+}
+
+}  // namespace plb
+#endif
