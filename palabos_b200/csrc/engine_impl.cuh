@@ -9,6 +9,7 @@
 // Citations are relative to /root/reference/src.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 #include <vector>
@@ -50,7 +51,10 @@ class LatticeImpl : public LatticeBase {
         std::vector<int> stageOffsets;     ///< items of stage s are [stageOffsets[s], stageOffsets[s+1]) ...
         std::vector<int> stageSplit;       ///< ... plane items first, finite-difference items from stageSplit[s]
         size_t nItems = 0;
+        int* dSparse = nullptr; size_t dSparseCap = 0;
+        int nSparse = 0;                   ///< cells listed for the sweep's list blocks (z-face plane cells and their sector mates)
         bool dirtyKind = true, dirtyBcIndex = true, dirtySched = true;
+        bool kindUnflagged = true;         ///< dKind was uploaded from hKind and carries no KIND_PLANE flags
         int bcDirtyLo = 0, bcDirtyHi = 0;  ///< record range whose values must be re-uploaded
     };
 
@@ -65,6 +69,9 @@ class LatticeImpl : public LatticeBase {
     bool dirtyDyns_ = true;
     std::vector<Proc> procs_;
     bool swapped_ = false;
+    bool allowFuse_ = true;                  ///< PLB_B200_EAGER_PLANES=1 in the environment turns the fusion off (A/B tests)
+    bool fused_ = false;                     ///< stage-0 plane items are completed by the next sweep, not by plane_stage_kernel
+    bool pending_ = false;                   ///< ... and that completion is currently outstanding in storage
     bool statsOn_ = true;
     bool anySetup_ = false;
     bool stepped_ = false;
@@ -80,6 +87,9 @@ class LatticeImpl : public LatticeBase {
     size_t profUsed_ = 0;
 
     static constexpr size_t STAGE_BYTES = size_t(256) << 20;
+    static constexpr size_t XFER_CHUNK_BYTES = size_t(64) << 20;   ///< one of the two upload/download staging halves
+    cudaStream_t copyStream_ = nullptr;
+    cudaEvent_t copied_[2] = {nullptr, nullptr}, transposed_[2] = {nullptr, nullptr};
 
 public:
     explicit LatticeImpl(const CreateDesc& d) : desc_(d), nx_(d.nx), ny_(d.ny), nz_(d.nz), P_(d.ny * d.nz) {
@@ -92,6 +102,7 @@ public:
         G_ = d.nRanks * d.slabsPerRank;
         if (G_ > nx_) throw PlbError("more slabs than x-planes");
         if ((long long)ny_ * nz_ >= (1ll << 30)) throw PlbError("y-z plane too large");
+        if (const char* e = std::getenv("PLB_B200_EAGER_PLANES")) allowFuse_ = !(e[0] == '1');
         add_dyn(d.dynamics, d.p1, d.p2);     // entry 0: the background dynamics
         for (int s = 0; s < d.slabsPerRank; ++s) {
             Slab sl;
@@ -121,12 +132,16 @@ public:
     ~LatticeImpl() override {
         cudaStreamSynchronize(stream_);
         for (Slab& sl : slabs_) {
-            cudaFree(sl.F); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems);
+            cudaFree(sl.F); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems); cudaFree(sl.dSparse);
             cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket);
         }
         cudaFree(dDyns_); cudaFree(dStage_); cudaFree(dReduce_);
         if (comm_) NcclApi::get().CommDestroy(comm_);
         for (cudaEvent_t e : profEvents_) cudaEventDestroy(e);
+        if (copyStream_) {
+            cudaStreamDestroy(copyStream_);
+            for (int k = 0; k < 2; ++k) { cudaEventDestroy(copied_[k]); cudaEventDestroy(transposed_[k]); }
+        }
     }
 
     // ------------------------------------------------------------------------------ plumbing
@@ -283,6 +298,7 @@ public:
         const T v[3] = {(T)u[0], (T)u[1], (T)u[2]};
         for_records_in(box, [&](Bc<T>& b) {
             if (L::is_rho_plane(b.kind)) return false;
+            if (std::memcmp(b.u, v, sizeof v) == 0) return false;      // unchanged: nothing to re-upload
             b.u[0] = v[0]; b.u[1] = v[1]; b.u[2] = v[2];
             return true;
         });
@@ -293,6 +309,7 @@ public:
         const T rb = (T)rho - (T)1;
         for_records_in(box, [&](Bc<T>& b) {
             if (!L::is_rho_plane(b.kind)) return false;
+            if (std::memcmp(&b.rhoBar, &rb, sizeof rb) == 0) return false;
             b.rhoBar = rb;
             return true;
         });
@@ -301,6 +318,7 @@ public:
     void initialize_at_equilibrium(const int box[6], double rho, const double u[3]) override {
         check_box(box);
         sync_setup();
+        materialize();
         for (Slab& sl : slabs_) {
             BoxL b;
             if (!local_box(sl, box, b)) continue;
@@ -315,6 +333,7 @@ public:
         check_box(box);
         if (!ru) throw PlbError("null field");
         sync_setup();
+        materialize();
         const long long rowCells = (long long)(box[3] - box[2] + 1) * (box[5] - box[4] + 1);
         for (Slab& sl : slabs_) {
             BoxL b;
@@ -358,6 +377,7 @@ public:
         check_box(box);
         if (bytes != local_bytes(box) / Q * 4) throw PlbError("buffer size does not match the box");
         sync_setup();
+        materialize();
         char* host = (char*)out;
         for (Slab& sl : slabs_) {
             BoxL b;
@@ -388,6 +408,7 @@ public:
         for (int s = 0; s < n; ++s) {
             for (Slab& sl : slabs_) launch_sweep(sl);
             swapped_ = !swapped_;
+            pending_ = false;                  // the sweep has applied the outstanding completion
             exchange();
             run_processors();
             stepped_ = true;
@@ -522,7 +543,7 @@ private:
     CellCtx<T> ctx(const Slab& sl) const {
         CellCtx<T> c;
         c.F = sl.F; c.kind = sl.dKind; c.bcIdx = sl.dBcIdx; c.dyns = dDyns_; c.bcs = sl.dBcs;
-        c.g = geo(sl); c.swapped = swapped_;
+        c.g = geo(sl); c.swapped = swapped_; c.pending = pending_;
         return c;
     }
 
@@ -537,7 +558,7 @@ private:
         if (type == DYN_SMAGO) { cs = (T)p2; d.preFactor = L::smago_prefactor(d.omega, cs); }
         for (size_t k = 0; k < dyns_.size(); ++k)
             if (std::memcmp(&dyns_[k], &d, sizeof d) == 0 && dynCs_[k] == cs) return (int)k;
-        if (dyns_.size() >= 256) throw PlbError("too many distinct dynamics (256)");
+        if (dyns_.size() > (size_t)KIND_MASK) throw PlbError("too many distinct dynamics (64)");
         dyns_.push_back(d);
         dynCs_.push_back(cs);
         dirtyDyns_ = true;
@@ -681,6 +702,34 @@ private:
         std::vector<Item> sorted(items.size());
         std::vector<int> cursor(count.begin(), count.begin() + 2 * nStages);
         for (size_t k = 0; k < items.size(); ++k) sorted[cursor[bucket(k)]++] = items[k];
+        // stage-0 plane cells that do not (nearly) fill the 32-cell piece a warp of the sweep covers -- one
+        // per warp on a z-face -- are listed for the sweep's list blocks together with the cells that
+        // share their sector; see sweep_kernel
+        std::vector<int> sparse;
+        if (nStages > 0 && count[1] > count[0]) {
+            std::unordered_map<int, int> perPiece;
+            for (int k = count[0]; k < count[1]; ++k) ++perPiece[(sorted[k].cell - P_) / 32];
+            const int G = PLB_SPARSE_GROUP;
+            const int lo = P_, hi = (sl.nxl + 1) * P_;
+            for (int k = count[0]; k < count[1]; ++k) {
+                const int cell = sorted[k].cell;
+                if (perPiece[(cell - P_) / 32] >= 16) continue;
+                const int g0 = cell / G * G;
+                for (int c2 = std::max(g0, lo); c2 < std::min(g0 + G, hi); ++c2) sparse.push_back(c2);
+            }
+            std::sort(sparse.begin(), sparse.end());
+            sparse.erase(std::unique(sparse.begin(), sparse.end()), sparse.end());
+        }
+        sl.nSparse = (int)sparse.size();
+        if (sparse.size() > sl.dSparseCap) {
+            if (sl.dSparse) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dSparse); devBytes_ -= sl.dSparseCap * sizeof(int); }
+            sl.dSparse = (int*)dev_alloc(sparse.size() * sizeof(int));
+            sl.dSparseCap = sparse.size();
+        }
+        if (!sparse.empty()) {
+            PLB_CUDA(cudaMemcpyAsync(sl.dSparse, sparse.data(), sparse.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+            PLB_CUDA(cudaStreamSynchronize(stream_));
+        }
         sl.stageOffsets.assign(nStages + 1, 0);
         sl.stageSplit.assign(nStages, 0);
         for (int st = 0; st < nStages; ++st) { sl.stageOffsets[st] = count[2 * st]; sl.stageSplit[st] = count[2 * st + 1]; }
@@ -697,7 +746,29 @@ private:
         }
     }
 
+    /// Run the outstanding plane completion as a pass of its own (what the eager path does after
+    /// every step).  Needed before anything changes its inputs (boundary records, dynamics, uploaded
+    /// or re-initialised populations) and before the populations are read back in bulk.
+    void materialize() {
+        if (!pending_) return;
+        for (Slab& sl : slabs_) {
+            if (sl.stageOffsets.size() < 2) continue;
+            const int first = sl.stageOffsets[0], split = sl.stageSplit[0];
+            if (split > first) {
+                const int n = split - first;
+                plane_stage_kernel<T, Q><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
+                launched();
+            }
+        }
+        pending_ = false;
+    }
+
     void sync_setup() {
+        bool anyDirty = dirtyDyns_;
+        for (Slab& sl : slabs_) anyDirty = anyDirty || sl.dirtyKind || sl.dirtyBcIndex || sl.dirtySched || sl.bcDirtyHi > sl.bcDirtyLo;
+        if (!anyDirty) return;
+        materialize();                         // with the device state the completion was deferred under
+        bool reflag = false;
         if (dirtyDyns_) {
             PLB_CUDA(cudaMemcpyAsync(dDyns_, dyns_.data(), dyns_.size() * sizeof(Dyn<T>), cudaMemcpyHostToDevice, stream_));
             PLB_CUDA(cudaStreamSynchronize(stream_));
@@ -708,6 +779,7 @@ private:
                 PLB_CUDA(cudaMemcpyAsync(sl.dKind, sl.hKind.data(), (size_t)sl.cellsStore, cudaMemcpyHostToDevice, stream_));
                 PLB_CUDA(cudaStreamSynchronize(stream_));
                 sl.dirtyKind = false;
+                sl.kindUnflagged = true;
             }
             if (sl.dirtyBcIndex) {
                 // records keep their position (dead ones are simply not indexed)
@@ -740,7 +812,33 @@ private:
                 PLB_CUDA(cudaStreamSynchronize(stream_));
                 sl.bcDirtyLo = sl.bcDirtyHi = 0;
             }
-            if (sl.dirtySched) { build_schedule(sl); sl.dirtySched = false; }
+            if (sl.dirtySched) { build_schedule(sl); sl.dirtySched = false; reflag = true; }
+            if (sl.kindUnflagged) reflag = true;
+        }
+        if (reflag) {
+            // fuse when every plane item is in stage 0, i.e. no processor of the reference's sequence
+            // reads or writes a plane cell before its completion runs (then "complete on load" == eager)
+            fused_ = allowFuse_;
+            for (Slab& sl : slabs_)
+                for (size_t s = 1; s + 1 < sl.stageOffsets.size(); ++s)
+                    if (sl.stageSplit[s] > sl.stageOffsets[s]) fused_ = false;
+            for (Slab& sl : slabs_) {
+                if (!sl.kindUnflagged) {   // drop flags of an earlier schedule
+                    PLB_CUDA(cudaMemcpyAsync(sl.dKind, sl.hKind.data(), (size_t)sl.cellsStore, cudaMemcpyHostToDevice, stream_));
+                    PLB_CUDA(cudaStreamSynchronize(stream_));
+                }
+                sl.kindUnflagged = false;
+                if (!fused_ || sl.stageOffsets.size() < 2) continue;
+                const int n = sl.stageSplit[0] - sl.stageOffsets[0];
+                if (n > 0) {
+                    flag_plane_cells_kernel<<<(n + 255) / 256, 256, 0, stream_>>>(sl.dItems + sl.stageOffsets[0], n, sl.dKind);
+                    launched();
+                    if (sl.nSparse > 0) {
+                        flag_sparse_cells_kernel<<<(sl.nSparse + 255) / 256, 256, 0, stream_>>>(sl.dSparse, sl.nSparse, sl.dKind);
+                        launched();
+                    }
+                }
+            }
         }
     }
 
@@ -748,11 +846,19 @@ private:
 
     template <int MAIN, bool GEN, bool ODD>
     void launch_sweep_as(Slab& sl, SweepArgs<T>& a, int mainIdx) {
-        auto kern = sweep_kernel<T, Q, MAIN, GEN, ODD>;
+        if (a.applyPlanes) launch_sweep_with<MAIN, GEN, ODD, true>(sl, a, mainIdx);
+        else launch_sweep_with<MAIN, GEN, ODD, false>(sl, a, mainIdx);
+    }
+
+    template <int MAIN, bool GEN, bool ODD, bool PLANES>
+    void launch_sweep_with(Slab& sl, SweepArgs<T>& a, int mainIdx) {
+        auto kern = sweep_kernel<T, Q, MAIN, GEN, ODD, PLANES>;
         constexpr int threads = sweep_threads(ODD);
         const int nTiles = (a.cellEnd - a.cellBegin + threads - 1) / threads;
-        const int grid = std::max(1, std::min(nTiles, numSMs_ * sweep_grid_factor(ODD)));
+        int grid = std::max(1, std::min(nTiles, numSMs_ * sweep_grid_factor(ODD)));
         (void)mainIdx;
+        a.nListBlocks = PLANES ? (a.nSparse + threads - 1) / threads : 0;
+        grid += a.nListBlocks;
         if (grid > sl.partialsCap) {
             if (sl.dPartials) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dPartials); devBytes_ -= (size_t)sl.partialsCap * 4 * sizeof(double); }
             sl.partialsCap = std::max(grid, numSMs_ * 16);
@@ -772,7 +878,10 @@ private:
     void launch_sweep(Slab& sl) {
         SweepArgs<T> a;
         a.F = sl.F; a.kind = sl.dKind; a.dyns = dDyns_; a.g = geo(sl);
+        a.bcIdx = sl.dBcIdx; a.bcs = sl.dBcs;
+        a.applyPlanes = (pending_ && sl.stageOffsets.size() >= 2 && sl.stageSplit[0] > sl.stageOffsets[0]) ? 1 : 0;
         a.cellBegin = P_; a.cellEnd = (sl.nxl + 1) * P_;
+        a.sparseCells = sl.dSparse; a.nSparse = a.applyPlanes ? sl.nSparse : 0; a.nListBlocks = 0;
         a.omega = dyns_[0].omega; a.preFactor = dyns_[0].preFactor;
         a.gatherStats = statsOn_ ? 1 : 0;
         a.partials = nullptr; a.ticket = sl.dTicket; a.statsOut = sl.dStats;
@@ -792,11 +901,13 @@ private:
     }
 
     void run_processors() {
+        materialize();                         // processors run twice in a row (initialize() called again)
+        if (fused_) pending_ = true;           // stage-0 plane items: left to the next sweep; later readers complete on the fly
         for (Slab& sl : slabs_) {
             const int nStages = (int)sl.stageOffsets.size() - 1;
             for (int s = 0; s < nStages; ++s) {
                 const int first = sl.stageOffsets[s], split = sl.stageSplit[s], last = sl.stageOffsets[s + 1];
-                if (split > first) {
+                if (split > first && !(fused_ && s == 0)) {
                     const int n = split - first;
                     plane_stage_kernel<T, Q><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
                     launched();
@@ -889,35 +1000,60 @@ private:
 
     // ----------------------------------------------------------------------- transfer, analysis
 
+    /// upload / download in the CoProcessor3D wire format.  The AoS <-> SoA transposition runs on the
+    /// device; chunks alternate between two staging buffers so that the PCIe copy of one chunk (copy
+    /// stream) overlaps the transposition kernel of the other (lattice stream).
     void transfer(const int box[6], void* data, size_t bytes, bool up) {
         check_box(box);
         if (bytes != local_bytes(box)) throw PlbError("buffer size does not match the box");
         if (!data && bytes) throw PlbError("null buffer");
         sync_setup();
+        materialize();
+        if (!copyStream_) {
+            PLB_CUDA(cudaStreamCreateWithFlags(&copyStream_, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; ++k) {
+                PLB_CUDA(cudaEventCreateWithFlags(&copied_[k], cudaEventDisableTiming));
+                PLB_CUDA(cudaEventCreateWithFlags(&transposed_[k], cudaEventDisableTiming));
+            }
+        }
+        const size_t half = std::max(XFER_CHUNK_BYTES, (size_t)(box[3] - box[2] + 1) * (box[5] - box[4] + 1) * Q * sizeof(T));
+        char* st = (char*)stage(2 * half);
         char* host = (char*)data;
+        int chunk = 0;
         for (Slab& sl : slabs_) {
             BoxL b;
             if (!local_box(sl, box, b)) continue;
             const size_t planeBytes = (size_t)b.ny() * b.nz() * Q * sizeof(T);
-            const int planesPerChunk = (int)std::max<size_t>(1, STAGE_BYTES / planeBytes);
-            for (int X = b.X0; X <= b.X1; X += planesPerChunk) {
+            const int planesPerChunk = (int)std::max<size_t>(1, half / planeBytes);
+            for (int X = b.X0; X <= b.X1; X += planesPerChunk, ++chunk) {
                 BoxL cb = b;
                 cb.X0 = X; cb.X1 = std::min(b.X1, X + planesPerChunk - 1);
                 const size_t nb = (size_t)cb.cells() * Q * sizeof(T);
-                T* st = (T*)stage(nb);
+                const int k = chunk & 1;
+                T* buf = (T*)(st + k * half);
                 const unsigned grid = (unsigned)((cb.cells() + 127) / 128);
                 if (up) {
-                    PLB_CUDA(cudaMemcpyAsync(st, host, nb, cudaMemcpyHostToDevice, stream_));
-                    transfer_kernel<T, Q, true><<<grid, 128, 0, stream_>>>(ctx(sl), sl.F, cb, st);
+                    if (chunk >= 2) PLB_CUDA(cudaStreamWaitEvent(copyStream_, transposed_[k], 0));   // buffer free again
+                    PLB_CUDA(cudaMemcpyAsync(buf, host, nb, cudaMemcpyHostToDevice, copyStream_));
+                    PLB_CUDA(cudaEventRecord(copied_[k], copyStream_));
+                    PLB_CUDA(cudaStreamWaitEvent(stream_, copied_[k], 0));
+                    transfer_kernel<T, Q, true><<<grid, 128, 0, stream_>>>(ctx(sl), sl.F, cb, buf);
+                    launched();
+                    PLB_CUDA(cudaEventRecord(transposed_[k], stream_));
                 } else {
-                    transfer_kernel<T, Q, false><<<grid, 128, 0, stream_>>>(ctx(sl), sl.F, cb, st);
-                    PLB_CUDA(cudaMemcpyAsync(host, st, nb, cudaMemcpyDeviceToHost, stream_));
+                    if (chunk >= 2) PLB_CUDA(cudaStreamWaitEvent(stream_, copied_[k], 0));
+                    transfer_kernel<T, Q, false><<<grid, 128, 0, stream_>>>(ctx(sl), sl.F, cb, buf);
+                    launched();
+                    PLB_CUDA(cudaEventRecord(transposed_[k], stream_));
+                    PLB_CUDA(cudaStreamWaitEvent(copyStream_, transposed_[k], 0));
+                    PLB_CUDA(cudaMemcpyAsync(host, buf, nb, cudaMemcpyDeviceToHost, copyStream_));
+                    PLB_CUDA(cudaEventRecord(copied_[k], copyStream_));
                 }
-                launched();
-                PLB_CUDA(cudaStreamSynchronize(stream_));
                 host += nb;
             }
         }
+        PLB_CUDA(cudaStreamSynchronize(copyStream_));
+        PLB_CUDA(cudaStreamSynchronize(stream_));
     }
 
     double box_sum(const int box[6], int what) {

@@ -61,6 +61,18 @@ constexpr int SWEEP_MAX_THREADS = 1024;
 
 enum XMode : int { XMODE_EDGE = 0, XMODE_GHOST = 1, XMODE_WRAP = 2 };
 
+/// Per-cell kind byte: bits 0-5 = index into the dynamics table, bit 7 = the cell carries a plane
+/// boundary record whose completePopulations is fused into the sweep (see "lazy completion" below).
+constexpr int KIND_MASK = 0x3f;
+constexpr int KIND_SPARSE = 0x40;   ///< the cell is processed by the list blocks of the sweep while a completion is pending
+constexpr int KIND_PLANE = 0x80;
+#ifndef PLB_LIST_PLACEMENT
+#define PLB_LIST_PLACEMENT 1        ///< list blocks: 0 interleaved with the streaming blocks, 1 after them, 2 before them
+#endif
+#ifndef PLB_SPARSE_GROUP
+#define PLB_SPARSE_GROUP 4          ///< cells per listed group (4 doubles = one 32-byte sector)
+#endif
+
 struct Geo {
     int nxl, ny, nz;      ///< owned planes, rows, columns
     int P;                ///< ny*nz cells per x-plane
@@ -128,6 +140,13 @@ __device__ __forceinline__ long long pop_index(const Geo& g, const Nbr& n, int c
     return stream_target<T, Q, L::opp(I)>(g, n, c);
 }
 
+__device__ __forceinline__ void decode_cell(const Geo& g, int c, int& X, int& y, int& z) {
+    X = c / g.P;
+    const int r = c - X * g.P;
+    y = r / g.nz;
+    z = r - y * g.nz;
+}
+
 template <class T, int Q, int I = 0>
 struct CellIO {
     __device__ __forceinline__ static void load(const T* __restrict__ F, const Geo& g, const Nbr& n, int c, bool swapped, T* f) {
@@ -189,11 +208,22 @@ struct CellIO<T, Q, Q> {
 // ---------------------------------------------------------------------------------- the sweep
 
 
+struct Item {
+    int cell;            ///< storage cell index
+    signed char cls;     ///< ProcClass
+    signed char a, b, c; ///< edge: plane, normal1, normal2; corner: xNormal, yNormal, zNormal
+};
+
 template <class T>
 struct SweepArgs {
     T* F;
     const uint8_t* kind;
     const Dyn<T>* dyns;       ///< dynamics table in global memory
+    const int* bcIdx;         ///< boundary record index per cell (read for KIND_PLANE cells only)
+    const Bc<T>* bcs;         ///< boundary records
+    int applyPlanes;          ///< the plane completion of the previous step is pending: apply it on load
+    const int* sparseCells;   ///< KIND_SPARSE cells, processed by nListBlocks blocks spread over the grid
+    int nSparse, nListBlocks;
     Geo g;
     int cellBegin, cellEnd;   ///< storage cell range [begin, end) swept by this launch
     T omega, preFactor;       ///< parameters of dynamics-table entry 0 (the lattice's background dynamics)
@@ -256,39 +286,71 @@ __device__ __forceinline__ void reduce_stats(double sRho, double sU, double mU, 
     }
 }
 
+/// completePopulations of a plane boundary cell with (direction, orientation) turned into compile-time
+/// constants, as the reference's templates <direction, orientation> have them
+/// (WrappedLocalBoundaryFunctional3D::process boundaryCondition/wrappedLocalBoundaryProcessor3D.hh:42-62).
+template <class T, int Q>
+__device__ __forceinline__ void complete_by_face(int baseType, Bc<T> b, T* f) {
+    using L = LB<T, Q>;
+    switch (b.dir * 2 + (b.ori > 0 ? 1 : 0)) {
+    case 0: b.dir = 0; b.ori = -1; L::complete_populations(baseType, b, f); break;
+    case 1: b.dir = 0; b.ori = +1; L::complete_populations(baseType, b, f); break;
+    case 2: b.dir = 1; b.ori = -1; L::complete_populations(baseType, b, f); break;
+    case 3: b.dir = 1; b.ori = +1; L::complete_populations(baseType, b, f); break;
+    case 4: b.dir = 2; b.ori = -1; L::complete_populations(baseType, b, f); break;
+    default: b.dir = 2; b.ori = +1; L::complete_populations(baseType, b, f); break;
+    }
+}
+
+/// Out-of-line form for the sweep and the on-the-fly readers: the populations travel through local
+/// memory so that the caller's register file is not sized for this rarely taken path.
+template <class T, int Q>
+__device__ __noinline__ void complete_pending(int baseType, const Bc<T>* __restrict__ bcs, int bi, T* f) {
+    complete_by_face<T, Q>(baseType, bcs[bi], f);
+}
+
 /// The fused collide-and-stream sweep (BlockLattice3D::collideAndStream, atomicBlock/blockLattice3D.hh:253-312,
 /// with Cell::collide -> Dynamics::collide inlined as a device functor and gatherStatistics,
 /// core/latticeStatistics.h:36-45, reduced per block).
 ///   MAIN     dynamics type of table entry 0, compiled in
 ///   GENERIC  false: every cell is entry 0, BounceBack or NoDynamics; true: any table entry per cell
 ///   ODD      which half of the AA pattern (see file header)
-template <class T, int Q, int MAIN, bool GENERIC, bool ODD>
+///   PLANES   the lattice has plane boundary cells whose completion is fused into the sweep ("lazy
+///            completion"): completePopulations of such a cell is a function of its own post-stream
+///            populations and its record only, so instead of a pass over the face cells after the
+///            step, the next sweep applies it to the populations it has just gathered.
+template <class T, int Q, int MAIN, bool GENERIC, bool ODD, bool PLANES>
 __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) sweep_kernel(const SweepArgs<T> a) {
     using L = LB<T, Q>;
     constexpr int SWEEP_THREADS = sweep_threads(ODD);
     const Geo& g = a.g;
     double sRho = 0., sU = 0., mU = -DBL_MAX, cnt = 0.;
-    const int nTiles = (a.cellEnd - a.cellBegin + SWEEP_THREADS - 1) / SWEEP_THREADS;
-    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-        const int c = a.cellBegin + tile * SWEEP_THREADS + threadIdx.x;
-        if (c >= a.cellEnd) continue;
-        T f[Q];
-        Nbr n;
+
+    // gather the populations that arrive at cell c
+    auto gather = [&](int c, Nbr& n, T* f) {
         if (ODD) {
-            const int X = c / g.P;
-            const int r = c - X * g.P;
-            const int y = r / g.nz;
-            const int z = r - y * g.nz;
+            int X, y, z;
+            decode_cell(g, c, X, y, z);
             n = make_nbr(g, X, y, z);
             CellIO<T, Q>::load_pull(a.F, g, n, c, f);
         } else {
             CellIO<T, Q>::load_local(a.F, g, c, f);
         }
-        if (sweep_prefetch(ODD) > 0) {
-            const long long delta = (long long)sweep_prefetch(ODD) * gridDim.x * SWEEP_THREADS;
-            if (c + delta < a.cellEnd) CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
-        }
-        const int k = a.kind[c];
+    };
+    // outstanding completePopulations of a plane boundary cell (k = its kind byte)
+    auto complete = [&](int c, int k, T* f) {
+        const int bi = a.bcIdx[c];
+        if (bi < 0) return;
+        T tmp[Q];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) tmp[i] = f[i];
+        complete_pending<T, Q>(a.dyns[k & KIND_MASK].type, a.bcs, bi, tmp);
+#pragma unroll
+        for (int i = 0; i < Q; ++i) f[i] = tmp[i];
+    };
+    // Cell::collide, scatter, gatherStatistics
+    auto collide_scatter = [&](int c, int k, const Nbr& n, T* f) {
+        k &= KIND_MASK;
         T rhoBar = (T)0, uSqr = (T)0;
         bool took;
         if (!GENERIC) {
@@ -309,6 +371,68 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
             sU += (double)uSqr;
             mU = fmax(mU, (double)uSqr);
             cnt += 1.;
+        }
+    };
+
+    // Lazy completion, lane-efficiently.  The x- and y-faces fill whole warps (z is the fastest index)
+    // and are completed in line.  A z-face puts ONE plane cell into a warp; running the ~2000-instruction
+    // completion for one lane in the streaming loop would nearly double the instruction count of the
+    // sweep.  The host therefore lists such cells (in sector-sized groups of SPARSE_GROUP neighbours,
+    // flagged KIND_SPARSE); the streaming blocks skip them, and "list" blocks interleaved with them in
+    // the same grid process the list one cell per lane.  The AA pattern allows that: within a launch each
+    // storage location is read and written by the thread of one cell only, whichever thread that is.
+    const bool planes = PLANES && a.applyPlanes;
+    int mainIdx = blockIdx.x, mainGrid = gridDim.x;
+    if (PLANES && a.nListBlocks > 0) {
+#if PLB_LIST_PLACEMENT == 0
+        const int R = (int)gridDim.x / a.nListBlocks;          // every R-th block is a list block
+        const int b = blockIdx.x;
+        const bool isList = b % R == R - 1 && b / R < a.nListBlocks;
+        const int listIdx = b / R, mainIfNot = b - min(a.nListBlocks, b / R);
+#elif PLB_LIST_PLACEMENT == 1
+        const int b = blockIdx.x, nMain = (int)gridDim.x - a.nListBlocks;
+        const bool isList = b >= nMain;
+        const int listIdx = b - nMain, mainIfNot = b;
+#else
+        const int b = blockIdx.x;
+        const bool isList = b < a.nListBlocks;
+        const int listIdx = b, mainIfNot = b - a.nListBlocks;
+#endif
+        if (isList) {
+            const int t = listIdx * SWEEP_THREADS + threadIdx.x;
+            if (t < a.nSparse) {
+                const int c = a.sparseCells[t];
+                T f[Q];
+                Nbr n;
+                gather(c, n, f);
+                const int k = a.kind[c];
+                if (k & KIND_PLANE) complete(c, k, f);
+                collide_scatter(c, k, n, f);
+            }
+            mainIdx = -1;
+        } else {
+            mainIdx = mainIfNot;
+            mainGrid = (int)gridDim.x - a.nListBlocks;
+        }
+    }
+    if (mainIdx >= 0) {
+        const int nTiles = (a.cellEnd - a.cellBegin + SWEEP_THREADS - 1) / SWEEP_THREADS;
+        for (int tile = mainIdx; tile < nTiles; tile += mainGrid) {
+            const int c = a.cellBegin + tile * SWEEP_THREADS + threadIdx.x;
+            if (c >= a.cellEnd) continue;
+            T f[Q];
+            Nbr n;
+            gather(c, n, f);
+            if (sweep_prefetch(ODD) > 0) {
+                const long long delta = (long long)sweep_prefetch(ODD) * mainGrid * SWEEP_THREADS;
+                if (c + delta < a.cellEnd) CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
+            }
+            const int k = a.kind[c];
+            if (PLANES && planes) {
+                if (k & KIND_SPARSE) continue;
+                if (k & KIND_PLANE) complete(c, k, f);
+            }
+            collide_scatter(c, k, n, f);
         }
     }
     if (a.gatherStats) reduce_stats(sRho, sU, mU, cnt, a.partials, a.ticket, a.statsOut);
@@ -353,12 +477,6 @@ __global__ void unpack_halo_kernel(T* F, Geo g, int side) {
 
 // ------------------------------------------------------------------- boundary processors
 
-struct Item {
-    int cell;            ///< storage cell index
-    signed char cls;     ///< ProcClass
-    signed char a, b, c; ///< edge: plane, normal1, normal2; corner: xNormal, yNormal, zNormal
-};
-
 template <class T>
 struct CellCtx {
     const T* F;
@@ -368,14 +486,8 @@ struct CellCtx {
     const Bc<T>* bcs;
     Geo g;
     bool swapped;
+    bool pending;        ///< plane completion is pending in storage: readers of KIND_PLANE cells apply it on the fly
 };
-
-__device__ __forceinline__ void decode_cell(const Geo& g, int c, int& X, int& y, int& z) {
-    X = c / g.P;
-    const int r = c - X * g.P;
-    y = r / g.nz;
-    z = r - y * g.nz;
-}
 
 template <class T, int Q>
 struct CellView {
@@ -389,7 +501,8 @@ struct CellView {
 template <class T, int Q>
 __device__ __forceinline__ void fetch_cell(const CellCtx<T>& cx, int c, bool needDensityPops, bool needVelocityPops, CellView<T, Q>& v) {
     using L = LB<T, Q>;
-    v.d = cx.dyns[cx.kind[c]];
+    const int kb = cx.kind[c];
+    v.d = cx.dyns[kb & KIND_MASK];
     const int bi = cx.bcIdx[c];
     v.hasBc = bi >= 0;
     if (v.hasBc) v.b = cx.bcs[bi];
@@ -401,6 +514,7 @@ __device__ __forceinline__ void fetch_cell(const CellCtx<T>& cx, int c, bool nee
         decode_cell(cx.g, c, X, y, z);
         const Nbr n = make_nbr(cx.g, X, y, z);
         CellIO<T, Q>::load(cx.F, cx.g, n, c, cx.swapped, v.f);
+        if (cx.pending && (kb & KIND_PLANE) && v.hasBc) complete_pending<T, Q>(v.d.type, cx.bcs, bi, v.f);
     } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) v.f[i] = (T)0;
@@ -479,27 +593,19 @@ __device__ __forceinline__ void fd_regularize(const CellCtx<T>& cx, T* F, int c,
 /// of the six faces, as the reference's templates <direction, orientation> do.
 template <class T, int Q>
 __global__ void __launch_bounds__(128) plane_stage_kernel(CellCtx<T> cx, T* F, const Item* items, int nItems) {
-    using L = LB<T, Q>;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nItems) return;
     const int c = items[t].cell;
     const int bi = cx.bcIdx[c];
     if (bi < 0) return;
-    Bc<T> b = cx.bcs[bi];
-    const int baseType = cx.dyns[cx.kind[c]].type;
+    const Bc<T> b = cx.bcs[bi];
+    const int baseType = cx.dyns[cx.kind[c] & KIND_MASK].type;
     int X, y, z;
     decode_cell(cx.g, c, X, y, z);
     const Nbr n = make_nbr(cx.g, X, y, z);
     T f[Q];
     CellIO<T, Q>::load(F, cx.g, n, c, cx.swapped, f);
-    switch (b.dir * 2 + (b.ori > 0 ? 1 : 0)) {
-    case 0: b.dir = 0; b.ori = -1; L::complete_populations(baseType, b, f); break;
-    case 1: b.dir = 0; b.ori = +1; L::complete_populations(baseType, b, f); break;
-    case 2: b.dir = 1; b.ori = -1; L::complete_populations(baseType, b, f); break;
-    case 3: b.dir = 1; b.ori = +1; L::complete_populations(baseType, b, f); break;
-    case 4: b.dir = 2; b.ori = -1; L::complete_populations(baseType, b, f); break;
-    default: b.dir = 2; b.ori = +1; L::complete_populations(baseType, b, f); break;
-    }
+    complete_by_face<T, Q>(baseType, b, f);
     CellIO<T, Q>::store(F, cx.g, n, c, cx.swapped, f);
 }
 
@@ -574,7 +680,7 @@ __global__ void init_equilibrium_kernel(CellCtx<T> cx, T* F, BoxL box, T rho, T 
     T u[3] = { ux, uy, uz };
     if (field) { rho = (T)field[4 * k]; u[0] = (T)field[4 * k + 1]; u[1] = (T)field[4 * k + 2]; u[2] = (T)field[4 * k + 3]; }
     T f[Q];
-    L::ini_equilibrium(cx.dyns[cx.kind[c]].type, f, rho, u);
+    L::ini_equilibrium(cx.dyns[cx.kind[c] & KIND_MASK].type, f, rho, u);
     const Nbr n = make_nbr(cx.g, X, y, z);
     CellIO<T, Q>::store(F, cx.g, n, c, cx.swapped, f);
 }
@@ -648,6 +754,16 @@ __global__ void __launch_bounds__(256) box_sum_kernel(CellCtx<T> cx, BoxL box, i
         for (int w = 1; w < (int)(blockDim.x >> 5); ++w) a += sh[w];
         partials[blockIdx.x] = a;
     }
+}
+
+/// Mark the cells of the plane items whose completion is fused into the sweep.
+static __global__ void flag_plane_cells_kernel(const Item* items, int n, uint8_t* kind) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) kind[items[t].cell] |= (uint8_t)KIND_PLANE;
+}
+static __global__ void flag_sparse_cells_kernel(const int* cells, int n, uint8_t* kind) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) kind[cells[t]] |= (uint8_t)KIND_SPARSE;
 }
 
 /// Scatter the sparse (cell -> boundary record) map into the dense per-cell index.

@@ -199,3 +199,97 @@ def test_coprocessor_surface_bgk_pure_block():
     want = o.download(); o.close()
     assert np.array_equal(out[1:-1, 1:-1, 1:-1], want[1:-1, 1:-1, 1:-1])
     assert np.array_equal(out, want)        # we also reproduce the reference's rim rule
+
+
+# ---- plane boundaries fused into the sweep ("lazy completion") against the eager
+# ---- plane_stage_kernel path of the same engine, and the cases where the fusion must not be used
+
+def _launches_per_step(sc_factory, monkeypatch, eager):
+    import palabos_b200 as pb
+    if eager:
+        monkeypatch.setenv("PLB_B200_EAGER_PLANES", "1")
+    else:
+        monkeypatch.delenv("PLB_B200_EAGER_PLANES", raising=False)
+    sc = sc_factory()
+    eng = pb.Lattice(sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2)
+    try:
+        replay(sc, eng)
+        a = eng.launch_count()
+        eng.collide_and_stream(4)
+        b = eng.launch_count()
+        return (b - a) / 4.0, eng.download(), eng.compute_density_velocity()
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("name", ["cavity_bgk_10x9x8", "cavity_zouhe_10x9x8", "inlet_outlet_local", "cavity_bgk_q27_8x8x9",
+                                  "cavity_bgk_f32_10x9x8", "obstacle_zouhe_24x12x10"])
+def test_fused_plane_completion_equals_eager_pass(name, monkeypatch):
+    fused = _launches_per_step(CASES[name][0], monkeypatch, eager=False)
+    eager = _launches_per_step(CASES[name][0], monkeypatch, eager=True)
+    assert fused[0] == eager[0] - 1, "one plane_stage launch per step must have disappeared: %r vs %r" % (fused[0], eager[0])
+    assert np.array_equal(fused[1], eager[1])
+    assert np.array_equal(fused[2], eager[2])
+
+
+def test_plane_added_after_the_edge_that_reads_it_is_not_fused():
+    """An edge processor inserted BEFORE the plane it reads sees the un-completed plane cells in the
+    reference's sequential order: the plane items land in a later stage and the fusion is off."""
+    import palabos_b200 as pb
+    from scenario import OracleEngine
+    nx, ny, nz = 8, 7, 9
+    box = (0, nx - 1, 0, ny - 1, 0, nz - 1)
+    engines = [pb.Lattice(19, "f64", nx, ny, nz, "BGK", 1.4), OracleEngine(19, "f64", nx, ny, nz, "BGK", 1.4)]
+    for eng in engines:
+        eng.add_external_velocity_edge("local", 0, 1, 1, (1, nx - 2, ny - 1, ny - 1, nz - 1, nz - 1))
+        eng.add_velocity_boundary("local", 1, 1, (1, nx - 2, ny - 1, ny - 1, 1, nz - 2))
+        eng.add_velocity_boundary("local", 2, 1, (1, nx - 2, 1, ny - 2, nz - 1, nz - 1))
+        eng.set_boundary_velocity(box, (0.01, 0, 0))
+        eng.set_boundary_velocity((1, nx - 2, 1, ny - 2, nz - 1, nz - 1), (0.03, 0.0, 0))
+        eng.initialize_at_equilibrium(box, 1.0, (0.01, 0, 0))
+        eng.initialize()
+        eng.collide_and_stream(7)
+    assert np.array_equal(engines[0].download(), engines[1].download())
+    assert np.array_equal(engines[0].compute_density_velocity(), engines[1].compute_density_velocity())
+    stages, items = engines[0].boundary_stages()
+    assert stages >= 2
+    for eng in engines:
+        eng.close()
+
+
+def test_pending_completion_survives_every_reader_and_writer():
+    """Between steps the completion is pending in storage; each API that reads or writes populations or
+    boundary records must behave as if it had been applied eagerly."""
+    import palabos_b200 as pb
+    from scenario import OracleEngine
+    sc = cavity(10, 8, 9, 0)
+    box = sc.box
+    engines = [pb.Lattice(19, "f64", 10, 8, 9, "RLB", 1.3, slabs_per_rank=2), OracleEngine(19, "f64", 10, 8, 9, "RLB", 1.3)]
+    for eng in engines:
+        eng.set_velocity_condition_on_block_boundaries("local", box, box)
+        eng.set_boundary_velocity(box, (0, 0, 0))
+        eng.set_boundary_velocity((1, 8, 1, 6, 8, 8), (0.02, 0.01, 0))
+        eng.initialize_at_equilibrium(box, 1.0, (0, 0, 0))
+        eng.initialize()
+        eng.initialize()                                               # processors twice in a row
+        eng.collide_and_stream(3)
+    energy = [eng.compute_average_energy(box) for eng in engines]              # on-the-fly completion in the reduction
+    assert energy[0] == pytest.approx(energy[1], rel=1e-13)
+    for eng in engines:
+        eng.collide_and_stream(2)
+        eng.define_dynamics((3, 5, 0, 0, 3, 4), "BB", 1.0)             # kills plane records while pending
+        eng.collide_and_stream(2)
+        eng.initialize_at_equilibrium((0, 9, 0, 7, 6, 8), 1.01, (0.0, 0.01, 0.0))   # overwrites pending cells
+        eng.collide_and_stream(1)
+        eng.set_boundary_velocity((1, 8, 1, 6, 8, 8), (0.03, 0.0, 0))
+        eng.collide_and_stream(2)
+    a, b = engines[0].download((0, 9, 0, 7, 7, 8)), engines[1].download((0, 9, 0, 7, 7, 8))
+    assert np.array_equal(a, b)
+    pops = engines[1].download()
+    for eng in engines:
+        eng.upload(pops * 0.75)                                        # upload over pending cells
+        eng.collide_and_stream(3)
+    assert np.array_equal(engines[0].download(), engines[1].download())
+    assert np.array_equal(engines[0].compute_density_velocity(), engines[1].compute_density_velocity())
+    for eng in engines:
+        eng.close()

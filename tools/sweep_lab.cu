@@ -70,10 +70,10 @@ int main(int argc, char** argv) {
     fill<<<148 * 8, 256>>>(F, nF, Q);
     CK(cudaDeviceSynchronize());
     SweepArgs<T> a;
-    a.F = F; a.kind = kind; a.dyns = dyns; a.g = g; a.cellBegin = g.P; a.cellEnd = (n + 1) * g.P;
+    a.F = F; a.kind = kind; a.dyns = dyns; a.bcIdx = nullptr; a.bcs = nullptr; a.applyPlanes = 0; a.sparseCells = nullptr; a.nSparse = 0; a.nListBlocks = 0; a.g = g; a.cellBegin = g.P; a.cellEnd = (n + 1) * g.P;
     a.omega = (T)1.2388; a.preFactor = (T)0.01; a.gatherStats = 1; a.partials = partials; a.ticket = ticket; a.statsOut = stats;
-    auto kEven = sweep_kernel<T, Q, LAB_DYN, false, false>;
-    auto kOdd = sweep_kernel<T, Q, LAB_DYN, false, true>;
+    auto kEven = sweep_kernel<T, Q, LAB_DYN, false, false, false>;
+    auto kOdd = sweep_kernel<T, Q, LAB_DYN, false, true, false>;
     int occE = 0, occO = 0, sms = 0;
     constexpr int TE = sweep_threads(false), TO = sweep_threads(true);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kEven, TE, 0));
