@@ -34,8 +34,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-Q, PREC, BYTES_PER_LU = 19, "f64", 2 * 19 * 8
 U_MAX, RE = 0.02, 100.0
+
+# BASELINE.json configs.  "cavity" (configs[1]) is the bench line the driver reads; the others are run on
+# request (--workload) and print the same line for their own config.
+WORKLOADS = {
+    "cavity":      dict(q=19, prec="f64", dyn="BGK",   scaling="weak",   shape=lambda N, n: (n * N, n, n)),
+    "channel_trt": dict(q=19, prec="f64", dyn="TRT",   scaling="strong", shape=lambda N, n: (2048, 512, 512)),
+    "obstacle":    dict(q=19, prec="f64", dyn="BGK",   scaling="strong", shape=lambda N, n: (1024, 384, 384)),
+    "les_q27_f64": dict(q=27, prec="f64", dyn="SMAGO", scaling="weak",   shape=lambda N, n: (n * N, n, n)),
+    "les_q27_f32": dict(q=27, prec="f32", dyn="SMAGO", scaling="weak",   shape=lambda N, n: (n * N, n, n)),
+}
 
 
 def cavity_omega(ny):
@@ -177,19 +186,55 @@ def our_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n = args.n
-    nx, ny, nz = n * world, n, n
-    omega = cavity_omega(ny)
-    lat = pb.Lattice(Q, PREC, nx, ny, nz, "BGK", omega, rank=rank, n_ranks=world, slabs_per_rank=1)
+    wl = WORKLOADS[args.workload]
+    Q, PREC = wl["q"], wl["prec"]
+    BYTES_PER_LU = 2 * Q * (8 if PREC == "f64" else 4)
+    nx, ny, nz = wl["shape"](world, n)
+    cavity = args.workload == "cavity"
+    if cavity:
+        omega, p2 = cavity_omega(ny), 0.0
+        what = "3D lid-driven cavity D3Q19 BGK fp64, %dx%dx%d (%d^3 per GPU), regularized velocity BC on faces/edges/corners" % (nx, ny, nz, n)
+    elif args.workload == "channel_trt":
+        omega, p2 = 1.2, 0.0
+        what = "periodic channel D3Q19 TRT fp64 (s+=1.2, s-=1.1), %dx%dx%d, periodic x,z, BounceBack walls y=0,ny-1, uniform initial flow u=0.05" % (nx, ny, nz)
+    elif args.workload == "obstacle":
+        omega, p2 = 1.5, 0.0
+        what = ("flow past a voxelised obstacle D3Q19 BGK fp64 (omega 1.5), %dx%dx%d, Zou-He velocity inlet / pressure outlet, BounceBack side walls "
+                "and obstacle voxels (analytic sphere mask)" % (nx, ny, nz))
+    else:
+        omega, p2 = 1.99, 0.14
+        what = "turbulent channel D3Q27 Smagorinsky LES %s (omega0 1.99, Cs 0.14), %dx%dx%d (%d^3 per GPU), periodic x,z, BounceBack walls" % (PREC, nx, ny, nz, n)
+    lat = pb.Lattice(Q, PREC, nx, ny, nz, wl["dyn"], omega, p2, rank=rank, n_ranks=world, slabs_per_rank=1)
     if world > 1:
         uid = [pb.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         lat.comm_init(uid[0])
     box = lat.box
     lid = (1, nx - 2, 1, ny - 2, nz - 1, nz - 1)
-    lat.set_velocity_condition_on_block_boundaries("local", box, box)
-    lat.set_boundary_velocity(box, (0, 0, 0))
-    lat.set_boundary_velocity(lid, (U_MAX, 0, 0))
-    lat.initialize_at_equilibrium(box, 1.0, (0, 0, 0))
+    if cavity:
+        lat.set_velocity_condition_on_block_boundaries("local", box, box)
+        lat.set_boundary_velocity(box, (0, 0, 0))
+        lat.set_boundary_velocity(lid, (U_MAX, 0, 0))
+        lat.initialize_at_equilibrium(box, 1.0, (0, 0, 0))
+    elif args.workload == "obstacle":
+        lat.add_velocity_boundary("zouhe", 0, -1, (0, 0, 1, ny - 2, 1, nz - 2))
+        lat.add_pressure_boundary("zouhe", 0, +1, (nx - 1, nx - 1, 1, ny - 2, 1, nz - 2))
+        for wall in ((0, nx - 1, 0, 0, 0, nz - 1), (0, nx - 1, ny - 1, ny - 1, 0, nz - 1),
+                     (0, nx - 1, 0, ny - 1, 0, 0), (0, nx - 1, 0, ny - 1, nz - 1, nz - 1)):
+            lat.define_dynamics(wall, "BB", 1.0)
+        xx, yy, zz = np.ogrid[0:nx, 0:ny, 0:nz]
+        r = min(ny, nz) / 5.0
+        mask = (((xx - nx // 3) ** 2 + (yy - (ny / 2 - 0.5)) ** 2 + (zz - (nz / 2 - 0.5)) ** 2) <= r * r).astype(np.int32)
+        lat.define_dynamics_mask(mask, 1, "BB", 1.0)
+        del mask
+        lat.set_boundary_velocity(box, (0.03, 0, 0))
+        lat.set_boundary_density(box, 1.0)
+        lat.initialize_at_equilibrium(box, 1.0, (0.03, 0, 0))
+    else:
+        lat.set_periodicity(True, False, True)
+        lat.define_dynamics((0, nx - 1, 0, 0, 0, nz - 1), "BB", 1.0)
+        lat.define_dynamics((0, nx - 1, ny - 1, ny - 1, 0, nz - 1), "BB", 1.0)
+        lat.initialize_at_equilibrium(box, 1.0, (0.05, 0, 0))
     lat.initialize()
     lat.synchronize()
 
@@ -242,13 +287,14 @@ def our_arm(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "sweep_kernel<double,19,BGK> (even/odd AA halves averaged)", "peak_source": peak_src,
+                "kernel": "sweep_kernel<%s,%d,%s> (even/odd AA halves averaged)" % ("double" if PREC == "f64" else "float", Q, wl["dyn"]),
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": BYTES_PER_LU, "cells_per_launch": cells_local,
                 "kernel_ms": sweep_ms / max(sweep_n, 1), "kernel_share_of_step": sweep_ms / ms}
 
     # ---- e2e: the same job from host buffers through the C-ABI ----------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and cavity:
         nbytes = cells_local * Q * 8
         try:
             host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
@@ -284,17 +330,16 @@ def our_arm(args):
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and cavity:
         cpu = cpu_reference_run(128, 10, 1)
 
     if rank == 0:
         line = {"metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "3D lid-driven cavity D3Q19 BGK fp64, %dx%dx%d (%d^3 per GPU), regularized velocity BC on faces/edges/corners"
-                                       % (nx, ny, nz, n),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+                "dtype": PREC, "data": "synthetic",
+                "config": {"workload": what,
                            "parallelism": "x-slabs, %d rank(s)" % world, "streaming": "in-place AA pattern",
-                           "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed" % (cells_local * Q * 8 / 1e9),
+                           "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed" % (cells_local * BYTES_PER_LU / 2 / 1e9),
                            "omega": omega, "stored_avg_energy": 0.5 * stats[1], "stored_avg_density": stats[0] + 1.0},
                 "mlups_per_gpu": value / world,
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
@@ -311,6 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=512, help="cavity edge per GPU (default: the configs[1] size)")
+    ap.add_argument("--workload", default="cavity", choices=sorted(WORKLOADS), help="BASELINE.json config (default: configs[1], the bench line)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

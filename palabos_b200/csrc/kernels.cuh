@@ -25,15 +25,14 @@
 namespace plb200 {
 
 // Launch shape and cache policy of the sweep.  The defaults are the measured optimum on B200 for
-// D3Q19 fp64 at 512^3 (profiles/sweep_lab_r01.md): the even (local) half runs 512-thread blocks, the odd
-// (neighbour) half 256-thread blocks with an L2 prefetch one grid stride ahead; both use many more
-// blocks than are resident (grid = SMs x factor), which staggers the load / compute / store phases
-// of the resident blocks.  The macros exist for tools/sweep_lab.cu, which explores the alternatives.
+// D3Q19 fp64 at 512^3 (profiles/r01_sweep_lab.log): 512-thread blocks for both halves, the odd
+// (neighbour) half with an L2 prefetch one grid stride ahead; both use many more blocks than are
+// resident (grid = SMs x factor), which staggers the load / compute / store phases of the resident blocks.  The macros exist for tools/sweep_lab.cu, which explores the alternatives.
 #ifndef PLB_SWEEP_THREADS_EVEN
 #define PLB_SWEEP_THREADS_EVEN 512
 #endif
 #ifndef PLB_SWEEP_THREADS_ODD
-#define PLB_SWEEP_THREADS_ODD 256
+#define PLB_SWEEP_THREADS_ODD 512
 #endif
 #ifndef PLB_SWEEP_PF_EVEN       // L2 prefetch distance in grid strides (0 = off)
 #define PLB_SWEEP_PF_EVEN 0
@@ -45,7 +44,7 @@ namespace plb200 {
 #define PLB_SWEEP_GRID_EVEN 64
 #endif
 #ifndef PLB_SWEEP_GRID_ODD
-#define PLB_SWEEP_GRID_ODD 16
+#define PLB_SWEEP_GRID_ODD 128
 #endif
 #ifndef PLB_SWEEP_LD
 #define PLB_SWEEP_LD(p) (*(p))
@@ -54,7 +53,12 @@ namespace plb200 {
 #define PLB_SWEEP_ST(p, v) (*(p) = (v))
 #endif
 __host__ __device__ constexpr int sweep_threads(bool odd) { return odd ? PLB_SWEEP_THREADS_ODD : PLB_SWEEP_THREADS_EVEN; }
-__host__ __device__ constexpr int sweep_minblocks(bool odd) { return 512 / sweep_threads(odd) > 0 ? 512 / sweep_threads(odd) : 1; }
+#ifndef PLB_SWEEP_REGS          // register budget per thread that the launch bounds ask the compiler to keep
+#define PLB_SWEEP_REGS 128
+#endif
+__host__ __device__ constexpr int sweep_minblocks(bool odd) {
+    return 65536 / PLB_SWEEP_REGS / sweep_threads(odd) > 0 ? 65536 / PLB_SWEEP_REGS / sweep_threads(odd) : 1;
+}
 __host__ __device__ constexpr int sweep_prefetch(bool odd) { return odd ? PLB_SWEEP_PF_ODD : PLB_SWEEP_PF_EVEN; }
 __host__ __device__ constexpr int sweep_grid_factor(bool odd) { return odd ? PLB_SWEEP_GRID_ODD : PLB_SWEEP_GRID_EVEN; }
 constexpr int SWEEP_MAX_THREADS = 1024;
@@ -147,6 +151,8 @@ __device__ __forceinline__ void decode_cell(const Geo& g, int c, int& X, int& y,
     z = r - y * g.nz;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <class T, int Q, int I = 0>
 struct CellIO {
     __device__ __forceinline__ static void load(const T* __restrict__ F, const Geo& g, const Nbr& n, int c, bool swapped, T* f) {
@@ -177,8 +183,30 @@ struct CellIO {
         PLB_SWEEP_ST(F + k, f[I]);
         CellIO<T, Q, I + 1>::store_push(F, g, n, c, f);
     }
+    // interior cells (every neighbour exists at its plain offset): the slot base plus the neighbour offset
+    // is the same for the whole launch, the address is that uniform base plus the cell index.  (Passing the
+    // Q byte offsets in the constant bank makes the addresses cheaper still -- 2 instead of ~7 instructions
+    // -- but the leaner instruction stream issues the 19 loads in a tighter burst and measured SLOWER,
+    // 6.84 vs 6.67 ms at 512^3: profiles/r01_sweep_lab.log.)
+    __device__ __forceinline__ static long long interior_target(const Geo& g) {
+        using L = LB<T, Q>;
+        return (long long)I * g.S + (L::c(I, 0) * g.P + L::c(I, 1) * g.nz + L::c(I, 2));
+    }
+    __device__ __forceinline__ static void load_pull_interior(const T* __restrict__ F, const Geo& g, int c, T* f) {
+        const T* base = F + CellIO<T, Q, LB<T, Q>::opp(I)>::interior_target(g);
+        f[I] = PLB_SWEEP_LD(base + c);
+        CellIO<T, Q, I + 1>::load_pull_interior(F, g, c, f);
+    }
+    __device__ __forceinline__ static void store_push_interior(T* __restrict__ F, const Geo& g, int c, const T* f) {
+        T* base = F + interior_target(g);
+        PLB_SWEEP_ST(base + c, f[I]);
+        CellIO<T, Q, I + 1>::store_push_interior(F, g, c, f);
+    }
+    __device__ __forceinline__ static void prefetch_interior(const T* __restrict__ F, const Geo& g, int c) {
+        prefetch_l2(F + interior_target(g) + c);
+        CellIO<T, Q, I + 1>::prefetch_interior(F, g, c);
+    }
 };
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 /// L2 prefetch of the cell that this thread will process `delta` cells further on: same slots and
 /// (for the odd half) the same neighbour offsets as the current cell -- a hint, exact away from rims.
@@ -203,6 +231,9 @@ struct CellIO<T, Q, Q> {
     __device__ __forceinline__ static void store_local_swapped(T*, const Geo&, int, const T*) {}
     __device__ __forceinline__ static void load_pull(const T*, const Geo&, const Nbr&, int, T*) {}
     __device__ __forceinline__ static void store_push(T*, const Geo&, const Nbr&, int, const T*) {}
+    __device__ __forceinline__ static void load_pull_interior(const T*, const Geo&, int, T*) {}
+    __device__ __forceinline__ static void store_push_interior(T*, const Geo&, int, const T*) {}
+    __device__ __forceinline__ static void prefetch_interior(const T*, const Geo&, int) {}
 };
 
 // ---------------------------------------------------------------------------------- the sweep
@@ -326,13 +357,16 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
     const Geo& g = a.g;
     double sRho = 0., sU = 0., mU = -DBL_MAX, cnt = 0.;
 
-    // gather the populations that arrive at cell c
-    auto gather = [&](int c, Nbr& n, T* f) {
+    // gather the populations that arrive at cell c = (X, y, z); `interior` (odd half): every neighbour
+    // of the cell exists at its plain offset, so no per-population validity / wrap-around logic is needed
+    auto gather = [&](int c, bool interior, int X, int y, int z, Nbr& n, T* f) {
         if (ODD) {
-            int X, y, z;
-            decode_cell(g, c, X, y, z);
-            n = make_nbr(g, X, y, z);
-            CellIO<T, Q>::load_pull(a.F, g, n, c, f);
+            if (interior) {
+                CellIO<T, Q>::load_pull_interior(a.F, g, c, f);
+            } else {
+                n = make_nbr(g, X, y, z);
+                CellIO<T, Q>::load_pull(a.F, g, n, c, f);
+            }
         } else {
             CellIO<T, Q>::load_local(a.F, g, c, f);
         }
@@ -349,7 +383,7 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
         for (int i = 0; i < Q; ++i) f[i] = tmp[i];
     };
     // Cell::collide, scatter, gatherStatistics
-    auto collide_scatter = [&](int c, int k, const Nbr& n, T* f) {
+    auto collide_scatter = [&](int c, int k, bool interior, const Nbr& n, T* f) {
         k &= KIND_MASK;
         T rhoBar = (T)0, uSqr = (T)0;
         bool took;
@@ -364,8 +398,12 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
             const Dyn<T> d = a.dyns[k];
             took = L::collide_any(d, f, rhoBar, uSqr);
         }
-        if (ODD) CellIO<T, Q>::store_push(a.F, g, n, c, f);
-        else CellIO<T, Q>::store_local_swapped(a.F, g, c, f);
+        if (ODD) {
+            if (interior) CellIO<T, Q>::store_push_interior(a.F, g, c, f);
+            else CellIO<T, Q>::store_push(a.F, g, n, c, f);
+        } else {
+            CellIO<T, Q>::store_local_swapped(a.F, g, c, f);
+        }
         if (took) {
             sRho += (double)rhoBar;
             sU += (double)uSqr;
@@ -404,10 +442,12 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
                 const int c = a.sparseCells[t];
                 T f[Q];
                 Nbr n;
-                gather(c, n, f);
+                int X = 0, y = 0, z = 0;
+                if (ODD) decode_cell(g, c, X, y, z);
+                gather(c, false, X, y, z, n, f);
                 const int k = a.kind[c];
                 if (k & KIND_PLANE) complete(c, k, f);
-                collide_scatter(c, k, n, f);
+                collide_scatter(c, k, false, n, f);
             }
             mainIdx = -1;
         } else {
@@ -418,21 +458,36 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
     if (mainIdx >= 0) {
         const int nTiles = (a.cellEnd - a.cellBegin + SWEEP_THREADS - 1) / SWEEP_THREADS;
         for (int tile = mainIdx; tile < nTiles; tile += mainGrid) {
-            const int c = a.cellBegin + tile * SWEEP_THREADS + threadIdx.x;
+            const int tileBegin = a.cellBegin + tile * SWEEP_THREADS;      // block-uniform
+            const int c = tileBegin + threadIdx.x;
             if (c >= a.cellEnd) continue;
+            bool interior = false;
+            int X = 0, y = 0, z = 0;
+            if (ODD) {
+                // decode the first cell of the warp's 32; if the 32 lie in one row of interior y, clear of the
+                // row ends, in a plane whose x-neighbours are plain planes, the whole warp takes the fast path
+                decode_cell(g, tileBegin + (int)(threadIdx.x & ~31u), X, y, z);
+                interior = z > 0 && z + 32 < g.nz && y > 0 && y < g.ny - 1
+                        && (X > 1 || g.lowMode == XMODE_GHOST) && (X < g.nxl || g.highMode == XMODE_GHOST);
+                z += (int)(threadIdx.x & 31u);
+                if (z >= g.nz) decode_cell(g, c, X, y, z);
+            }
             T f[Q];
             Nbr n;
-            gather(c, n, f);
+            gather(c, interior, X, y, z, n, f);
             if (sweep_prefetch(ODD) > 0) {
                 const long long delta = (long long)sweep_prefetch(ODD) * mainGrid * SWEEP_THREADS;
-                if (c + delta < a.cellEnd) CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
+                if (c + delta < a.cellEnd) {
+                    if (ODD && interior) CellIO<T, Q>::prefetch_interior(a.F, g, c + (int)delta);
+                    else CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
+                }
             }
             const int k = a.kind[c];
             if (PLANES && planes) {
                 if (k & KIND_SPARSE) continue;
                 if (k & KIND_PLANE) complete(c, k, f);
             }
-            collide_scatter(c, k, n, f);
+            collide_scatter(c, k, interior, n, f);
         }
     }
     if (a.gatherStats) reduce_stats(sRho, sU, mU, cnt, a.partials, a.ticket, a.statsOut);

@@ -293,3 +293,34 @@ def test_pending_completion_survives_every_reader_and_writer():
     assert np.array_equal(engines[0].compute_density_velocity(), engines[1].compute_density_velocity())
     for eng in engines:
         eng.close()
+
+
+@pytest.mark.parametrize("shape,slabs", [((5, 6, 100), 1), ((7, 5, 131), 2), ((4, 4, 300), 1)])
+def test_long_rows_take_the_interior_fast_path_of_the_odd_half(shape, slabs):
+    """Rows longer than a warp: the odd (neighbour) half of the AA sweep addresses whole warps of interior
+    cells through launch-uniform slot bases; rims, wrap-around and ghost planes take the general path."""
+    import palabos_b200 as pb
+    from scenario import OracleEngine
+    nx, ny, nz = shape
+    box = (0, nx - 1, 0, ny - 1, 0, nz - 1)
+    rng = np.random.default_rng(10)
+    pops = (rng.random((nx, ny, nz, 19)) - 0.5) * 1e-2
+    for periodic in ((False, False, False), (True, True, True), (True, False, True)):
+        engines = [pb.Lattice(19, "f64", nx, ny, nz, "BGK", 1.7, slabs_per_rank=slabs), OracleEngine(19, "f64", nx, ny, nz, "BGK", 1.7)]
+        for eng in engines:
+            eng.set_periodicity(*periodic)
+            if not any(periodic):
+                eng.set_velocity_condition_on_block_boundaries("local", box, box)
+                eng.set_boundary_velocity(box, (0, 0, 0))
+                eng.set_boundary_velocity((1, nx - 2, 1, ny - 2, nz - 1, nz - 1), (0.02, 0, 0))
+            else:
+                eng.define_dynamics((0, nx - 1, 2, 2, 10, 60), "BB", 1.0)
+            eng.upload(pops)
+            eng.initialize()
+            eng.collide_and_stream(5)
+        assert np.array_equal(engines[0].download(), engines[1].download()), periodic
+        for eng in engines:
+            eng.collide_and_stream(4)
+        assert np.array_equal(engines[0].download(), engines[1].download()), periodic
+        for eng in engines:
+            eng.close()

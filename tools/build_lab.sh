@@ -2,16 +2,16 @@
 # builds the sweep_lab variants (development tool); usage: tools/build_lab.sh
 set -e
 cd "$(dirname "$0")/.."
+mkdir -p tools/bin
 rm -f tools/bin/lab_*
 NV="nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Ipalabos_b200/csrc tools/sweep_lab.cu"
-build() { name=$1; shift; $NV "$@" -o tools/bin/lab_$name & }
-build default
-build e512pf0_o512pf1 -DPLB_SWEEP_THREADS_ODD=512
-build e256pf0_o128pf1 -DPLB_SWEEP_THREADS_EVEN=256 -DPLB_SWEEP_THREADS_ODD=128
-build e512pf1_o256pf2 -DPLB_SWEEP_PF_EVEN=1 -DPLB_SWEEP_PF_ODD=2
-build f32 -DLAB_T=float
-build q27 -DLAB_Q=27
-build q27f32 -DLAB_Q=27 -DLAB_T=float
-build trt -DLAB_DYN=DYN_TRT
-wait
+build() { local nm=$1; shift; $NV "$@" -o tools/bin/lab_$nm & }
+for cfg in "q27 -DLAB_Q=27" "q27f32 -DLAB_Q=27 -DLAB_T=float" "f32 -DLAB_T=float" "q27smago -DLAB_Q=27 -DLAB_DYN=DYN_SMAGO"; do
+  set -- $cfg; name=$1; shift
+  build ${name}_t512r128 "$@"
+  build ${name}_t384r168 "$@" -DPLB_SWEEP_THREADS_EVEN=384 -DPLB_SWEEP_THREADS_ODD=384 -DPLB_SWEEP_REGS=168
+  build ${name}_t256r255 "$@" -DPLB_SWEEP_THREADS_EVEN=256 -DPLB_SWEEP_THREADS_ODD=256 -DPLB_SWEEP_REGS=255
+  build ${name}_t256r128 "$@" -DPLB_SWEEP_THREADS_EVEN=256 -DPLB_SWEEP_THREADS_ODD=256
+  wait
+done
 ls tools/bin

@@ -12,7 +12,7 @@ while [ $# -gt 1 ]; do
   rm -rf $d/palabos_b200/csrc/build
   cp -r include/* $d/include/
   cp bench.py MEASURED_PEAKS.json $d/ 2>/dev/null || true
-  cp -r tests $d/tests
+  cp -r tests $d/tests; mkdir -p $d/oracle; cp oracle/liboracle.so oracle/Makefile oracle/plb_oracle* $d/oracle/
   for v in f64_q27 f32_q19 f32_q27; do
     printf '#include "engine.h"\nnamespace plb200 { LatticeBase* make_lattice_%s(const CreateDesc&) { throw PlbError("not in this variant build"); } }\n' $v > $d/palabos_b200/csrc/inst_$v.cu
   done
