@@ -6,12 +6,8 @@ mkdir -p tools/bin
 rm -f tools/bin/lab_*
 NV="nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Ipalabos_b200/csrc tools/sweep_lab.cu"
 build() { local nm=$1; shift; $NV "$@" -o tools/bin/lab_$nm & }
-for cfg in "q27 -DLAB_Q=27" "q27f32 -DLAB_Q=27 -DLAB_T=float" "f32 -DLAB_T=float" "q27smago -DLAB_Q=27 -DLAB_DYN=DYN_SMAGO"; do
-  set -- $cfg; name=$1; shift
-  build ${name}_t512r128 "$@"
-  build ${name}_t384r168 "$@" -DPLB_SWEEP_THREADS_EVEN=384 -DPLB_SWEEP_THREADS_ODD=384 -DPLB_SWEEP_REGS=168
-  build ${name}_t256r255 "$@" -DPLB_SWEEP_THREADS_EVEN=256 -DPLB_SWEEP_THREADS_ODD=256 -DPLB_SWEEP_REGS=255
-  build ${name}_t256r128 "$@" -DPLB_SWEEP_THREADS_EVEN=256 -DPLB_SWEEP_THREADS_ODD=256
-  wait
-done
+for p in 0 1 2 3 4 5; do build pol$p -DLAB_POLICY=$p; done
+build pol0pf0 -DPLB_SWEEP_PF_ODD=0
+build pol5pf0 -DLAB_POLICY=5 -DPLB_SWEEP_PF_ODD=0
+wait
 ls tools/bin

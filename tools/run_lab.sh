@@ -2,5 +2,5 @@
 # runs the built sweep_lab variants (on the GPU box); output to gpurun_out/lab.log
 mkdir -p gpurun_out
 {
-for b in tools/bin/lab_*; do for g in 32 128; do timeout 120 $b ${1:-512} 5 $g $g; done; done
+for b in tools/bin/lab_*; do for g in 64 128; do echo -n "$(basename $b) "; timeout 120 $b ${1:-512} 5 64 $g; done; done
 } 2>&1 | tee gpurun_out/lab.log
