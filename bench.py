@@ -200,7 +200,7 @@ def our_arm(args):
     elif args.workload == "obstacle":
         omega, p2 = 1.5, 0.0
         what = ("flow past a voxelised obstacle D3Q19 BGK fp64 (omega 1.5), %dx%dx%d, Zou-He velocity inlet / pressure outlet, BounceBack side walls "
-                "and obstacle voxels (analytic sphere mask)" % (nx, ny, nz))
+                "and on the voxels of ball.stl" % (nx, ny, nz))
     else:
         omega, p2 = 1.99, 0.14
         what = "turbulent channel D3Q27 Smagorinsky LES %s (omega0 1.99, Cs 0.14), %dx%dx%d (%d^3 per GPU), periodic x,z, BounceBack walls" % (PREC, nx, ny, nz, n)
@@ -222,9 +222,16 @@ def our_arm(args):
         for wall in ((0, nx - 1, 0, 0, 0, nz - 1), (0, nx - 1, ny - 1, ny - 1, 0, nz - 1),
                      (0, nx - 1, 0, ny - 1, 0, 0), (0, nx - 1, 0, ny - 1, nz - 1, nz - 1)):
             lat.define_dynamics(wall, "BB", 1.0)
-        xx, yy, zz = np.ogrid[0:nx, 0:ny, 0:nz]
-        r = min(ny, nz) / 5.0
-        mask = (((xx - nx // 3) ** 2 + (yy - (ny / 2 - 0.5)) ** 2 + (zz - (nz / 2 - 0.5)) ** 2) <= r * r).astype(np.int32)
+        # the obstacle: the reference's ball.stl (its triangles are kept with the golden voxel matrices), scaled to 40 % of
+        # the channel height and voxelised on the device (plb_b200_mesh_to_lattice + plb_b200_voxelize); inside and
+        # innerBorder voxels become BounceBack, as defineDynamics(lattice, voxelMatrix, flag, BounceBack) does
+        soup = np.load(os.path.join(ROOT, "tests", "golden", "voxel_ball_40.npz"))["soup"]
+        tri, vdims, _, _ = pb.mesh_to_lattice(soup, int(0.4 * min(ny, nz)), 0, 4)
+        flags, vox_ms = pb.voxelize(tri, vdims, 1, return_ms=True)
+        mask = np.zeros((nx, ny, nz), dtype=np.int32)
+        ox, oy, oz = nx // 3 - vdims[0] // 2, (ny - vdims[1]) // 2, (nz - vdims[2]) // 2
+        mask[ox:ox + vdims[0], oy:oy + vdims[1], oz:oz + vdims[2]] = (flags >= 3)
+        what += "; voxelizer: %d triangles -> %dx%dx%d flags in %.3f ms on the device" % ((tri.shape[0],) + tuple(vdims) + (vox_ms,))
         lat.define_dynamics_mask(mask, 1, "BB", 1.0)
         del mask
         lat.set_boundary_velocity(box, (0.03, 0, 0))

@@ -155,6 +155,26 @@ int plb_b200_boundary_stages(plb_b200_lattice* L, int* n_stages, int64_t* n_item
 int plb_b200_profile_sweeps(plb_b200_lattice* L, int on);
 int plb_b200_profile_read(plb_b200_lattice* L, double* total_ms, int* n_launches);
 
+/* ---- geometry side of the path: STL -> voxel flags --------------------------------- */
+
+/* voxelize(mesh, domain, borderWidth) offLattice/voxelizer.hh:107-142 + detectBorderLine :640-690, on the device.
+ * triangles: double [n][3 vertices][x,y,z] in lattice units (what TriangularSurfaceMesh hands to the voxelizer);
+ * flags_out: int32 [nx][ny][nz] (host), voxelFlag values offLattice/voxelizer.h:38-48: 1 outside, 2 outerBorder,
+ * 3 inside, 4 innerBorder.  kernel_ms (optional): device time of the kernels.  The matrix is what
+ * defineDynamics(lattice, mask, flag, dynamics) (plb_b200_define_dynamics_mask) takes. */
+int plb_b200_voxelize(const double* triangles, int64_t n_triangles, int nx, int ny, int nz, int border_width,
+                      int32_t* flags_out, double* kernel_ms);
+/* TriangleSet<T>(fileName, FLT) offLattice/triangleSet.hh:130-260: ASCII or binary STL -> float [n][3][3]
+ * (malloc'ed, release with plb_b200_stl_free) */
+int plb_b200_stl_read(const char* path, float** soup, int64_t* n_triangles);
+void plb_b200_stl_free(float* soup);
+/* DEFscaledMesh(triangleSet, resolution, referenceDirection, margin, extraLayer) offLattice/triangleBoundary3D.hh:255-301
+ * followed by TriangularSurfaceMesh::inflate(inflate) triangularSurfaceMesh.hh:1419-1425 (reference default 1e-3):
+ * triangles_out double [n][3][3] in lattice units, dims = size of the voxel matrix (voxelizer.hh:84-104),
+ * dx / location = physical size of a cell and position of lattice node (0,0,0). */
+int plb_b200_mesh_to_lattice(const float* soup, int64_t n_triangles, int resolution, int reference_direction, int margin,
+                             int extra_layer, double inflate, double* triangles_out, int dims[3], double* dx, double location[3]);
+
 /* ---- the reference's own plug-in surface: plb::CoProcessor3D<T> (coProcessor3D.h:59-116) ------------- */
 /* D3Q19 BGK only, domain = whole block incl. envelope, result undefined in the outer 1-cell layer.
  * These four are what global::defaultCoProcessor3D<T>() (coProcessor3D.h:179-186) should forward to. */

@@ -39,6 +39,7 @@ SYMBOLS = [
     "plb_b200_compute_density_velocity", "plb_b200_launch_count", "plb_b200_device_bytes",
     "plb_b200_boundary_stages", "plb_b200_profile_sweeps", "plb_b200_profile_read", "plb_b200_coproc_add_domain", "plb_b200_coproc_send",
     "plb_b200_coproc_receive", "plb_b200_coproc_collide_and_stream", "plb_b200_coproc_remove_domain",
+    "plb_b200_voxelize", "plb_b200_stl_read", "plb_b200_stl_free", "plb_b200_mesh_to_lattice",
 ]
 
 
@@ -109,6 +110,11 @@ def lib():
         L.plb_b200_coproc_receive.argtypes = [ci, vp, vp, ctypes.c_size_t]
         L.plb_b200_coproc_collide_and_stream.argtypes = [ci]
         L.plb_b200_coproc_remove_domain.argtypes = [ci]
+        L.plb_b200_voxelize.argtypes = [vp, ctypes.c_int64, ci, ci, ci, ci, vp, vp]
+        L.plb_b200_stl_read.argtypes = [ctypes.c_char_p, vp, vp]
+        L.plb_b200_stl_free.restype = None
+        L.plb_b200_stl_free.argtypes = [vp]
+        L.plb_b200_mesh_to_lattice.argtypes = [vp, ctypes.c_int64, ci, ci, ci, ci, cd, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -123,6 +129,44 @@ def _box(b):
 
 def _vec(u):
     return (ctypes.c_double * 3)(*[float(v) for v in u])
+
+
+def _ck(ok):
+    if not ok:
+        raise PlbError(lib().plb_b200_last_error().decode())
+
+
+def stl_read(path):
+    """Triangles of an ASCII or binary STL file as float32 [n,3,3] (TriangleSet<T>(fileName, FLT))."""
+    ptr, n = ctypes.c_void_p(), ctypes.c_int64()
+    _ck(lib().plb_b200_stl_read(str(path).encode(), ctypes.byref(ptr), ctypes.byref(n)))
+    try:
+        buf = (ctypes.c_float * (n.value * 9)).from_address(ptr.value) if n.value else []
+        return np.array(buf, dtype=np.float32).reshape(-1, 3, 3)
+    finally:
+        lib().plb_b200_stl_free(ptr)
+
+
+def mesh_to_lattice(soup, resolution, reference_direction, margin, extra_layer=0, inflate=1e-3):
+    """DEFscaledMesh + inflate: returns (triangles float64 [n,3,3] in lattice units, dims, dx, location)."""
+    soup = np.ascontiguousarray(soup, dtype=np.float32).reshape(-1, 3, 3)
+    tri = np.empty(soup.shape, dtype=np.float64)
+    dims, dx, loc = (ctypes.c_int * 3)(), ctypes.c_double(), (ctypes.c_double * 3)()
+    _ck(lib().plb_b200_mesh_to_lattice(soup.ctypes.data_as(ctypes.c_void_p), soup.shape[0], int(resolution), int(reference_direction),
+                                       int(margin), int(extra_layer), float(inflate), tri.ctypes.data_as(ctypes.c_void_p),
+                                       dims, ctypes.byref(dx), loc))
+    return tri, tuple(dims), dx.value, tuple(loc)
+
+
+def voxelize(triangles, dims, border_width=1, return_ms=False):
+    """voxelize(mesh, domain, borderWidth) + detectBorderLine on the device: int32 [nx,ny,nz] of voxelFlag values."""
+    tri = np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1, 3, 3)
+    nx, ny, nz = [int(d) for d in dims]
+    flags = np.empty((nx, ny, nz), dtype=np.int32)
+    ms = ctypes.c_double()
+    _ck(lib().plb_b200_voxelize(tri.ctypes.data_as(ctypes.c_void_p), tri.shape[0], nx, ny, nz, int(border_width),
+                                flags.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ms)))
+    return (flags, ms.value) if return_ms else flags
 
 
 def slab_range(nx, n_slabs, slab):

@@ -17,6 +17,7 @@ struct plb_b200_lattice { LatticeBase* impl; };
 static thread_local std::string g_err;
 
 static int fail(const std::string& m) { g_err = m; return 0; }
+namespace plb200 { int set_last_error(const std::string& m) { return fail(m); } }
 
 #define PLB_TRY(L, body)                                           \
     if (!(L) || !(L)->impl) return fail("null lattice handle");    \

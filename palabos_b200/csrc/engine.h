@@ -68,6 +68,9 @@ LatticeBase* make_lattice_f64_q27(const CreateDesc&);
 LatticeBase* make_lattice_f32_q19(const CreateDesc&);
 LatticeBase* make_lattice_f32_q27(const CreateDesc&);
 
+/// Record the message plb_b200_last_error() returns on this thread; returns 0 (the failure code of the ABI).
+int set_last_error(const std::string& m);
+
 /// Balanced x-slabs: slab s of n owns [s*nx/n, (s+1)*nx/n).
 inline void slab_range(int nx, int nSlabs, int slab, int& x0, int& x1) {
     x0 = (int)((long long)slab * nx / nSlabs);
