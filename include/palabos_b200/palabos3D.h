@@ -25,6 +25,7 @@
 #include <cstddef>
 #include <stdexcept>
 #include <string>
+#include <memory>
 #include <vector>
 #include "../plb_b200.h"
 
@@ -423,6 +424,103 @@ public:
     }
     virtual int collideAndStream(int domainHandle) { return plb_b200_coproc_collide_and_stream(domainHandle); }
 };
+
+// ------------------------------------------- STL -> voxel flags (offLattice/)
+
+enum Precision { FLT, DBL, LDBL, INF };                     // core/globalDefs.h:88-93
+
+namespace voxelFlag {                                       // offLattice/voxelizer.h:38-48
+static const int undetermined = 0, outside = 1, outerBorder = 2, inside = 3, innerBorder = 4;
+inline bool insideFlag(int arg) { return arg == inside || arg == innerBorder; }
+inline bool outsideFlag(int arg) { return arg == outside || arg == outerBorder; }
+}
+
+/// TriangleSet<T>(fname, precision) offLattice/triangleSet.h: the triangles of an ASCII or binary STL file
+template <typename T>
+class TriangleSet {
+public:
+    explicit TriangleSet(std::string fname, Precision precision_ = DBL) : precision(precision_) {
+        float* p = 0; int64_t n = 0;
+        detail::check(plb_b200_stl_read(fname.c_str(), &p, &n));
+        soup.assign(p, p + 9 * n);
+        plb_b200_stl_free(p);
+    }
+    plint getNumTriangles() const { return (plint)(soup.size() / 9); }
+    std::vector<float> const& b200Soup() const { return soup; }
+private:
+    std::vector<float> soup;
+    Precision precision;
+};
+
+/// DEFscaledMesh<T>(triangleSet, resolution, referenceDirection, margin, extraLayer) offLattice/triangleBoundary3D.h:44-82,
+/// with TriangularSurfaceMesh::inflate() (triangularSurfaceMesh.hh:1419-1425) folded in as inflate().
+template <typename T>
+class DEFscaledMesh {
+public:
+    DEFscaledMesh(TriangleSet<T> const& set, plint resolution_, plint referenceDirection_, plint margin_, plint extraLayer_)
+        : soup(set.b200Soup()), resolution(resolution_), referenceDirection(referenceDirection_), margin(margin_), extraLayer(extraLayer_) { build(0.); }
+    void inflate(T amount = (T)1.e-3) { build((double)amount); }
+    plint getMargin() const { return margin; }
+    T getDx() const { return (T)dx; }
+    Array<T, 3> getPhysicalLocation() const { return Array<T, 3>((T)location[0], (T)location[1], (T)location[2]); }
+    plint getNumTriangles() const { return (plint)(soup.size() / 9); }
+    std::vector<double> const& b200Triangles() const { return triangles; }
+    const int* b200Dims() const { return dims; }
+    plint b200Layer() const { return margin + extraLayer; }
+private:
+    void build(double amount) {
+        triangles.resize(soup.size());
+        detail::check(plb_b200_mesh_to_lattice(soup.data(), (int64_t)(soup.size() / 9), (int)resolution, (int)referenceDirection, (int)margin,
+                                               (int)extraLayer, amount, triangles.data(), dims, &dx, location));
+    }
+    std::vector<float> soup;
+    std::vector<double> triangles;
+    plint resolution, referenceDirection, margin, extraLayer;
+    int dims[3];
+    double dx, location[3];
+};
+
+/// the slice of MultiScalarField3D<int> (multiBlock/multiDataField3D.h) a voxel matrix needs
+template <typename T>
+class MultiScalarField3D {
+public:
+    MultiScalarField3D(plint nx_, plint ny_, plint nz_, T ini = T()) : nx(nx_), ny(ny_), nz(nz_), data((size_t)(nx_ * ny_ * nz_), ini) {}
+    plint getNx() const { return nx; }
+    plint getNy() const { return ny; }
+    plint getNz() const { return nz; }
+    Box3D getBoundingBox() const { return Box3D(0, nx - 1, 0, ny - 1, 0, nz - 1); }
+    T& get(plint x, plint y, plint z) { return data[(size_t)((x * ny + y) * nz + z)]; }
+    T const& get(plint x, plint y, plint z) const { return data[(size_t)((x * ny + y) * nz + z)]; }
+    std::vector<T>& b200Data() { return data; }
+    std::vector<T> const& b200Data() const { return data; }
+private:
+    plint nx, ny, nz;
+    std::vector<T> data;
+};
+
+/// voxelize(mesh, symmetricLayer, borderWidth) offLattice/voxelizer.hh:84-104 (+ detectBorderLine :640-690), on the device
+template <typename T>
+std::unique_ptr<MultiScalarField3D<int> > voxelize(DEFscaledMesh<T> const& mesh, plint /*symmetricLayer*/, plint borderWidth) {
+    const int* d = mesh.b200Dims();
+    std::unique_ptr<MultiScalarField3D<int> > m(new MultiScalarField3D<int>(d[0], d[1], d[2], voxelFlag::undetermined));
+    detail::check(plb_b200_voxelize(mesh.b200Triangles().data(), (int64_t)mesh.getNumTriangles(), d[0], d[1], d[2], (int)borderWidth,
+                                    m->b200Data().data(), 0));
+    return m;
+}
+
+/// defineDynamics(lattice, voxelMatrix, dynamics, flag) with the voxel matrix placed at `offset` in the lattice
+/// (the reference's matrix and lattice share a domain; cells outside the matrix keep their dynamics)
+template <typename T, template <typename U> class Descriptor>
+void defineDynamics(MultiBlockLattice3D<T, Descriptor>& lattice, MultiScalarField3D<int> const& voxels, Array<plint, 3> offset,
+                    Dynamics<T, Descriptor>* dynamics, int whichFlag) {
+    std::vector<int> mask((size_t)(lattice.getNx() * lattice.getNy() * lattice.getNz()), whichFlag == 0 ? 1 : 0);
+    for (plint x = 0; x < voxels.getNx(); ++x) for (plint y = 0; y < voxels.getNy(); ++y) for (plint z = 0; z < voxels.getNz(); ++z) {
+        const plint X = x + offset[0], Y = y + offset[1], Z = z + offset[2];
+        if (X < 0 || Y < 0 || Z < 0 || X >= lattice.getNx() || Y >= lattice.getNy() || Z >= lattice.getNz()) continue;
+        mask[(size_t)((X * lattice.getNy() + Y) * lattice.getNz() + Z)] = voxels.get(x, y, z);
+    }
+    defineDynamics(lattice, mask, dynamics, whichFlag);
+}
 
 namespace global {
 template <typename T>

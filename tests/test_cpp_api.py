@@ -28,6 +28,7 @@ def test_examples_build_against_the_header():
     subprocess.run(["make", "-C", EX, "clean"], check=True, capture_output=True)
     subprocess.run(["make", "-C", EX], check=True, capture_output=True)
     assert os.path.exists(os.path.join(EX, "cavity3d")) and os.path.exists(os.path.join(EX, "channel3d"))
+    assert os.path.exists(os.path.join(EX, "voxelize_stl"))
 
 
 @pytest.mark.gpu
@@ -64,3 +65,39 @@ def test_channel3d_cpp_matches_oracle(model, prec):
     assert abs(float(stored.group(1)) - want[2]) <= rel * abs(want[2])
     assert abs(float(stored.group(2)) - want[1]) <= rel * abs(want[1])
     assert re.search(r"Av\. density (\S+)", out).group(1) == "%e" % want[5]
+
+
+@pytest.mark.gpu
+def test_voxelize_stl_cpp_matches_reference_matrix_and_oracle_flow():
+    """examples/voxelize_stl.cpp (the reference's utility/stl/revoxelize.cpp up to the voxel matrix, then flow around it)"""
+    import struct
+    from scenario import OracleEngine
+    g = np.load(os.path.join(ROOT, "tests", "golden", "voxel_cylinder_17_y.npz"))
+    res, rdir, margin, extra, bw = [int(x) for x in g["params"]]
+    assert (margin, extra, bw) != (4, 0, 1)          # this fixture uses other parameters than the example: only soup is used
+    g = np.load(os.path.join(ROOT, "tests", "golden", "voxel_cylinder_40.npz"))
+    with tempfile.TemporaryDirectory() as tmp:
+        stl = os.path.join(tmp, "c.stl")
+        with open(stl, "wb") as f:
+            f.write(b"from the golden fixture".ljust(80, b" "))
+            f.write(struct.pack("<I", len(g["soup"])))
+            for t in g["soup"]:
+                f.write(struct.pack("<3f", 0, 0, 0) + t.astype("<f4").tobytes() + b"\0\0")
+        dump = os.path.join(tmp, "flags.bin")
+        out = subprocess.run([_exe("voxelize_stl"), stl, "40", "0", dump], check=True, capture_output=True, text=True).stdout
+        flags = np.fromfile(dump, dtype=np.int32).reshape(g["flags"].shape)
+    assert np.array_equal(flags, g["flags"])
+    assert "outside 85035 outerBorder 14034 inside 68408 innerBorder 12598" in out      # SURVEY.md 8c known answer
+    nx, ny, nz = 2 * flags.shape[0], flags.shape[1], flags.shape[2]
+    mask = np.zeros((nx, ny, nz), dtype=np.int32)
+    mask[flags.shape[0] // 2: flags.shape[0] // 2 + flags.shape[0]] = flags
+    o = OracleEngine(19, "f64", nx, ny, nz, "BGK", 1.7)
+    o.set_periodicity(True, True, True)
+    o.define_dynamics_mask(mask, 3, "BB", 1.0)
+    o.define_dynamics_mask(mask, 4, "BB", 1.0)
+    o.initialize_at_equilibrium((0, nx - 1, 0, ny - 1, 0, nz - 1), 1.0, (0.03, 0.0, 0.0))
+    o.initialize()
+    o.collide_and_stream(20)
+    m = re.search(r"Av\. energy (\S+) Av\. density (\S+)", out)
+    assert m.group(1) == "%e" % o.compute_average_energy() and m.group(2) == "%e" % o.compute_average_density()
+    o.close()
