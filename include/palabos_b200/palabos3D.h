@@ -440,15 +440,15 @@ template <typename T>
 class TriangleSet {
 public:
     explicit TriangleSet(std::string fname, Precision precision_ = DBL) : precision(precision_) {
-        float* p = 0; int64_t n = 0;
+        double* p = 0; int64_t n = 0;
         detail::check(plb_b200_stl_read(fname.c_str(), &p, &n));
         soup.assign(p, p + 9 * n);
         plb_b200_stl_free(p);
     }
     plint getNumTriangles() const { return (plint)(soup.size() / 9); }
-    std::vector<float> const& b200Soup() const { return soup; }
+    std::vector<double> const& b200Soup() const { return soup; }
 private:
-    std::vector<float> soup;
+    std::vector<double> soup;
     Precision precision;
 };
 
@@ -473,7 +473,7 @@ private:
         detail::check(plb_b200_mesh_to_lattice(soup.data(), (int64_t)(soup.size() / 9), (int)resolution, (int)referenceDirection, (int)margin,
                                                (int)extraLayer, amount, triangles.data(), dims, &dx, location));
     }
-    std::vector<float> soup;
+    std::vector<double> soup;
     std::vector<double> triangles;
     plint resolution, referenceDirection, margin, extraLayer;
     int dims[3];

@@ -164,15 +164,16 @@ int plb_b200_profile_read(plb_b200_lattice* L, double* total_ms, int* n_launches
  * defineDynamics(lattice, mask, flag, dynamics) (plb_b200_define_dynamics_mask) takes. */
 int plb_b200_voxelize(const double* triangles, int64_t n_triangles, int nx, int ny, int nz, int border_width,
                       int32_t* flags_out, double* kernel_ms);
-/* TriangleSet<T>(fileName, FLT) offLattice/triangleSet.hh:130-260: ASCII or binary STL -> float [n][3][3]
- * (malloc'ed, release with plb_b200_stl_free) */
-int plb_b200_stl_read(const char* path, float** soup, int64_t* n_triangles);
-void plb_b200_stl_free(float* soup);
+/* TriangleSet<T>(fileName, FLT) offLattice/triangleSet.hh:130-350: ASCII (numbers read as double) or binary STL ->
+ * double [n][3][3] (malloc'ed, release with plb_b200_stl_free); degenerate facets are dropped and vertices 1, 2 swapped
+ * where the facet normal of the file says so (checkForDegenerateTrianglesAndFixOrientationNoAbort :497-548) */
+int plb_b200_stl_read(const char* path, double** soup, int64_t* n_triangles);
+void plb_b200_stl_free(double* soup);
 /* DEFscaledMesh(triangleSet, resolution, referenceDirection, margin, extraLayer) offLattice/triangleBoundary3D.hh:255-301
  * followed by TriangularSurfaceMesh::inflate(inflate) triangularSurfaceMesh.hh:1419-1425 (reference default 1e-3):
  * triangles_out double [n][3][3] in lattice units, dims = size of the voxel matrix (voxelizer.hh:84-104),
  * dx / location = physical size of a cell and position of lattice node (0,0,0). */
-int plb_b200_mesh_to_lattice(const float* soup, int64_t n_triangles, int resolution, int reference_direction, int margin,
+int plb_b200_mesh_to_lattice(const double* soup, int64_t n_triangles, int resolution, int reference_direction, int margin,
                              int extra_layer, double inflate, double* triangles_out, int dims[3], double* dx, double location[3]);
 
 /* ---- the reference's own plug-in surface: plb::CoProcessor3D<T> (coProcessor3D.h:59-116) ------------- */

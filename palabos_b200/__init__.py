@@ -137,19 +137,19 @@ def _ck(ok):
 
 
 def stl_read(path):
-    """Triangles of an ASCII or binary STL file as float32 [n,3,3] (TriangleSet<T>(fileName, FLT))."""
+    """Triangles of an ASCII or binary STL file as float64 [n,3,3] (TriangleSet<T>(fileName, FLT))."""
     ptr, n = ctypes.c_void_p(), ctypes.c_int64()
     _ck(lib().plb_b200_stl_read(str(path).encode(), ctypes.byref(ptr), ctypes.byref(n)))
     try:
-        buf = (ctypes.c_float * (n.value * 9)).from_address(ptr.value) if n.value else []
-        return np.array(buf, dtype=np.float32).reshape(-1, 3, 3)
+        buf = (ctypes.c_double * (n.value * 9)).from_address(ptr.value) if n.value else []
+        return np.array(buf, dtype=np.float64).reshape(-1, 3, 3)
     finally:
         lib().plb_b200_stl_free(ptr)
 
 
 def mesh_to_lattice(soup, resolution, reference_direction, margin, extra_layer=0, inflate=1e-3):
     """DEFscaledMesh + inflate: returns (triangles float64 [n,3,3] in lattice units, dims, dx, location)."""
-    soup = np.ascontiguousarray(soup, dtype=np.float32).reshape(-1, 3, 3)
+    soup = np.ascontiguousarray(soup, dtype=np.float64).reshape(-1, 3, 3)
     tri = np.empty(soup.shape, dtype=np.float64)
     dims, dx, loc = (ctypes.c_int * 3)(), ctypes.c_double(), (ctypes.c_double * 3)()
     _ck(lib().plb_b200_mesh_to_lattice(soup.ctypes.data_as(ctypes.c_void_p), soup.shape[0], int(resolution), int(reference_direction),

@@ -42,7 +42,8 @@ class LatticeImpl : public LatticeBase {
         Bc<T>* dBcs = nullptr; size_t dBcsCap = 0;
         Item* dItems = nullptr; size_t dItemsCap = 0;
         double* dPartials = nullptr; int partialsCap = 0;
-        double* dStats = nullptr;          ///< [4]
+        double* dStats = nullptr;          ///< [3 launches][4]: a step sweeps a slab in up to three launches (5.)
+        int statSlots = 0;                 ///< launches of the last step
         unsigned int* dTicket = nullptr;
         std::vector<uint8_t> hKind;
         std::vector<BcRec> recs;
@@ -53,6 +54,7 @@ class LatticeImpl : public LatticeBase {
         size_t nItems = 0;
         int* dSparse = nullptr; size_t dSparseCap = 0;
         int nSparse = 0;                   ///< cells listed for the sweep's list blocks (z-face plane cells and their sector mates)
+        std::vector<int> hSparse;          ///< host copy (ascending): a launch over part of the slab takes its sub-range
         bool dirtyKind = true, dirtyBcIndex = true, dirtySched = true;
         bool kindUnflagged = true;         ///< dKind was uploaded from hKind and carries no KIND_PLANE flags
         int bcDirtyLo = 0, bcDirtyHi = 0;  ///< record range whose values must be re-uploaded
@@ -88,6 +90,10 @@ class LatticeImpl : public LatticeBase {
 
     static constexpr size_t STAGE_BYTES = size_t(256) << 20;
     static constexpr size_t XFER_CHUNK_BYTES = size_t(64) << 20;   ///< one of the two upload/download staging halves
+    cudaStream_t commStream_ = nullptr;      ///< envelope exchange, overlapped with the sweep of the interior planes
+    cudaEvent_t rimDone_ = nullptr, commDone_ = nullptr;
+    int overlap_ = -1;                       ///< overlap the exchange with the interior sweep: -1 = when a slab has two exchanging
+                                             ///< faces (more than two slabs, or periodic x), PLB_B200_OVERLAP=0/1 in the environment forces it
     cudaStream_t copyStream_ = nullptr;
     cudaEvent_t copied_[2] = {nullptr, nullptr}, transposed_[2] = {nullptr, nullptr};
 
@@ -103,6 +109,7 @@ public:
         if (G_ > nx_) throw PlbError("more slabs than x-planes");
         if ((long long)ny_ * nz_ >= (1ll << 30)) throw PlbError("y-z plane too large");
         if (const char* e = std::getenv("PLB_B200_EAGER_PLANES")) allowFuse_ = !(e[0] == '1');
+        if (const char* e = std::getenv("PLB_B200_OVERLAP")) overlap_ = e[0] == '1' ? 1 : (e[0] == '0' ? 0 : -1);
         add_dyn(d.dynamics, d.p1, d.p2);     // entry 0: the background dynamics
         for (int s = 0; s < d.slabsPerRank; ++s) {
             Slab sl;
@@ -120,7 +127,7 @@ public:
             PLB_CUDA(cudaMemsetAsync(sl.F, 0, nF * sizeof(T), stream_));
             sl.dKind = (uint8_t*)dev_alloc(sl.cellsStore);
             sl.dBcIdx = (int*)dev_alloc(sl.cellsStore * sizeof(int));
-            sl.dStats = (double*)dev_alloc(4 * sizeof(double));
+            sl.dStats = (double*)dev_alloc(3 * 4 * sizeof(double));
             sl.dTicket = (unsigned int*)dev_alloc(sizeof(unsigned int));
             PLB_CUDA(cudaMemsetAsync(sl.dTicket, 0, sizeof(unsigned int), stream_));
             sl.hKind.assign((size_t)sl.cellsStore, 0);
@@ -138,6 +145,7 @@ public:
         cudaFree(dDyns_); cudaFree(dStage_); cudaFree(dReduce_);
         if (comm_) NcclApi::get().CommDestroy(comm_);
         for (cudaEvent_t e : profEvents_) cudaEventDestroy(e);
+        if (commStream_) { cudaStreamDestroy(commStream_); cudaEventDestroy(rimDone_); cudaEventDestroy(commDone_); }
         if (copyStream_) {
             cudaStreamDestroy(copyStream_);
             for (int k = 0; k < 2; ++k) { cudaEventDestroy(copied_[k]); cudaEventDestroy(transposed_[k]); }
@@ -406,10 +414,41 @@ public:
         if (desc_.nRanks > 1 && !comm_) throw PlbError("plb_b200_comm_init must be called before stepping a multi-rank lattice");
         sync_setup();
         for (int s = 0; s < n; ++s) {
-            for (Slab& sl : slabs_) launch_sweep(sl);
-            swapped_ = !swapped_;
-            pending_ = false;                  // the sweep has applied the outstanding completion
-            exchange();
+            // splitting the sweep costs ~0.05 ms at 512^3 per slab; hiding one face's exchange gains less than that, two faces' more
+            const bool overlap = G_ > 1 && (overlap_ == 1 || (overlap_ == -1 && (G_ > 2 || per_[0])));
+            if (!overlap) {
+                for (Slab& sl : slabs_) { launch_sweep(sl, 1, sl.nxl, 0); sl.statSlots = 1; }
+                swapped_ = !swapped_;
+                pending_ = false;              // the sweep has applied the outstanding completion
+                exchange_copies(stream_);
+            } else {
+                // the two planes next to the slab faces first; their face-crossing populations travel on the
+                // communication stream while the interior planes are swept
+                if (!commStream_) {
+                    PLB_CUDA(cudaStreamCreateWithFlags(&commStream_, cudaStreamNonBlocking));
+                    PLB_CUDA(cudaEventCreateWithFlags(&rimDone_, cudaEventDisableTiming));
+                    PLB_CUDA(cudaEventCreateWithFlags(&commDone_, cudaEventDisableTiming));
+                }
+                for (Slab& sl : slabs_) {
+                    sl.statSlots = 0;
+                    launch_sweep(sl, 1, 1, sl.statSlots++);
+                    if (sl.nxl > 1) launch_sweep(sl, sl.nxl, sl.nxl, sl.statSlots++);
+                }
+                PLB_CUDA(cudaEventRecord(rimDone_, stream_));
+                PLB_CUDA(cudaStreamWaitEvent(commStream_, rimDone_, 0));
+                const bool wasPending = pending_;
+                swapped_ = !swapped_;
+                exchange_copies(commStream_);
+                PLB_CUDA(cudaEventRecord(commDone_, commStream_));
+                swapped_ = !swapped_;          // the interior launches still belong to the old layout
+                pending_ = wasPending;
+                for (Slab& sl : slabs_)
+                    if (sl.nxl > 2) launch_sweep(sl, 2, sl.nxl - 1, sl.statSlots++);
+                swapped_ = !swapped_;
+                pending_ = false;
+                PLB_CUDA(cudaStreamWaitEvent(stream_, commDone_, 0));
+            }
+            exchange_unpack();
             run_processors();
             stepped_ = true;
         }
@@ -423,10 +462,12 @@ public:
         if (stepped_ && statsOn_) {
             PLB_CUDA(cudaStreamSynchronize(stream_));
             for (Slab& sl : slabs_) {
-                double h[4];
+                double h[12];
                 PLB_CUDA(cudaMemcpy(h, sl.dStats, sizeof h, cudaMemcpyDeviceToHost));
-                sum[0] += h[0]; sum[1] += h[1]; sum[2] += h[3];
-                mx = std::max(mx, h[2]);
+                for (int k = 0; k < sl.statSlots; ++k) {
+                    sum[0] += h[4 * k]; sum[1] += h[4 * k + 1]; sum[2] += h[4 * k + 3];
+                    mx = std::max(mx, h[4 * k + 2]);
+                }
             }
         }
         if (desc_.nRanks > 1) {
@@ -721,6 +762,7 @@ private:
             sparse.erase(std::unique(sparse.begin(), sparse.end()), sparse.end());
         }
         sl.nSparse = (int)sparse.size();
+        sl.hSparse = sparse;
         if (sparse.size() > sl.dSparseCap) {
             if (sl.dSparse) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dSparse); devBytes_ -= sl.dSparseCap * sizeof(int); }
             sl.dSparse = (int*)dev_alloc(sparse.size() * sizeof(int));
@@ -875,16 +917,22 @@ private:
         if (prof) { PLB_CUDA(cudaEventRecord(profEvents_[profUsed_ + 1], stream_)); profUsed_ += 2; }
     }
 
-    void launch_sweep(Slab& sl) {
+    /// sweep the planes X0..X1 of a slab; `slot`: which statistics slot of the slab this launch reports to
+    void launch_sweep(Slab& sl, int X0, int X1, int slot) {
         SweepArgs<T> a;
         a.F = sl.F; a.kind = sl.dKind; a.dyns = dDyns_; a.g = geo(sl);
         a.bcIdx = sl.dBcIdx; a.bcs = sl.dBcs;
         a.applyPlanes = (pending_ && sl.stageOffsets.size() >= 2 && sl.stageSplit[0] > sl.stageOffsets[0]) ? 1 : 0;
-        a.cellBegin = P_; a.cellEnd = (sl.nxl + 1) * P_;
-        a.sparseCells = sl.dSparse; a.nSparse = a.applyPlanes ? sl.nSparse : 0; a.nListBlocks = 0;
+        a.cellBegin = X0 * P_; a.cellEnd = (X1 + 1) * P_;
+        a.sparseCells = sl.dSparse; a.nSparse = 0; a.nListBlocks = 0;
+        if (a.applyPlanes && sl.nSparse > 0) {
+            const int lo = (int)(std::lower_bound(sl.hSparse.begin(), sl.hSparse.end(), a.cellBegin) - sl.hSparse.begin());
+            const int hi = (int)(std::lower_bound(sl.hSparse.begin(), sl.hSparse.end(), a.cellEnd) - sl.hSparse.begin());
+            a.sparseCells = sl.dSparse + lo; a.nSparse = hi - lo;
+        }
         a.omega = dyns_[0].omega; a.preFactor = dyns_[0].preFactor;
         a.gatherStats = statsOn_ ? 1 : 0;
-        a.partials = nullptr; a.ticket = sl.dTicket; a.statsOut = sl.dStats;
+        a.partials = nullptr; a.ticket = sl.dTicket; a.statsOut = sl.dStats + 4 * slot;
         bool generic = L::is_inert(dyns_[0].type);
         for (size_t k = 1; k < dyns_.size(); ++k) if (!L::is_inert(dyns_[k].type)) generic = true;
         const bool odd = swapped_;
@@ -930,7 +978,7 @@ private:
     ///                                         g+1's first plane, slots c_x=+1 -> high ghost plane of g
     ///   after an odd step (layout NORMAL):    high ghost of g, slots c_x=+1   -> low ghost of g+1 -> (unpack) first plane of g+1
     ///                                         low ghost of g+1, slots c_x=-1  -> high ghost of g  -> (unpack) last plane of g
-    void exchange() {
+    void exchange_copies(cudaStream_t stream) {
         if (G_ == 1) return;
         const int nFaces = per_[0] ? G_ : G_ - 1;
         const size_t planeBytes = (size_t)P_ * sizeof(T);
@@ -959,16 +1007,21 @@ private:
                     T* sp = src ? plane_ptr(*src, i, srcPlane) : nullptr;
                     T* dp = dst ? plane_ptr(*dst, i, dstPlane) : nullptr;
                     if (src && dst) {
-                        PLB_CUDA(cudaMemcpyAsync(dp, sp, planeBytes, cudaMemcpyDeviceToDevice, stream_));
+                        PLB_CUDA(cudaMemcpyAsync(dp, sp, planeBytes, cudaMemcpyDeviceToDevice, stream));
                     } else if (src) {
-                        n->check(n->Send(sp, planeBytes, ncclInt8, dstG / desc_.slabsPerRank, comm_, stream_), "ncclSend");
+                        n->check(n->Send(sp, planeBytes, ncclInt8, dstG / desc_.slabsPerRank, comm_, stream), "ncclSend");
                     } else {
-                        n->check(n->Recv(dp, planeBytes, ncclInt8, srcG / desc_.slabsPerRank, comm_, stream_), "ncclRecv");
+                        n->check(n->Recv(dp, planeBytes, ncclInt8, srcG / desc_.slabsPerRank, comm_, stream), "ncclRecv");
                     }
                 }
             }
         }
         if (remote) n->check(n->GroupEnd(), "ncclGroupEnd");
+    }
+
+    /// second half of the exchange after an odd step (on the lattice's stream, once the copies have arrived)
+    void exchange_unpack() {
+        if (G_ == 1) return;
         if (!swapped_) {
             for (Slab& sl : slabs_) {
                 const Geo g = geo(sl);

@@ -324,3 +324,15 @@ def test_long_rows_take_the_interior_fast_path_of_the_odd_half(shape, slabs):
         assert np.array_equal(engines[0].download(), engines[1].download()), periodic
         for eng in engines:
             eng.close()
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+@pytest.mark.parametrize("name,slabs", [("cavity_bgk_10x9x8", 2), ("cavity_zouhe_10x9x8", 5), ("channel_trt_16x12x10", 4), ("periodic_rlb_q27", 2)])
+def test_exchange_overlapped_with_the_interior_sweep_or_not(name, slabs, mode, monkeypatch):
+    """PLB_B200_OVERLAP=1: rim planes swept first, exchange on a second stream while the interior planes are swept
+    (three launches per slab and step); =0: one launch, exchange afterwards.  Same populations and statistics."""
+    monkeypatch.setenv("PLB_B200_OVERLAP", mode)
+    sc = CASES[name][0]()
+    got = run_gpu(sc, slabs=slabs)
+    assert_same(name, got, run_oracle(sc), sc.prec)
+    check_golden(name, got)
