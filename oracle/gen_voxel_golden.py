@@ -2,7 +2,9 @@
 """Golden vectors of the STL -> voxel-flag pipeline, produced by the UNMODIFIED
 reference through oracle/_ref/ref_voxel (utility/stl/revoxelize.cpp:40-80 restated as a driver).
 Run in the build container (needs /root/reference); writes tests/golden/voxel_*.npz:
-  soup    float32 [nt,3,3]  the triangles of the STL file as stored in it (input of our own mesh pipeline)
+  soup    float64 [nt,3,3]  the triangles of the STL file as TriangleSet holds them: ASCII numbers read as double,
+                            degenerate facets dropped, vertices 1, 2 swapped where the facet normal says so
+                            (read by oracle/voxel_oracle.py:read_stl, the restatement of TriangleSet::readSTL)
   tri     float64 [nt',3,3] the triangles the reference hands to voxelize(): lattice units, after
                             DEFscaledMesh scaling/translation and TriangularSurfaceMesh::inflate()
   flags   int8 [nx,ny,nz]   voxelFlag values (offLattice/voxelizer.h:38-48) after detectBorderLine
@@ -16,6 +18,9 @@ import tempfile
 
 import numpy as np
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import voxel_oracle  # noqa: E402
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 STL_DIR = "/root/reference/viscosityTest/stl"
@@ -26,17 +31,6 @@ CASES = {   # name: (file, resolution, referenceDirection, margin, extraLayer, b
     "voxel_cylinder_31_z": ("cylinderSimple.stl", 31, 2, 5, 0, 1),
     "voxel_cylinder_17_y": ("cylinderSimple.stl", 17, 1, 2, 2, 1),
 }
-
-
-def read_stl_soup(path):
-    """Triangles of a binary or ASCII STL as float32 [nt,3,3] (the numbers in the file, nothing else)."""
-    raw = open(path, "rb").read()
-    if b"endfacet" in raw[:4096]:
-        vals = [ln.split()[1:4] for ln in raw.decode("ascii", "replace").splitlines() if ln.strip().startswith("vertex")]
-        return np.array(vals, dtype=np.float32).reshape(-1, 3, 3)
-    nt = struct.unpack("<I", raw[80:84])[0]
-    rec = np.frombuffer(raw, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), count=nt, offset=84)
-    return np.ascontiguousarray(rec["v"])
 
 
 def main():
@@ -51,7 +45,7 @@ def main():
         dims = np.frombuffer(b[8:32], dtype=np.int64)
         tri = np.frombuffer(b[32:32 + nt * 72], dtype=np.float64).reshape(nt, 3, 3)
         flags = np.frombuffer(b[32 + nt * 72:], dtype=np.int32).reshape(dims).astype(np.int8)
-        soup = read_stl_soup(os.path.join(STL_DIR, fn))
+        soup = voxel_oracle.read_stl(os.path.join(STL_DIR, fn))
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), soup=soup, tri=tri, flags=flags,
                             params=np.array([res, rdir, margin, extra, bw], dtype=np.int64))
         print(name, "triangles", nt, "soup", soup.shape[0], "matrix", tuple(dims), "counts", np.bincount(flags.ravel(), minlength=5))

@@ -13,11 +13,11 @@ bit for bit against tests/golden/voxel_*.npz, voxel matrices dumped by the UNMOD
 (oracle/_ref/ref_voxel, oracle/gen_voxel_golden.py) for two STL files of the reference at five resolutions /
 orientations / margins / border widths.
 
-Known deviation of the mesh preparation: the reference's inflate() moves a vertex along the normalised sum of the
-unit normals of the triangles its half-edge walk reaches (getNeighborTriangleIds, triangularSurfaceMesh.hh:495-518),
-which on meshes with inconsistently oriented patches (cylinderSimple.stl: the caps) is only part of the one-ring;
-this file and the product sum over the whole one-ring.  Vertices then differ by up to the inflate amount (1e-3
-lattice units); the voxel matrices of all golden cases are nevertheless identical.
+The mesh preparation follows the reference operation by operation, including two quirks of this fork that decide
+where inflate() moves a vertex: TriangleToDef::fixOrientation never changes a triangle (offLattice/triangleToDef.hh:240-330)
+and getNeighborTriangleIds (triangularSurfaceMesh.hh:495-518) walks half-edges that, on inconsistently wound patches
+(the caps of cylinderSimple.stl), reach only part of a vertex's one-ring.  Pinned on the triangles the reference hands
+to voxelize() (fixture key "tri"): agreement to 1e-10 lattice units.
 """
 import numpy as np
 
@@ -94,23 +94,153 @@ def flags_from_inside(inside, bw):
     return flags
 
 
+MESH_EPS = 10.0 * float(np.finfo(np.float32).eps)       # getEpsilon<T>(FLT) core/globalDefs.h:104-127
+
+
+def _is_zero(x):
+    """util::fpequal(x, 0, eps) core/util.h:428-457"""
+    return abs(x) <= 2.0 * MESH_EPS
+
+
+def fix_facets(tris, normals):
+    """TriangleSet::checkForDegenerateTrianglesAndFixOrientationNoAbort offLattice/triangleSet.hh:497-548: drop facets
+    with a vanishing edge or area, swap vertices 1, 2 where the facet's own normal disagrees with the stated one"""
+    out = []
+    for t, n in zip(np.asarray(tris, dtype=np.float64), np.asarray(normals, dtype=np.float64)):
+        e01, e02, e12 = t[1] - t[0], t[2] - t[0], t[2] - t[1]
+        cn = np.cross(e01, e02)
+        nrm = lambda v: float(np.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]))
+        if _is_zero(nrm(e01)) or _is_zero(nrm(e02)) or _is_zero(nrm(e12)) or _is_zero(nrm(cn)):
+            continue
+        if cn[0] * n[0] + cn[1] * n[1] + cn[2] * n[2] < 0.0:
+            t = t[[0, 2, 1]]
+        out.append(t)
+    return np.array(out, dtype=np.float64).reshape(-1, 3, 3)
+
+
+def read_stl(path):
+    """TriangleSet<T>(fileName, FLT) offLattice/triangleSet.hh:130-350 -> float64 [n,3,3]"""
+    import struct
+    raw = open(path, "rb").read()
+    if b"endfacet" in raw[:4096]:
+        normals, verts = [], []
+        for ln in raw.decode("ascii", "replace").splitlines():
+            w = ln.split()
+            if len(w) >= 5 and w[0] == "facet" and w[1] == "normal":
+                normals.append([float(x) for x in w[2:5]])
+            elif len(w) >= 4 and w[0] == "vertex":
+                verts.append([float(x) for x in w[1:4]])
+        return fix_facets(np.array(verts, dtype=np.float64).reshape(-1, 3, 3), np.array(normals, dtype=np.float64))
+    nt = struct.unpack("<I", raw[80:84])[0]
+    rec = np.frombuffer(raw, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), count=nt, offset=84)
+    return fix_facets(rec["v"].astype(np.float64), rec["n"].astype(np.float64))
+
+
+def _lt(x, y):
+    return (x < y) and (0.5 * (abs(x - y) + abs(y - x)) > MESH_EPS)
+
+
+def _vertex_less(a, b):
+    """TriangleToDef::VsLessThan offLattice/triangleToDef.hh:65-99"""
+    eq = lambda x, y: (not _lt(x, y)) and (not _lt(y, x))
+    return _lt(a[0], b[0]) or (eq(a[0], b[0]) and _lt(a[1], b[1])) or (eq(a[0], b[0]) and eq(a[1], b[1]) and _lt(a[2], b[2]))
+
+
+class _Key:
+    def __init__(self, v):
+        self.v = v
+
+    def __lt__(self, other):
+        return _vertex_less(self.v, other.v)
+
+
+def surface_mesh(soup):
+    """constructSurfaceMesh / TriangleToDef offLattice/triangleToDef.hh:200-235 for closed meshes: unique vertices in
+    order of first appearance, vertex indices per triangle, neighbouring half-edge `ne` (half-edge 3t+k runs from local
+    vertex k to k+1), emanating half-edge per vertex"""
+    import bisect
+    tris = np.asarray(soup, dtype=np.float64).reshape(-1, 3, 3)
+    nt = len(tris)
+    keys, ids, verts = [], [], []
+    idx = np.zeros((nt, 3), dtype=np.int64)
+    for t in range(nt):
+        for k in range(3):
+            v = tuple(float(c) for c in tris[t, k])
+            key = _Key(v)
+            p = bisect.bisect_left(keys, key)
+            if p < len(keys) and not _vertex_less(v, keys[p].v) and not _vertex_less(keys[p].v, v):
+                idx[t, k] = ids[p]
+            else:
+                keys.insert(p, key)
+                ids.insert(p, len(verts))
+                idx[t, k] = len(verts)
+                verts.append(v)
+    table = {}
+    for t in range(nt):
+        for le in range(3):
+            i0, i1 = int(idx[t, le]), int(idx[t, (le + 1) % 3])
+            key = (min(i0, i1), max(i0, i1))
+            if key not in table:
+                table[key] = [t, -1]
+            elif table[key][1] == -1:
+                table[key][1] = t
+            else:
+                raise ValueError("the surface mesh contains non-manifold edges")
+    ne = -np.ones(3 * nt, dtype=np.int64)
+
+    def local_edge(t, a, b):
+        for le in range(3):
+            if {int(idx[t, le]), int(idx[t, (le + 1) % 3])} == {a, b}:
+                return le
+        raise ValueError("problem with the surface mesh connectivity")
+    for (a, b), (t1, t2) in table.items():
+        if t2 != -1:
+            l1, l2 = local_edge(t1, a, b), local_edge(t2, a, b)
+            ne[3 * t1 + l1] = 3 * t2 + l2
+            ne[3 * t2 + l2] = 3 * t1 + l1
+    em = -np.ones(len(verts), dtype=np.int64)
+    for t in range(nt):
+        for le in range(3):
+            if em[idx[t, le]] == -1:
+                em[idx[t, le]] = 3 * t + le
+    return np.array(verts, dtype=np.float64), idx, ne, em
+
+
+def _neighbor_triangles(v, ne, em):
+    """TriangularSurfaceMesh::getNeighborTriangleIds triangularSurfaceMesh.hh:495-518"""
+    prev = lambda e: e + 2 if e % 3 == 0 else e - 1
+    ee = int(em[v])
+    out = [ee // 3]
+    e = int(ne[prev(ee)])
+    if e < 0:
+        e = ee
+    while e != ee:
+        out.append(e // 3)
+        e = int(ne[prev(e)])
+        if e < 0:
+            e = ee
+        if len(out) > len(ne):
+            raise ValueError("half-edge walk does not close")
+    return out
+
+
 def mesh_to_lattice(soup, resolution, reference_direction, margin, extra_layer=0, inflate=1e-3):
-    """float32 [n,3,3] as stored in the STL -> (float64 [n,3,3] in lattice units, dims)"""
-    v = np.asarray(soup, dtype=np.float32).astype(np.float64).reshape(-1, 3)
-    uniq, inv = np.unique(v, axis=0, return_inverse=True)
-    idx = inv.reshape(-1, 3)
-    lo, hi = uniq.min(axis=0), uniq.max(axis=0)
+    """DEFscaledMesh(set, resolution, referenceDirection, margin, extraLayer) (offLattice/triangleBoundary3D.hh:255-301,
+    toLatticeUnits triangularSurfaceMesh.hh:1552-1577) + inflate (:1419-1425, vertex by vertex in place):
+    float64 [n,3,3] of the STL -> (float64 [n,3,3] in lattice units, dims of the voxel matrix)"""
+    verts, idx, ne, em = surface_mesh(soup)
+    lo, hi = verts.min(axis=0), verts.max(axis=0)
     scale = float(resolution) / (hi[reference_direction] - lo[reference_direction])
     off = float(margin + extra_layer)
-    P = (uniq - lo) * scale + off
+    P = ((verts + (-lo)) * scale) + off
     if inflate:
-        t = P[idx]
-        n = np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0])
-        n /= np.linalg.norm(n, axis=1)[:, None]
-        vn = np.zeros_like(P)
-        for k in range(3):
-            np.add.at(vn, idx[:, k], n)
-        vn /= np.linalg.norm(vn, axis=1)[:, None]
-        P = P + inflate * vn
+        for v in range(len(P)):
+            n = np.zeros(3)
+            for t in _neighbor_triangles(v, ne, em):
+                a, b, c = P[idx[t, 0]], P[idx[t, 1]], P[idx[t, 2]]
+                e1, e2 = b - a, c - a
+                m = np.array([e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]])
+                n = n + m / np.sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2])
+            P[v] = P[v] + inflate * (n / np.sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]))
     dims = tuple(int(e) + 1 + 2 * (margin + extra_layer) for e in (P.max(axis=0) - P.min(axis=0)))
     return P[idx], dims

@@ -70,19 +70,19 @@ def test_channel3d_cpp_matches_oracle(model, prec):
 @pytest.mark.gpu
 def test_voxelize_stl_cpp_matches_reference_matrix_and_oracle_flow():
     """examples/voxelize_stl.cpp (the reference's utility/stl/revoxelize.cpp up to the voxel matrix, then flow around it)"""
-    import struct
     from scenario import OracleEngine
-    g = np.load(os.path.join(ROOT, "tests", "golden", "voxel_cylinder_17_y.npz"))
-    res, rdir, margin, extra, bw = [int(x) for x in g["params"]]
-    assert (margin, extra, bw) != (4, 0, 1)          # this fixture uses other parameters than the example: only soup is used
     g = np.load(os.path.join(ROOT, "tests", "golden", "voxel_cylinder_40.npz"))
     with tempfile.TemporaryDirectory() as tmp:
         stl = os.path.join(tmp, "c.stl")
-        with open(stl, "wb") as f:
-            f.write(b"from the golden fixture".ljust(80, b" "))
-            f.write(struct.pack("<I", len(g["soup"])))
+        with open(stl, "w") as f:             # ASCII: keeps the doubles of the fixture; facet normals as the triangles have them
+            f.write("solid from_the_golden_fixture\n")
             for t in g["soup"]:
-                f.write(struct.pack("<3f", 0, 0, 0) + t.astype("<f4").tobytes() + b"\0\0")
+                n = np.cross(t[1] - t[0], t[2] - t[0])
+                f.write(" facet normal %r %r %r\n  outer loop\n" % tuple(float(c) for c in n))
+                for v in t:
+                    f.write("   vertex %r %r %r\n" % tuple(float(c) for c in v))
+                f.write("  endloop\n endfacet\n")
+            f.write("endsolid\n")
         dump = os.path.join(tmp, "flags.bin")
         out = subprocess.run([_exe("voxelize_stl"), stl, "40", "0", dump], check=True, capture_output=True, text=True).stdout
         flags = np.fromfile(dump, dtype=np.int32).reshape(g["flags"].shape)
