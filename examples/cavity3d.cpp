@@ -42,6 +42,22 @@ int run(plint nx, plint ny, plint nz, plint steps, const char* dump) {
     std::printf("stored: energy %.17g density %.17g max velocity %.17g\n", getStoredAverageEnergy(lattice),
                 getStoredAverageDensity(lattice), getStoredMaxVelocity(lattice));
     std::printf("Mega site updates per second: %.1f\n", (double)nx * ny * nz * steps / sec / 1e6);
+    if (dump && std::getenv("CAVITY3D_FIELDS")) {
+        // what the reference's cavity3d writes as images / VTK: density, velocity, velocity norm (dataAnalysisWrapper3D.h:50-70);
+        // and a checkpoint in the reference's format (saveBinaryBlock)
+        std::unique_ptr<MultiScalarField3D<T> > rho = computeDensity(lattice);
+        std::unique_ptr<MultiTensorField3D<T, 3> > u = computeVelocity(lattice);
+        std::unique_ptr<MultiScalarField3D<T> > un = computeVelocityNorm(lattice);
+        std::unique_ptr<MultiScalarField3D<T> > uy = computeVelocityComponent(lattice, lattice.getBoundingBox(), 1);
+        FILE* fp = std::fopen(std::getenv("CAVITY3D_FIELDS"), "wb");
+        if (!fp) { std::fprintf(stderr, "cannot write fields\n"); return 2; }
+        for (plint x = 0; x < nx; ++x) for (plint y = 0; y < ny; ++y) for (plint z = 0; z < nz; ++z) {
+            const T rec[6] = {rho->get(x, y, z), u->get(x, y, z)[0], u->get(x, y, z)[1], u->get(x, y, z)[2], un->get(x, y, z), uy->get(x, y, z)};
+            std::fwrite(rec, sizeof(T), 6, fp);
+        }
+        std::fclose(fp);
+        saveBinaryBlock(lattice, std::string(std::getenv("CAVITY3D_FIELDS")) + ".ckpt");
+    }
     if (dump) {
         std::vector<T> pops;
         lattice.getPopulations(lattice.getBoundingBox(), pops);

@@ -336,6 +336,16 @@ T computeAverageDensity(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domai
 template <typename T, template <typename U> class Descriptor>
 T computeAverageDensity(MultiBlockLattice3D<T, Descriptor>& lattice) { return computeAverageDensity(lattice, lattice.getBoundingBox()); }
 
+/// saveBinaryBlock / loadBinaryBlock io/serializerIO_3D.cpp:37-66 (files interchangeable with the reference's)
+template <typename T, template <typename U> class Descriptor>
+void saveBinaryBlock(MultiBlockLattice3D<T, Descriptor>& lattice, std::string fName, bool /*enforceUint*/ = false) {
+    detail::check(plb_b200_save_binary_block(lattice.b200Handle(), fName.c_str()));
+}
+template <typename T, template <typename U> class Descriptor>
+void loadBinaryBlock(MultiBlockLattice3D<T, Descriptor>& lattice, std::string fName, bool /*enforceUint*/ = false) {
+    detail::check(plb_b200_load_binary_block(lattice.b200Handle(), fName.c_str()));
+}
+
 // ------------------------------------------- boundary conditions (boundaryCondition/boundaryCondition3D.h)
 
 template <typename T, template <typename U> class Descriptor>
@@ -497,6 +507,73 @@ private:
     plint nx, ny, nz;
     std::vector<T> data;
 };
+
+/// the slice of MultiTensorField3D<T,nDim> (multiBlock/multiDataField3D.h) field extraction needs
+template <typename T, int nDim>
+class MultiTensorField3D {
+public:
+    MultiTensorField3D(plint nx_, plint ny_, plint nz_) : nx(nx_), ny(ny_), nz(nz_), data((size_t)(nx_ * ny_ * nz_)) {}
+    plint getNx() const { return nx; }
+    plint getNy() const { return ny; }
+    plint getNz() const { return nz; }
+    Array<T, nDim>& get(plint x, plint y, plint z) { return data[(size_t)((x * ny + y) * nz + z)]; }
+    Array<T, nDim> const& get(plint x, plint y, plint z) const { return data[(size_t)((x * ny + y) * nz + z)]; }
+private:
+    plint nx, ny, nz;
+    std::vector<Array<T, nDim> > data;
+};
+
+namespace detail {
+/// rho and u of every cell of `domain` through Cell::computeDensity / computeVelocity (dynamics-aware), computed on the device
+template <typename T, template <typename U> class Descriptor>
+std::vector<T> densityVelocity(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain) {
+    CBox b(domain);
+    std::vector<T> ru((size_t)domain.nCells() * 4);
+    check(plb_b200_compute_density_velocity(lattice.b200Handle(), b.v, ru.data(), ru.size() * sizeof(T)));
+    return ru;
+}
+}
+
+/// computeDensity / computeVelocity / computeVelocityNorm / computeVelocityComponent (dataProcessors/dataAnalysisWrapper3D.h:50-70,
+/// dataAnalysisFunctional3D.hh: BoxDensityFunctional3D, BoxVelocityFunctional3D, BoxVelocityNormFunctional3D, BoxVelocityComponentFunctional3D);
+/// the returned field covers `domain`, index (0,0,0) = domain's lower corner
+template <typename T, template <typename U> class Descriptor>
+std::unique_ptr<MultiScalarField3D<T> > computeDensity(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain) {
+    std::vector<T> ru = detail::densityVelocity(lattice, domain);
+    std::unique_ptr<MultiScalarField3D<T> > f(new MultiScalarField3D<T>(domain.getNx(), domain.getNy(), domain.getNz()));
+    for (size_t k = 0; k < f->b200Data().size(); ++k) f->b200Data()[k] = ru[4 * k];
+    return f;
+}
+template <typename T, template <typename U> class Descriptor>
+std::unique_ptr<MultiScalarField3D<T> > computeDensity(MultiBlockLattice3D<T, Descriptor>& lattice) { return computeDensity(lattice, lattice.getBoundingBox()); }
+template <typename T, template <typename U> class Descriptor>
+std::unique_ptr<MultiTensorField3D<T, 3> > computeVelocity(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain) {
+    std::vector<T> ru = detail::densityVelocity(lattice, domain);
+    std::unique_ptr<MultiTensorField3D<T, 3> > f(new MultiTensorField3D<T, 3>(domain.getNx(), domain.getNy(), domain.getNz()));
+    size_t k = 0;
+    for (plint x = 0; x < domain.getNx(); ++x) for (plint y = 0; y < domain.getNy(); ++y) for (plint z = 0; z < domain.getNz(); ++z, ++k)
+        f->get(x, y, z) = Array<T, 3>(ru[4 * k + 1], ru[4 * k + 2], ru[4 * k + 3]);
+    return f;
+}
+template <typename T, template <typename U> class Descriptor>
+std::unique_ptr<MultiTensorField3D<T, 3> > computeVelocity(MultiBlockLattice3D<T, Descriptor>& lattice) { return computeVelocity(lattice, lattice.getBoundingBox()); }
+template <typename T, template <typename U> class Descriptor>
+std::unique_ptr<MultiScalarField3D<T> > computeVelocityNorm(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain) {
+    std::vector<T> ru = detail::densityVelocity(lattice, domain);
+    std::unique_ptr<MultiScalarField3D<T> > f(new MultiScalarField3D<T>(domain.getNx(), domain.getNy(), domain.getNz()));
+    for (size_t k = 0; k < f->b200Data().size(); ++k)      // std::sqrt(VectorTemplate<T,Descriptor>::normSqr(velocity))
+        f->b200Data()[k] = std::sqrt(ru[4 * k + 1] * ru[4 * k + 1] + ru[4 * k + 2] * ru[4 * k + 2] + ru[4 * k + 3] * ru[4 * k + 3]);
+    return f;
+}
+template <typename T, template <typename U> class Descriptor>
+std::unique_ptr<MultiScalarField3D<T> > computeVelocityNorm(MultiBlockLattice3D<T, Descriptor>& lattice) { return computeVelocityNorm(lattice, lattice.getBoundingBox()); }
+template <typename T, template <typename U> class Descriptor>
+std::unique_ptr<MultiScalarField3D<T> > computeVelocityComponent(MultiBlockLattice3D<T, Descriptor>& lattice, Box3D domain, plint iComponent) {
+    std::vector<T> ru = detail::densityVelocity(lattice, domain);
+    std::unique_ptr<MultiScalarField3D<T> > f(new MultiScalarField3D<T>(domain.getNx(), domain.getNy(), domain.getNz()));
+    for (size_t k = 0; k < f->b200Data().size(); ++k) f->b200Data()[k] = ru[4 * k + 1 + iComponent];
+    return f;
+}
 
 /// voxelize(mesh, symmetricLayer, borderWidth) offLattice/voxelizer.hh:84-104 (+ detectBorderLine :640-690), on the device
 template <typename T>

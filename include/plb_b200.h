@@ -118,6 +118,11 @@ int plb_b200_initialize(plb_b200_lattice* L);
  * passes / receives the part of the box it owns (its slabs), packed in x,y,z order. */
 int plb_b200_upload(plb_b200_lattice* L, const int box[6], const void* data, size_t bytes);
 int plb_b200_download(plb_b200_lattice* L, const int box[6], void* data, size_t bytes);
+/* saveBinaryBlock(lattice, fName) / loadBinaryBlock(lattice, fName) io/serializerIO_3D.cpp:37-66: base64 of the data size
+ * (64-bit) followed by base64 of the populations in the wire format above; files are interchangeable with the reference's
+ * (checkpoint / restart).  One rank only. */
+int plb_b200_save_binary_block(plb_b200_lattice* L, const char* path);
+int plb_b200_load_binary_block(plb_b200_lattice* L, const char* path);
 /* bytes a rank must supply to upload/download for `box` (cells it owns inside the box * q * sizeof(T)) */
 size_t plb_b200_local_bytes(plb_b200_lattice* L, const int box[6]);
 

@@ -281,6 +281,13 @@ static int runScenario(std::vector<std::string> const& lines, size_t first,
             if (!fp) fail("cannot write " + file);
             std::fwrite(d.data(), sizeof(T), d.size(), fp);
             std::fclose(fp);
+        } else if (cmd == "save_block") {
+            // saveBinaryBlock io/serializerIO_3D.cpp:37-49 (base64 stream of the block serializer, forward ordering)
+            std::string file; in >> file;
+            saveBinaryBlock(lattice, file);
+        } else if (cmd == "load_block") {
+            std::string file; in >> file;
+            loadBinaryBlock(lattice, file);
         } else if (cmd == "dump_rho_u") {
             // rho and u through Cell::computeDensity / computeVelocity (dynamics-aware).
             std::string file; in >> file;

@@ -39,6 +39,7 @@ SYMBOLS = [
     "plb_b200_compute_density_velocity", "plb_b200_launch_count", "plb_b200_device_bytes",
     "plb_b200_boundary_stages", "plb_b200_profile_sweeps", "plb_b200_profile_read", "plb_b200_coproc_add_domain", "plb_b200_coproc_send",
     "plb_b200_coproc_receive", "plb_b200_coproc_collide_and_stream", "plb_b200_coproc_remove_domain",
+    "plb_b200_save_binary_block", "plb_b200_load_binary_block",
     "plb_b200_voxelize", "plb_b200_stl_read", "plb_b200_stl_free", "plb_b200_mesh_to_lattice",
 ]
 
@@ -110,6 +111,8 @@ def lib():
         L.plb_b200_coproc_receive.argtypes = [ci, vp, vp, ctypes.c_size_t]
         L.plb_b200_coproc_collide_and_stream.argtypes = [ci]
         L.plb_b200_coproc_remove_domain.argtypes = [ci]
+        L.plb_b200_save_binary_block.argtypes = [vp, ctypes.c_char_p]
+        L.plb_b200_load_binary_block.argtypes = [vp, ctypes.c_char_p]
         L.plb_b200_voxelize.argtypes = [vp, ctypes.c_int64, ci, ci, ci, ci, vp, vp]
         L.plb_b200_stl_read.argtypes = [ctypes.c_char_p, vp, vp]
         L.plb_b200_stl_free.restype = None
@@ -333,6 +336,13 @@ class Lattice:
         ms, n = ctypes.c_double(), ctypes.c_int()
         self._ck(self.lib.plb_b200_profile_read(self.h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def save_binary_block(self, path):
+        """saveBinaryBlock(lattice, fName): checkpoint file in the reference's format"""
+        self._ck(self.lib.plb_b200_save_binary_block(self.h, str(path).encode()))
+
+    def load_binary_block(self, path):
+        self._ck(self.lib.plb_b200_load_binary_block(self.h, str(path).encode()))
 
     def boundary_stages(self):
         ns, ni = ctypes.c_int(), ctypes.c_int64()

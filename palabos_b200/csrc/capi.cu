@@ -2,7 +2,10 @@
 // Every entry point catches C++ exceptions and returns 1/0 like the reference's CoProcessor3D
 // methods (coProcessors/coProcessor3D.h:77,93,103,115).
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
+#include <functional>
+#include <vector>
 #include <map>
 #include <mutex>
 #include <string>
@@ -12,7 +15,7 @@
 
 using namespace plb200;
 
-struct plb_b200_lattice { LatticeBase* impl; };
+struct plb_b200_lattice { LatticeBase* impl; CreateDesc desc; };
 
 static thread_local std::string g_err;
 
@@ -42,6 +45,7 @@ plb_b200_lattice* plb_b200_create_distributed(int q, int prec, int nx, int ny, i
                                       : (q == 19 ? make_lattice_f32_q19(d) : make_lattice_f32_q27(d));
         plb_b200_lattice* L = new plb_b200_lattice;
         L->impl = impl;
+        L->desc = d;
         return L;
     } catch (const std::exception& e) { fail(e.what()); return nullptr; }
     catch (...) { fail("unknown error"); return nullptr; }
@@ -72,6 +76,142 @@ int plb_b200_slab_range(int nx, int nSlabs, int slab, int* x0, int* x1) {
     if (nx < 1 || nSlabs < 1 || nSlabs > nx || slab < 0 || slab >= nSlabs || !x0 || !x1) return fail("bad slab query");
     slab_range(nx, nSlabs, slab, *x0, *x1);
     return 1;
+}
+
+// ---- saveBinaryBlock / loadBinaryBlock (io/serializerIO_3D.cpp:37-66): the file is base64 (io/base64.hh: standard
+// alphabet, '=' padding, no line breaks) of the data size as a 64-bit integer, followed by base64 of the block
+// serializer's bytes in forward ordering -- for a lattice exactly the wire format of plb_b200_download.  Streamed
+// through x-plane chunks so that a 20 GB lattice does not need a 20 GB host copy.
+namespace {
+const char B64[65] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+
+struct B64Encoder {
+    FILE* fp; unsigned char carry[3]; int nCarry = 0; std::vector<char> out;
+    explicit B64Encoder(FILE* f) : fp(f) {}
+    void block(const unsigned char* d) {
+        out.push_back(B64[d[0] >> 2]); out.push_back(B64[((d[0] & 0x03) << 4) | ((d[1] & 0xf0) >> 4)]);
+        out.push_back(B64[((d[1] & 0x0f) << 2) | ((d[2] & 0xc0) >> 6)]); out.push_back(B64[d[2] & 0x3f]);
+    }
+    void write(const unsigned char* d, size_t n) {
+        size_t pos = 0;
+        out.clear(); out.reserve(n / 3 * 4 + 8);
+        while (nCarry > 0 && nCarry < 3 && pos < n) carry[nCarry++] = d[pos++];
+        if (nCarry == 3) { block(carry); nCarry = 0; }
+        for (; pos + 3 <= n; pos += 3) block(d + pos);
+        while (pos < n) carry[nCarry++] = d[pos++];
+        if (!out.empty() && std::fwrite(out.data(), 1, out.size(), fp) != out.size()) throw PlbError("write error");
+    }
+    void finish() {
+        if (nCarry == 0) return;
+        for (int k = nCarry; k < 3; ++k) carry[k] = 0;
+        char o[4] = {B64[carry[0] >> 2], B64[((carry[0] & 0x03) << 4) | ((carry[1] & 0xf0) >> 4)],
+                     nCarry == 2 ? B64[((carry[1] & 0x0f) << 2) | ((carry[2] & 0xc0) >> 6)] : '=', '='};
+        if (std::fwrite(o, 1, 4, fp) != 4) throw PlbError("write error");
+        nCarry = 0;
+    }
+};
+
+struct B64Decoder {
+    FILE* fp; std::vector<unsigned char> pending;   // decoded bytes not yet handed out
+    explicit B64Decoder(FILE* f) : fp(f) {}
+    static int val(int c) {
+        if (c >= 'A' && c <= 'Z') return c - 'A';
+        if (c >= 'a' && c <= 'z') return c - 'a' + 26;
+        if (c >= '0' && c <= '9') return c - '0' + 52;
+        if (c == '+') return 62;
+        if (c == '/') return 63;
+        if (c == '=') return 0;
+        return -1;
+    }
+    void read(unsigned char* dst, size_t n) {
+        size_t have = std::min(n, pending.size());
+        std::memcpy(dst, pending.data(), have);
+        pending.erase(pending.begin(), pending.begin() + have);
+        const size_t need = n - have;
+        if (!need) return;
+        const size_t groups = (need + 2) / 3;
+        std::vector<char> in(groups * 4);
+        size_t got = 0;
+        while (got < in.size()) {                    // operator>> of the reference skips white space
+            const int c = std::fgetc(fp);
+            if (c == EOF) throw PlbError("binary block file ends early");
+            if (c == ' ' || c == '\n' || c == '\r' || c == '\t') continue;
+            in[got++] = (char)c;
+        }
+        std::vector<unsigned char> dec(groups * 3);
+        for (size_t g = 0; g < groups; ++g) {
+            int v[4];
+            for (int k = 0; k < 4; ++k) { v[k] = val((unsigned char)in[4 * g + k]); if (v[k] < 0) throw PlbError("not a base64 character in binary block file"); }
+            dec[3 * g] = (unsigned char)(v[0] << 2 | v[1] >> 4);
+            dec[3 * g + 1] = (unsigned char)(v[1] << 4 | v[2] >> 2);
+            dec[3 * g + 2] = (unsigned char)(((v[2] << 6) & 0xc0) | v[3]);
+        }
+        std::memcpy(dst + have, dec.data(), need);
+        pending.assign(dec.begin() + need, dec.end());
+    }
+};
+
+/// x-plane chunks of about 64 MB
+void for_chunks(plb_b200_lattice* L, const std::function<void(const int box[6], size_t bytes)>& fn) {
+    const CreateDesc& d = L->desc;
+    if (d.nRanks != 1) throw PlbError("saveBinaryBlock / loadBinaryBlock: one rank only (the reference gathers on the main processor)");
+    const size_t planeBytes = (size_t)d.ny * d.nz * d.q * d.prec;
+    const int planes = (int)std::max<size_t>(1, (size_t(64) << 20) / planeBytes);
+    for (int x = 0; x < d.nx; x += planes) {
+        const int box[6] = {x, std::min(d.nx, x + planes) - 1, 0, d.ny - 1, 0, d.nz - 1};
+        fn(box, (size_t)(box[1] - box[0] + 1) * planeBytes);
+    }
+}
+}  // namespace
+
+int plb_b200_save_binary_block(plb_b200_lattice* L, const char* path) {
+    if (!L || !L->impl) return fail("null lattice handle");
+    FILE* fp = nullptr;
+    try {
+        if (!path) throw PlbError("null path");
+        fp = std::fopen(path, "wb");
+        if (!fp) throw PlbError(std::string("Could not open binary file ") + path + " for saving");
+        const CreateDesc& d = L->desc;
+        const uint64_t total = (uint64_t)d.nx * d.ny * d.nz * d.q * d.prec;
+        B64Encoder header(fp);
+        header.write((const unsigned char*)&total, sizeof total);
+        header.finish();
+        B64Encoder enc(fp);
+        std::vector<unsigned char> buf;
+        for_chunks(L, [&](const int box[6], size_t bytes) {
+            buf.resize(bytes);
+            L->impl->download(box, buf.data(), bytes);
+            enc.write(buf.data(), bytes);
+        });
+        enc.finish();
+        if (std::fclose(fp) != 0) { fp = nullptr; throw PlbError("write error"); }
+        return 1;
+    } catch (const std::exception& e) { if (fp) std::fclose(fp); return fail(e.what()); }
+}
+
+int plb_b200_load_binary_block(plb_b200_lattice* L, const char* path) {
+    if (!L || !L->impl) return fail("null lattice handle");
+    FILE* fp = nullptr;
+    try {
+        if (!path) throw PlbError("null path");
+        fp = std::fopen(path, "rb");
+        if (!fp) throw PlbError(std::string("Could not open binary file ") + path + " for reading");
+        const CreateDesc& d = L->desc;
+        const uint64_t total = (uint64_t)d.nx * d.ny * d.nz * d.q * d.prec;
+        uint64_t stored = 0;
+        B64Decoder header(fp);
+        header.read((unsigned char*)&stored, sizeof stored);
+        if (stored != total) throw PlbError("binary block file holds " + std::to_string(stored) + " bytes, the lattice needs " + std::to_string(total));
+        B64Decoder dec(fp);
+        std::vector<unsigned char> buf;
+        for_chunks(L, [&](const int box[6], size_t bytes) {
+            buf.resize(bytes);
+            dec.read(buf.data(), bytes);
+            L->impl->upload(box, buf.data(), bytes);
+        });
+        std::fclose(fp);
+        return 1;
+    } catch (const std::exception& e) { if (fp) std::fclose(fp); return fail(e.what()); }
 }
 
 int plb_b200_set_stream(plb_b200_lattice* L, void* s) { PLB_TRY(L, L->impl->set_stream((cudaStream_t)s)) }

@@ -92,8 +92,8 @@ class LatticeImpl : public LatticeBase {
     static constexpr size_t XFER_CHUNK_BYTES = size_t(64) << 20;   ///< one of the two upload/download staging halves
     cudaStream_t commStream_ = nullptr;      ///< envelope exchange, overlapped with the sweep of the interior planes
     cudaEvent_t rimDone_ = nullptr, commDone_ = nullptr;
-    int overlap_ = -1;                       ///< overlap the exchange with the interior sweep: -1 = when a slab has two exchanging
-                                             ///< faces (more than two slabs, or periodic x), PLB_B200_OVERLAP=0/1 in the environment forces it
+    int overlap_ = -1;                       ///< overlap the exchange with the interior sweep (default); PLB_B200_OVERLAP=0 in the
+                                             ///< environment: one launch per slab, exchange afterwards (A/B tests)
     cudaStream_t copyStream_ = nullptr;
     cudaEvent_t copied_[2] = {nullptr, nullptr}, transposed_[2] = {nullptr, nullptr};
 
@@ -414,8 +414,8 @@ public:
         if (desc_.nRanks > 1 && !comm_) throw PlbError("plb_b200_comm_init must be called before stepping a multi-rank lattice");
         sync_setup();
         for (int s = 0; s < n; ++s) {
-            // splitting the sweep costs ~0.05 ms at 512^3 per slab; hiding one face's exchange gains less than that, two faces' more
-            const bool overlap = G_ > 1 && (overlap_ == 1 || (overlap_ == -1 && (G_ > 2 || per_[0])));
+            // measured at 512^3 per GPU on 2 B200s: 7.18 ms per step overlapped against 7.26 (the split costs 0.03 ms of sweep time)
+            const bool overlap = G_ > 1 && overlap_ != 0;
             if (!overlap) {
                 for (Slab& sl : slabs_) { launch_sweep(sl, 1, sl.nxl, 0); sl.statSlots = 1; }
                 swapped_ = !swapped_;
@@ -425,7 +425,10 @@ public:
                 // the two planes next to the slab faces first; their face-crossing populations travel on the
                 // communication stream while the interior planes are swept
                 if (!commStream_) {
-                    PLB_CUDA(cudaStreamCreateWithFlags(&commStream_, cudaStreamNonBlocking));
+                    // highest priority: the copy kernels must get SMs while the interior sweep still has blocks to place
+                    int prLow = 0, prHigh = 0;
+                    PLB_CUDA(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+                    PLB_CUDA(cudaStreamCreateWithPriority(&commStream_, cudaStreamNonBlocking, prHigh));
                     PLB_CUDA(cudaEventCreateWithFlags(&rimDone_, cudaEventDisableTiming));
                     PLB_CUDA(cudaEventCreateWithFlags(&commDone_, cudaEventDisableTiming));
                 }

@@ -101,3 +101,22 @@ def test_voxelize_stl_cpp_matches_reference_matrix_and_oracle_flow():
     m = re.search(r"Av\. energy (\S+) Av\. density (\S+)", out)
     assert m.group(1) == "%e" % o.compute_average_energy() and m.group(2) == "%e" % o.compute_average_density()
     o.close()
+
+
+@pytest.mark.gpu
+def test_cavity3d_cpp_field_extraction_and_checkpoint():
+    """computeDensity / computeVelocity / computeVelocityNorm / computeVelocityComponent and saveBinaryBlock of the C++ mirror"""
+    import base64
+    nx, ny, nz = 9, 8, 10
+    with tempfile.TemporaryDirectory() as tmp:
+        dump, fields = os.path.join(tmp, "f.bin"), os.path.join(tmp, "fields.bin")
+        subprocess.run([_exe("cavity3d"), str(nx), str(ny), str(nz), "25", dump], check=True, capture_output=True, text=True,
+                       env=dict(os.environ, CAVITY3D_FIELDS=fields))
+        rec = np.fromfile(fields, dtype=np.float64).reshape(nx, ny, nz, 6)
+        ckpt = open(fields + ".ckpt", "rb").read()
+    want = run_oracle(cavity(nx, ny, nz, 25))
+    assert np.array_equal(rec[..., :4], want["rho_u_end"])
+    u = want["rho_u_end"][..., 1:]
+    assert np.array_equal(rec[..., 4], np.sqrt(u[..., 0] * u[..., 0] + u[..., 1] * u[..., 1] + u[..., 2] * u[..., 2]))
+    assert np.array_equal(rec[..., 5], u[..., 1])
+    assert base64.b64decode(ckpt[12:]) == want["f_end"].tobytes()
