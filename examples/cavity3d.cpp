@@ -57,6 +57,13 @@ int run(plint nx, plint ny, plint nz, plint steps, const char* dump) {
         }
         std::fclose(fp);
         saveBinaryBlock(lattice, std::string(std::getenv("CAVITY3D_FIELDS")) + ".ckpt");
+        {   // the writeVTK of the reference's examples (showCases/cavity3d): physical units through dx, dt
+            const T dx = 0.125, dt = 0.002;
+            VtkImageOutput3D<T, float, 3> vtkOut(std::string(std::getenv("CAVITY3D_FIELDS")) + ".vtk", dx);
+            vtkOut.writeData(*computeVelocityNorm(lattice), "velocityNorm", (float)(dx / dt));
+            vtkOut.writeData(*computeVelocity(lattice), "velocity", (float)(dx / dt));
+            vtkOut.writeData(*computeDensity(lattice), "density", (float)1, (float)-1);
+        }
     }
     if (dump) {
         std::vector<T> pops;

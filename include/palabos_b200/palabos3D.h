@@ -23,6 +23,8 @@
 
 #include <cmath>
 #include <cstddef>
+#include <fstream>
+#include <limits>
 #include <stdexcept>
 #include <string>
 #include <memory>
@@ -574,6 +576,83 @@ std::unique_ptr<MultiScalarField3D<T> > computeVelocityComponent(MultiBlockLatti
     for (size_t k = 0; k < f->b200Data().size(); ++k) f->b200Data()[k] = ru[4 * k + 1 + iComponent];
     return f;
 }
+
+/// VtkImageOutput3D<T,TConv,n> io/vtkDataOutput.h:100-136, io/vtkDataOutput.hh:57-392, io/vtkDataOutput.cpp:39-100 (this fork
+/// templates the class, not the methods): VTK ImageData XML, every field converted to TConv, optionally scaled / shifted in
+/// TConv arithmetic, written x fastest (IndexOrdering::backward) as base64 of a 32-bit byte count followed by base64 of the data.
+/// Files are byte-identical to the reference's.
+template <typename T, typename TConv = float, plint n = 3>
+class VtkImageOutput3D {
+public:
+    explicit VtkImageOutput3D(std::string fName, double deltaX_ = 1.)
+        : ostr((fName + ".vti").c_str()), deltaX(deltaX_), headerWritten(false) { offset[0] = offset[1] = offset[2] = 0.; }
+    VtkImageOutput3D(std::string fName, double deltaX_, Array<double, 3> offset_)
+        : ostr((fName + ".vti").c_str()), deltaX(deltaX_), headerWritten(false) { for (int d = 0; d < 3; ++d) offset[d] = offset_[d]; }
+    ~VtkImageOutput3D() { if (headerWritten) ostr << "</PointData>\n</Piece>\n</ImageData>\n</VTKFile>\n"; }
+    void writeData(MultiScalarField3D<T>& f, std::string name, TConv scalingFactor = (TConv)1, TConv additiveOffset = (TConv)0) {
+        std::vector<TConv> v((size_t)(f.getNx() * f.getNy() * f.getNz()));
+        size_t k = 0;
+        for (plint z = 0; z < f.getNz(); ++z) for (plint y = 0; y < f.getNy(); ++y) for (plint x = 0; x < f.getNx(); ++x, ++k) {
+            TConv c = (TConv)f.get(x, y, z);
+            if (!isOne(scalingFactor)) c = c * scalingFactor;
+            if (!isZero(additiveOffset)) c = c + additiveOffset;
+            v[k] = c;
+        }
+        field(f.getNx(), f.getNy(), f.getNz(), 1, v, name);
+    }
+    void writeData(MultiTensorField3D<T, n>& f, std::string name, TConv scalingFactor = (TConv)1) {
+        std::vector<TConv> v((size_t)(f.getNx() * f.getNy() * f.getNz() * n));
+        size_t k = 0;
+        for (plint z = 0; z < f.getNz(); ++z) for (plint y = 0; y < f.getNy(); ++y) for (plint x = 0; x < f.getNx(); ++x)
+            for (int d = 0; d < n; ++d, ++k) {
+                TConv c = (TConv)f.get(x, y, z)[d];
+                if (!isOne(scalingFactor)) c = c * scalingFactor;
+                v[k] = c;
+            }
+        field(f.getNx(), f.getNy(), f.getNz(), n, v, name);
+    }
+private:
+    // util::isZero / isOne core/util.h:583-596 with getEpsilon<T>() = 10 * machine epsilon of the type (core/globalDefs.h:104-145)
+    static TConv eps() { return (TConv)10.0 * std::numeric_limits<TConv>::epsilon(); }
+    static bool isZero(TConv x) { return std::fabs(x) <= eps(); }
+    static bool isOne(TConv x) { return std::fabs(x - (TConv)1) <= eps(); }
+    void field(plint nx, plint ny, plint nz, plint nDim, std::vector<TConv> const& v, std::string const& name) {
+        if (!headerWritten) {
+            ostr << "<?xml version=\"1.0\"?>\n<VTKFile type=\"ImageData\" version=\"0.1\" byte_order=\"LittleEndian\">\n";
+            ostr << "<ImageData WholeExtent=\"0 " << nx - 1 << " 0 " << ny - 1 << " 0 " << nz - 1 << "\" Origin=\""
+                 << offset[0] << " " << offset[1] << " " << offset[2] << "\" Spacing=\"" << deltaX << " " << deltaX << " " << deltaX << "\">\n";
+            ostr << "<Piece Extent=\"0 " << nx - 1 << " 0 " << ny - 1 << " 0 " << nz - 1 << "\">\n<PointData>\n";
+            headerWritten = true;
+        }
+        ostr << "<DataArray type=\"" << (sizeof(TConv) == 4 ? "Float32" : "Float64") << "\" Name=\"" << name << "\" format=\"binary\" encoding=\"base64";
+        if (nDim > 1) ostr << "\" NumberOfComponents=\"" << nDim;
+        ostr << "\">\n";
+        const unsigned int bytes = (unsigned int)(v.size() * sizeof(TConv));
+        base64(reinterpret_cast<const unsigned char*>(&bytes), sizeof bytes);
+        base64(reinterpret_cast<const unsigned char*>(v.data()), bytes);
+        ostr << "\n</DataArray>\n";
+    }
+    void base64(const unsigned char* d, size_t len) {
+        static const char* e = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+        std::string out;
+        out.reserve(len / 3 * 4 + 4);
+        size_t i = 0;
+        for (; i + 3 <= len; i += 3) {
+            out += e[d[i] >> 2]; out += e[((d[i] & 0x03) << 4) | ((d[i + 1] & 0xf0) >> 4)];
+            out += e[((d[i + 1] & 0x0f) << 2) | ((d[i + 2] & 0xc0) >> 6)]; out += e[d[i + 2] & 0x3f];
+        }
+        if (i < len) {
+            const unsigned char a = d[i], b = i + 1 < len ? d[i + 1] : 0;
+            out += e[a >> 2]; out += e[((a & 0x03) << 4) | ((b & 0xf0) >> 4)];
+            out += (i + 1 < len) ? e[(b & 0x0f) << 2] : '=';
+            out += '=';
+        }
+        ostr << out;
+    }
+    std::ofstream ostr;
+    double deltaX, offset[3];
+    bool headerWritten;
+};
 
 /// voxelize(mesh, symmetricLayer, borderWidth) offLattice/voxelizer.hh:84-104 (+ detectBorderLine :640-690), on the device
 template <typename T>

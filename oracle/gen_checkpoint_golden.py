@@ -54,5 +54,21 @@ def main():
         print(name, "file bytes", blob.size, "head", bytes(blob[:24]))
 
 
+def vtk_golden():
+    """tests/golden/vtk_cavity_9x8x10.npz: the .vti file the reference writes for the cavity of examples/cavity3d.cpp
+    (velocity norm, velocity, density as Float32; VtkImageOutput3D io/vtkDataOutput.hh)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cases import cavity
+    from scenario import run_reference
+    sc = cavity(9, 8, 10, 25, dumps=False)
+    sc.ops.append(("ref_file", "vtk out 0.125 0.002", "out.vti", "vti"))
+    ref = run_reference(sc)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "vtk_cavity_9x8x10.npz"), vti=ref["vti"],
+                        params=np.array([9, 8, 10, 25], dtype=np.int64), dx_dt=np.array([0.125, 0.002]))
+    print("vtk_cavity_9x8x10", ref["vti"].size, "bytes;", bytes(ref["vti"][:120]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "vtk":
+        sys.exit(vtk_golden())
     sys.exit(main())

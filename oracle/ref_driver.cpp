@@ -281,6 +281,14 @@ static int runScenario(std::vector<std::string> const& lines, size_t first,
             if (!fp) fail("cannot write " + file);
             std::fwrite(d.data(), sizeof(T), d.size(), fp);
             std::fclose(fp);
+        } else if (cmd == "vtk") {
+            // the writeVTK of the reference's examples: velocity norm, velocity and density as float, scaled
+            std::string file; double dx, dt; in >> file >> dx >> dt;
+            global::directories().setOutputDir("./");
+            VtkImageOutput3D<T, float, 3> vtkOut(file, dx);
+            vtkOut.writeData(*computeVelocityNorm(lattice), "velocityNorm", (float)(dx / dt));
+            vtkOut.writeData(*computeVelocity(lattice), "velocity", (float)(dx / dt));
+            vtkOut.writeData(*computeDensity(lattice), "density", (float)1, (float)-1);
         } else if (cmd == "save_block") {
             // saveBinaryBlock io/serializerIO_3D.cpp:37-49 (base64 stream of the block serializer, forward ordering)
             std::string file; in >> file;

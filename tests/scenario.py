@@ -131,6 +131,7 @@ def run_reference(sc: Scenario, timed_steps=None):
                  "lattice D3Q%d %s %d %d %d %s %r %r" % (sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2)]
         blob = 0
         dumps = []
+        files = []
         for op in sc.ops:
             k = op[0]
             if k == "periodic":
@@ -172,6 +173,10 @@ def run_reference(sc: Scenario, timed_steps=None):
             elif k in ("dump", "dump_rho_u"):
                 dumps.append((k, op[1]))
                 lines.append("%s %s.bin" % (k, op[1]))
+            elif k == "ref_file":
+                # a command of the reference driver that writes a file (vtk, save_block): op = (k, command line, file name, key)
+                lines.append(op[1])
+                files.append((op[2], op[3]))
             else:
                 raise ValueError(k)
         if timed_steps:
@@ -191,6 +196,8 @@ def run_reference(sc: Scenario, timed_steps=None):
         for kind, name in dumps:
             a = np.fromfile(os.path.join(tmp, name + ".bin"), dtype=sc.dtype)
             res[name] = a.reshape(sc.nx, sc.ny, sc.nz, sc.q if kind == "dump" else 4)
+        for fn, key in files:
+            res[key] = np.frombuffer(open(os.path.join(tmp, fn), "rb").read(), dtype=np.uint8)
         return res
 
 
@@ -389,6 +396,8 @@ def replay(sc: Scenario, engine):
             res[op[1]] = engine.download()
         elif k == "dump_rho_u":
             res[op[1]] = engine.compute_density_velocity()
+        elif k == "ref_file":
+            pass                                  # only the reference driver writes these
         else:
             raise ValueError(k)
     res["stats"] = np.array(res["stats"], dtype=np.float64).reshape(-1, 6)

@@ -114,6 +114,9 @@ def test_cavity3d_cpp_field_extraction_and_checkpoint():
                        env=dict(os.environ, CAVITY3D_FIELDS=fields))
         rec = np.fromfile(fields, dtype=np.float64).reshape(nx, ny, nz, 6)
         ckpt = open(fields + ".ckpt", "rb").read()
+        vti = open(fields + ".vtk.vti", "rb").read()
+    # VtkImageOutput3D: byte-identical to the file the unmodified reference writes for this cavity
+    assert vti == np.load(os.path.join(ROOT, "tests", "golden", "vtk_cavity_9x8x10.npz"))["vti"].tobytes()
     want = run_oracle(cavity(nx, ny, nz, 25))
     assert np.array_equal(rec[..., :4], want["rho_u_end"])
     u = want["rho_u_end"][..., 1:]
