@@ -1,7 +1,7 @@
 // examples/channel3d.cpp -- periodic channel (BASELINE.json configs[2] / [4] in small): periodic in x
 // and z, BounceBack walls at y = 0 and y = ny-1, parabolic initial profile; TRT or D3Q27 Smagorinsky
 // dynamics, double or float.  Written against the Palabos API (include/palabos_b200/palabos3D.h).
-//   channel3d [nx ny nz steps [trt|smago27] [f64|f32]]
+//   channel3d [nx ny nz steps [trt|incbgk|smago27] [f64|f32]]
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -43,6 +43,7 @@ int main(int argc, char** argv) {
     try {
         using namespace descriptors;
         if (model == "trt" && prec == "f64") return run<double, D3Q19Descriptor>(nx, ny, nz, steps, new TRTdynamics<double, D3Q19Descriptor>(1.2));
+        if (model == "incbgk") return run<double, D3Q19Descriptor>(nx, ny, nz, steps, new IncBGKdynamics<double, D3Q19Descriptor>(1.2));
         if (model == "trt") return run<float, D3Q19Descriptor>(nx, ny, nz, steps, new TRTdynamics<float, D3Q19Descriptor>(1.2f));
         if (prec == "f64") return run<double, D3Q27Descriptor>(nx, ny, nz, steps, new SmagorinskyBGKdynamics<double, D3Q27Descriptor>(1.9, 0.14));
         return run<float, D3Q27Descriptor>(nx, ny, nz, steps, new SmagorinskyBGKdynamics<float, D3Q27Descriptor>(1.9f, 0.14f));

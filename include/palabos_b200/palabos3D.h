@@ -116,6 +116,7 @@ public:
 PLB_B200_OMEGA_DYNAMICS(BGKdynamics, PLB_B200_DYN_BGK)                  // basicDynamics/isoThermalDynamics.h
 PLB_B200_OMEGA_DYNAMICS(RegularizedBGKdynamics, PLB_B200_DYN_RLB)       // basicDynamics/isoThermalDynamics.h
 PLB_B200_OMEGA_DYNAMICS(TRTdynamics, PLB_B200_DYN_TRT)                  // complexDynamics/trtDynamics.h
+PLB_B200_OMEGA_DYNAMICS(IncBGKdynamics, PLB_B200_DYN_INCBGK)            // basicDynamics/isoThermalDynamics.h (rho0 = 1)
 #undef PLB_B200_OMEGA_DYNAMICS
 
 /// complexDynamics/smagorinskyDynamics.h: SmagorinskyBGKdynamics(omega0, cSmago)

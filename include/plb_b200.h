@@ -34,9 +34,10 @@ extern "C" {
  *   TRT        TRTdynamics              complexDynamics/trtDynamics.hh:64-99            p1 = omega (s- = 1.1)
  *   SMAGO      SmagorinskyBGKdynamics   complexDynamics/smagorinskyDynamics.hh:290-304  p1 = omega0, p2 = cSmago
  *   BOUNCEBACK BounceBack               core/dynamics.hh:783-791                        p1 = rho
- *   NODYNAMICS NoDynamics               core/dynamics.hh:968-972                        p1 = rho   */
+ *   NODYNAMICS NoDynamics               core/dynamics.hh:968-972                        p1 = rho
+ *   INCBGK     IncBGKdynamics           basicDynamics/isoThermalDynamics.hh:1405-1417   p1 = omega (rho0 = 1)   */
 enum { PLB_B200_DYN_BGK = 0, PLB_B200_DYN_RLB = 1, PLB_B200_DYN_TRT = 2, PLB_B200_DYN_SMAGO = 3,
-       PLB_B200_DYN_BOUNCEBACK = 4, PLB_B200_DYN_NODYNAMICS = 5 };
+       PLB_B200_DYN_BOUNCEBACK = 4, PLB_B200_DYN_NODYNAMICS = 5, PLB_B200_DYN_INCBGK = 6 };
 /* Boundary-condition families: LOCAL = createLocalBoundaryCondition3D (regularized,
  * boundaryCondition/boundaryCondition3D.hh:1162-1167), ZOUHE = createZouHeBoundaryCondition3D
  * (boundaryCondition/zouHeBoundary3D.hh:338-350). */

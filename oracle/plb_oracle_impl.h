@@ -155,7 +155,8 @@ static REAL SFX(bgk_ma2_equilibrium)(const SFX(Lat)* L, int i, REAL rhoBar, REAL
 static REAL SFX(computeEquilibrium)(const SFX(Lat)* L, const SFX(Dyn)* d, int i, REAL rhoBar, const REAL j[3], REAL jSqr) {
     REAL invRho;
     if (d->type == PLBO_DYN_BOUNCEBACK || d->type == PLBO_DYN_NODYNAMICS) return (REAL)0;
-    invRho = INVRHO(rhoBar);
+    /* IncBGKdynamics::computeEquilibrium isoThermalDynamics.hh:1428-1435: the 1/rho of the O(Ma^2) term is 1/rho0 = 1 */
+    invRho = d->type == PLBO_DYN_INCBGK ? (REAL)1 : INVRHO(rhoBar);
     return SFX(bgk_ma2_equilibrium)(L, i, rhoBar, invRho, j, jSqr);
 }
 
@@ -253,6 +254,49 @@ static REAL SFX(bgk_ma2_collision)(const SFX(Lat)* L, REAL* f, REAL rhoBar, cons
         }
         return jSqr*invRho*invRho;
     }
+}
+
+/* bgk_ma2_collision_base(f, rhoBar, j, omega, invRho): dynamicsTemplates3D.h:2289-2368 (D3Q19), :467-571 (D3Q27);
+ * what bgk_inc_collision (:2480-2482, :1680-1682) calls with invRho0.  Pairs (i, i+q/2) in index order. */
+static REAL SFX(bgk_ma2_collision_base)(const SFX(Lat)* L, REAL* f, REAL rhoBar, const REAL j[3], REAL omega, REAL invRho) {
+    const int h = L->q / 2;
+    REAL one_m_omega = (REAL)1 - omega;
+    REAL t0_omega = L->t[0] * omega;
+    REAL t1_omega = L->t[1] * omega;
+    REAL t4_omega = L->t[4] * omega;
+    REAL jSqr   = j[0]*j[0] + j[1]*j[1] + j[2]*j[2];
+    REAL kx     = (REAL)3 * j[0];
+    REAL ky     = (REAL)3 * j[1];
+    REAL kz     = (REAL)3 * j[2];
+    REAL kxSqr_ = invRho / (REAL)2 * kx*kx;
+    REAL kySqr_ = invRho / (REAL)2 * ky*ky;
+    REAL kzSqr_ = invRho / (REAL)2 * kz*kz;
+    REAL kxky_  = invRho * kx*ky;
+    REAL kxkz_  = invRho * kx*kz;
+    REAL kykz_  = invRho * ky*kz;
+    REAL C1 = rhoBar + invRho*(REAL)3*jSqr;
+    REAL C2, C3;
+    C3 = -kxSqr_ - kySqr_ - kzSqr_;
+    f[0] *= one_m_omega; f[0] += t0_omega * (C1+C3);
+#define PLBO_PAIR(I, TW) f[I] *= one_m_omega; f[I] += TW * (C1+C2+C3); f[(I)+h] *= one_m_omega; f[(I)+h] += TW * (C1-C2+C3);
+    C2 = -kx;       C3 = -kySqr_ - kzSqr_;   PLBO_PAIR(1, t1_omega)
+    C2 = -ky;       C3 = -kxSqr_ - kzSqr_;   PLBO_PAIR(2, t1_omega)
+    C2 = -kz;       C3 = -kxSqr_ - kySqr_;   PLBO_PAIR(3, t1_omega)
+    C2 = -kx - ky;  C3 = kxky_ - kzSqr_;     PLBO_PAIR(4, t4_omega)
+    C2 = -kx + ky;  C3 = -kxky_ - kzSqr_;    PLBO_PAIR(5, t4_omega)
+    C2 = -kx - kz;  C3 = kxkz_ - kySqr_;     PLBO_PAIR(6, t4_omega)
+    C2 = -kx + kz;  C3 = -kxkz_ - kySqr_;    PLBO_PAIR(7, t4_omega)
+    C2 = -ky - kz;  C3 = kykz_ - kxSqr_;     PLBO_PAIR(8, t4_omega)
+    C2 = -ky + kz;  C3 = -kykz_ - kxSqr_;    PLBO_PAIR(9, t4_omega)
+    if (L->q == 27) {
+        REAL t10_omega = L->t[10] * omega;
+        C2 = -kx -ky -kz;  C3 = kxky_ + kxkz_ + kykz_;    PLBO_PAIR(10, t10_omega)
+        C2 = -kx -ky +kz;  C3 = kxky_ - kxkz_ - kykz_;    PLBO_PAIR(11, t10_omega)
+        C2 = -kx +ky -kz;  C3 = -kxky_ + kxkz_ - kykz_;   PLBO_PAIR(12, t10_omega)
+        C2 = -kx +ky +kz;  C3 = -kxky_ - kxkz_ + kykz_;   PLBO_PAIR(13, t10_omega)
+    }
+#undef PLBO_PAIR
+    return invRho*invRho*jSqr;
 }
 
 /* neqPiD3Q19 dynamicsTemplates3D.h:1903-1975 and neqPiD3Q27 :38-135: fromPiToFneq0..9 / 0..13.
@@ -367,6 +411,10 @@ static int SFX(collide_cell)(const SFX(Lat)* L, const SFX(Dyn)* d, REAL* f, REAL
         omega = SFX(smago_omega)(d->omega, d->preFactor, rhoBar, PiNeq);
         uSqr = SFX(bgk_ma2_collision)(L, f, rhoBar, j, omega);
         break; }
+    case PLBO_DYN_INCBGK:         /* IncBGKdynamics::collide isoThermalDynamics.hh:1405-1417, invRho0 = 1 */
+        SFX(get_rhoBar_j)(q, f, &rhoBar, j);
+        uSqr = SFX(bgk_ma2_collision_base)(L, f, rhoBar, j, d->omega, (REAL)1);
+        break;
     case PLBO_DYN_BOUNCEBACK:     /* core/dynamics.hh:783-791 */
         for (i = 1; i <= h; ++i) { REAL tmp = f[i]; f[i] = f[i+h]; f[i+h] = tmp; }
         return 0;
@@ -425,10 +473,14 @@ static REAL SFX(sub_sum)(const SFX(Lat)* L, const REAL* f, int dir, int value) {
 
 /* VelocityDirichletBoundaryDynamics::computeRhoBar boundaryCondition/boundaryDynamics.hh:639-668
  * (no external force in these descriptors: the 0.5*force terms vanish) */
-static REAL SFX(veldir_rhoBar)(const SFX(Lat)* L, const SFX(Bc)* b, const REAL* f) {
+/* velIsJ: Dynamics::velIsJ of the base dynamics (true for IncBGKdynamics isoThermalDynamics.hh:1437-1440; composite
+ * dynamics forward it, core/dynamics.hh:424-426) */
+#define VEL_IS_J(d) ((d)->type == PLBO_DYN_INCBGK)
+static REAL SFX(veldir_rhoBar)(const SFX(Lat)* L, const SFX(Bc)* b, const REAL* f, int velIsJ) {
     REAL rhoOnWall = SFX(sub_sum)(L, f, b->dir, 0);
     REAL rhoNormal = SFX(sub_sum)(L, f, b->dir, b->ori);
     REAL velNormal = (REAL)b->ori * ( b->u[b->dir]-0.5*(REAL)0 );
+    if (velIsJ) return (REAL)2*rhoNormal+rhoOnWall-velNormal;
     return ((REAL)2*rhoNormal+rhoOnWall-1*velNormal) / ((REAL)1+velNormal);
 }
 
@@ -442,12 +494,12 @@ static void SFX(rhodir_j)(const SFX(Lat)* L, const SFX(Bc)* b, const REAL* f, RE
 
 /* computeRhoBarJ of the plane boundary dynamics: velocity boundaryDynamics.hh:680-701,
  * density :822-828 */
-static void SFX(plane_rhoBar_j)(const SFX(Lat)* L, const SFX(Bc)* b, const REAL* f, REAL* rhoBar, REAL j[3]) {
+static void SFX(plane_rhoBar_j)(const SFX(Lat)* L, const SFX(Bc)* b, const REAL* f, REAL* rhoBar, REAL j[3], int velIsJ) {
     if (b->kind == BC_VEL_REG || b->kind == BC_VEL_ZH) {
         REAL rho; int d;
-        *rhoBar = SFX(veldir_rhoBar)(L, b, f);
+        *rhoBar = SFX(veldir_rhoBar)(L, b, f, velIsJ);
         rho = FULLRHO(*rhoBar);
-        for (d = 0; d < 3; ++d) j[d] = rho * (b->u[d] - 0.5*(REAL)0);
+        for (d = 0; d < 3; ++d) j[d] = velIsJ ? (b->u[d] - 0.5*(REAL)0) : rho * (b->u[d] - 0.5*(REAL)0);
     } else {
         *rhoBar = b->rhoBar;
         SFX(rhodir_j)(L, b, f, j);
@@ -489,7 +541,7 @@ static void SFX(zouhe_closure)(const SFX(Lat)* L, const SFX(Dyn)* base, const SF
         if (nn == 1 && !removed) { removed = 1; continue; }   /* erase the first axis-aligned one */
         diag[nDiag++] = missing[k];
     }
-    SFX(plane_rhoBar_j)(L, b, f, &rhoBar, j);
+    SFX(plane_rhoBar_j)(L, b, f, &rhoBar, j, VEL_IS_J(base));
     jSqr = j[0]*j[0] + j[1]*j[1] + j[2]*j[2];
     for (k = 0; k < nMissing; ++k) {
         int pop = missing[k];
@@ -516,7 +568,7 @@ static void SFX(zouhe_closure)(const SFX(Lat)* L, const SFX(Dyn)* base, const SF
 static void SFX(complete_populations)(const SFX(Lat)* L, const SFX(Dyn)* base, const SFX(Bc)* b, REAL* f) {
     if (b->kind == BC_VEL_REG || b->kind == BC_RHO_REG) {
         REAL rhoBar, j[3], jSqr, PiNeq[6];
-        SFX(plane_rhoBar_j)(L, b, f, &rhoBar, j);
+        SFX(plane_rhoBar_j)(L, b, f, &rhoBar, j, VEL_IS_J(base));
         jSqr = j[0]*j[0] + j[1]*j[1] + j[2]*j[2];
         SFX(boundary_PiNeq)(L, base, b, f, rhoBar, j, jSqr, PiNeq);
         SFX(regularize)(L, base, f, rhoBar, j, jSqr, PiNeq);
@@ -543,7 +595,7 @@ static REAL SFX(cell_density)(const SFX(Lat)* L, size_t cell) {
     int bi = L->bcIdx[cell];
     if (bi >= 0) {
         const SFX(Bc)* b = &L->bcs[bi];
-        if (b->kind == BC_VEL_REG || b->kind == BC_VEL_ZH) return FULLRHO(SFX(veldir_rhoBar)(L, b, f));
+        if (b->kind == BC_VEL_REG || b->kind == BC_VEL_ZH) return FULLRHO(SFX(veldir_rhoBar)(L, b, f, VEL_IS_J(d)));
         if (b->kind == BC_RHO_REG || b->kind == BC_RHO_ZH) return FULLRHO(b->rhoBar);
     }
     if (d->type == PLBO_DYN_BOUNCEBACK || d->type == PLBO_DYN_NODYNAMICS) return d->rho;
@@ -564,13 +616,19 @@ static void SFX(cell_velocity)(const SFX(Lat)* L, size_t cell, REAL u[3]) {
             REAL invRho = INVRHO(b->rhoBar);
             int k;
             SFX(rhodir_j)(L, b, f, u);
-            for (k = 0; k < 3; ++k) { u[k] *= invRho; u[k] += 0.5*(REAL)0; }
+            for (k = 0; k < 3; ++k) { if (!VEL_IS_J(d)) u[k] *= invRho; u[k] += 0.5*(REAL)0; }
             return;
         }
         u[0] = b->u[0]; u[1] = b->u[1]; u[2] = b->u[2];
         return;
     }
     if (d->type == PLBO_DYN_BOUNCEBACK || d->type == PLBO_DYN_NODYNAMICS) { u[0] = u[1] = u[2] = (REAL)0; return; }
+    if (d->type == PLBO_DYN_INCBGK) {   /* IncBGKdynamics::computeVelocity isoThermalDynamics.hh:1389-1396: u = j * invRho0 */
+        REAL dummyRhoBar;
+        SFX(get_rhoBar_j)(L->q, f, &dummyRhoBar, u);
+        u[0] *= (REAL)1; u[1] *= (REAL)1; u[2] *= (REAL)1;
+        return;
+    }
     {
         REAL invRho;
         SFX(get_j)(L->q, f, u);
@@ -589,7 +647,7 @@ static REAL SFX(cell_rhoBar)(const SFX(Lat)* L, size_t cell) {
     int bi = L->bcIdx[cell];
     if (bi >= 0) {
         const SFX(Bc)* b = &L->bcs[bi];
-        if (b->kind == BC_VEL_REG || b->kind == BC_VEL_ZH) return SFX(veldir_rhoBar)(L, b, f);
+        if (b->kind == BC_VEL_REG || b->kind == BC_VEL_ZH) return SFX(veldir_rhoBar)(L, b, f, VEL_IS_J(d));
         if (b->kind == BC_RHO_REG || b->kind == BC_RHO_ZH) return b->rhoBar;
         { REAL rho = SFX(cell_density)(L, cell); return RHOBAR(rho); }
     }
@@ -613,7 +671,8 @@ static void SFX(fd_regularize)(SFX(Lat)* L, size_t cell, REAL rho, REAL dA_uB[3]
     pi[2] = (dA_uB[0][2]+dA_uB[2][0]) * sToPi;
     pi[4] = (dA_uB[1][2]+dA_uB[2][1]) * sToPi;
     SFX(cell_velocity)(L, cell, vel);
-    j[0] = rho*vel[0]; j[1] = rho*vel[1]; j[2] = rho*vel[2];
+    if (VEL_IS_J(d)) { j[0] = vel[0]; j[1] = vel[1]; j[2] = vel[2]; }      /* finiteDifferenceBoundaryProcessor3D.hh:200-205 */
+    else { j[0] = rho*vel[0]; j[1] = rho*vel[1]; j[2] = rho*vel[2]; }
     jSqr = j[0]*j[0] + j[1]*j[1] + j[2]*j[2];
     SFX(regularize)(L, d, L->f + cell * L->q, RHOBAR(rho), j, jSqr, pi);
 }

@@ -86,6 +86,7 @@ static Dynamics<T,D>* makeDynamics(std::string const& kind, double p1, double p2
     if (kind == "RLB")   return new RegularizedBGKdynamics<T,D>((T)p1);
     if (kind == "TRT")   return new TRTdynamics<T,D>((T)p1);
     if (kind == "SMAGO") return new SmagorinskyBGKdynamics<T,D>((T)p1, (T)p2);
+    if (kind == "INCBGK") return new IncBGKdynamics<T,D>((T)p1);
     if (kind == "BB")    return new BounceBack<T,D>((T)p1);
     if (kind == "NODYN") return new NoDynamics<T,D>((T)p1);
     fail("unknown dynamics " + kind);

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(ROOT, "libplb_b200.so")
 CSRC = os.path.join(ROOT, "csrc")
 
-DYN = {"BGK": 0, "RLB": 1, "TRT": 2, "SMAGO": 3, "BB": 4, "NODYN": 5}
+DYN = {"BGK": 0, "RLB": 1, "TRT": 2, "SMAGO": 3, "BB": 4, "NODYN": 5, "INCBGK": 6}
 BC = {"local": 0, "zouhe": 1}
 
 #: every symbol include/plb_b200.h declares (tests check the library exports them all)

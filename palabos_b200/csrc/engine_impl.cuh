@@ -592,7 +592,7 @@ private:
     }
 
     int add_dyn(int type, double p1, double p2) {
-        if (type < DYN_BGK || type > DYN_NODYNAMICS) throw PlbError("unknown dynamics id");
+        if (type < DYN_BGK || type > DYN_INCBGK) throw PlbError("unknown dynamics id");
         Dyn<T> d;
         std::memset(&d, 0, sizeof d);
         d.type = type;
@@ -947,6 +947,7 @@ private:
         case DYN_BGK:   if (odd) launch_sweep_as<DYN_BGK, false, true>(sl, a, 0);   else launch_sweep_as<DYN_BGK, false, false>(sl, a, 0); break;
         case DYN_RLB:   if (odd) launch_sweep_as<DYN_RLB, false, true>(sl, a, 1);   else launch_sweep_as<DYN_RLB, false, false>(sl, a, 1); break;
         case DYN_TRT:   if (odd) launch_sweep_as<DYN_TRT, false, true>(sl, a, 2);   else launch_sweep_as<DYN_TRT, false, false>(sl, a, 2); break;
+        case DYN_INCBGK: if (odd) launch_sweep_as<DYN_INCBGK, false, true>(sl, a, 5); else launch_sweep_as<DYN_INCBGK, false, false>(sl, a, 5); break;
         default:        if (odd) launch_sweep_as<DYN_SMAGO, false, true>(sl, a, 3); else launch_sweep_as<DYN_SMAGO, false, false>(sl, a, 3); break;
         }
     }

@@ -627,7 +627,8 @@ __device__ __forceinline__ void fd_regularize(const CellCtx<T>& cx, T* F, int c,
     pi[2] = (dA_uB[0][2] + dA_uB[2][0]) * sToPi;
     pi[4] = (dA_uB[1][2] + dA_uB[2][1]) * sToPi;
     L::cell_velocity(v.d, v.hasBc, v.b, v.f, vel);
-    j[0] = rho * vel[0]; j[1] = rho * vel[1]; j[2] = rho * vel[2];
+    if (L::vel_is_j(v.d.type)) { j[0] = vel[0]; j[1] = vel[1]; j[2] = vel[2]; }     // finiteDifferenceBoundaryProcessor3D.hh:200-205
+    else { j[0] = rho * vel[0]; j[1] = rho * vel[1]; j[2] = rho * vel[2]; }
     const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
     if (L::is_inert(v.d.type)) return;      // regularize is a no-op there: the populations stay
     L::regularize(v.d.type, v.f, L::rhoBarOf(rho), j, jSqr, pi);

@@ -13,7 +13,7 @@
 
 namespace plb200 {
 
-enum DynType : int { DYN_BGK = 0, DYN_RLB = 1, DYN_TRT = 2, DYN_SMAGO = 3, DYN_BOUNCEBACK = 4, DYN_NODYNAMICS = 5 };
+enum DynType : int { DYN_BGK = 0, DYN_RLB = 1, DYN_TRT = 2, DYN_SMAGO = 3, DYN_BOUNCEBACK = 4, DYN_NODYNAMICS = 5, DYN_INCBGK = 6 };
 enum BcKind : int { BC_VEL_REG = 0, BC_RHO_REG = 1, BC_VEL_ZH = 2, BC_RHO_ZH = 3, BC_STORE_VEL = 4 };
 enum ProcClass : int { PROC_PLANE = 0, PROC_EDGE = 1, PROC_CORNER = 2 };
 
@@ -271,6 +271,49 @@ struct LB {
         }
     }
 
+    /// bgk_ma2_collision_base(f, rhoBar, j, omega, invRho) dynamicsTemplates3D.h:2289-2368 (D3Q19), :467-571 (D3Q27): the form
+    /// with an explicit invRho, used by bgk_inc_collision (:2480-2482, :1680-1682) with invRho0.  Returns invRho^2 * jSqr.
+    PLB_HD static T bgk_ma2_collision_base(T* f, T rhoBar, const T j[3], T omega, T invRho) {
+        constexpr int h = H;
+        const T one_m_omega = (T)1 - omega;
+        const T t0_omega = t(0) * omega;
+        const T t1_omega = t(1) * omega;
+        const T t4_omega = t(4) * omega;
+        const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+        const T kx = (T)3 * j[0];
+        const T ky = (T)3 * j[1];
+        const T kz = (T)3 * j[2];
+        const T kxSqr_ = invRho / (T)2 * kx * kx;
+        const T kySqr_ = invRho / (T)2 * ky * ky;
+        const T kzSqr_ = invRho / (T)2 * kz * kz;
+        const T kxky_ = invRho * kx * ky;
+        const T kxkz_ = invRho * kx * kz;
+        const T kykz_ = invRho * ky * kz;
+        const T C1 = rhoBar + invRho * (T)3 * jSqr;
+        T C2, C3;
+        C3 = -kxSqr_ - kySqr_ - kzSqr_;
+        f[0] *= one_m_omega; f[0] += t0_omega * (C1 + C3);
+#define PLB_PAIR(I, TW) f[I] *= one_m_omega; f[I] += TW * (C1 + C2 + C3); f[I + h] *= one_m_omega; f[I + h] += TW * (C1 - C2 + C3);
+        C2 = -kx;       C3 = -kySqr_ - kzSqr_;   PLB_PAIR(1, t1_omega)
+        C2 = -ky;       C3 = -kxSqr_ - kzSqr_;   PLB_PAIR(2, t1_omega)
+        C2 = -kz;       C3 = -kxSqr_ - kySqr_;   PLB_PAIR(3, t1_omega)
+        C2 = -kx - ky;  C3 = kxky_ - kzSqr_;     PLB_PAIR(4, t4_omega)
+        C2 = -kx + ky;  C3 = -kxky_ - kzSqr_;    PLB_PAIR(5, t4_omega)
+        C2 = -kx - kz;  C3 = kxkz_ - kySqr_;     PLB_PAIR(6, t4_omega)
+        C2 = -kx + kz;  C3 = -kxkz_ - kySqr_;    PLB_PAIR(7, t4_omega)
+        C2 = -ky - kz;  C3 = kykz_ - kxSqr_;     PLB_PAIR(8, t4_omega)
+        C2 = -ky + kz;  C3 = -kykz_ - kxSqr_;    PLB_PAIR(9, t4_omega)
+        if constexpr (Q == 27) {
+            const T t10_omega = t(10) * omega;
+            C2 = -kx - ky - kz;  C3 = kxky_ + kxkz_ + kykz_;    PLB_PAIR(10, t10_omega)
+            C2 = -kx - ky + kz;  C3 = kxky_ - kxkz_ - kykz_;    PLB_PAIR(11, t10_omega)
+            C2 = -kx + ky - kz;  C3 = -kxky_ + kxkz_ - kykz_;   PLB_PAIR(12, t10_omega)
+            C2 = -kx + ky + kz;  C3 = -kxky_ - kxkz_ + kykz_;   PLB_PAIR(13, t10_omega)
+        }
+#undef PLB_PAIR
+        return invRho * invRho * jSqr;
+    }
+
     /// neqPiD3Q19 dynamicsTemplates3D.h:1903-1975 and neqPiD3Q27 :38-135 (fromPiToFneq0..9 / 0..13)
     PLB_HD static void neqPi(const T* pi, T* n) {
         const T xx = pi[0], xy = pi[1], xz = pi[2], yy = pi[3], yz = pi[4], zz = pi[5];
@@ -344,6 +387,12 @@ struct LB {
         get_rhoBar_j(f, rhoBar, j);
         uSqr = bgk_ma2_collision(f, rhoBar, j, omega);
     }
+    /// IncBGKdynamics::collide isoThermalDynamics.hh:1405-1417: BGK whose O(Ma^2) terms carry 1/rho0 (= 1) instead of 1/rho
+    PLB_HD static void collide_incbgk(T* f, T omega, T& rhoBar, T& uSqr) {
+        T j[3];
+        get_rhoBar_j(f, rhoBar, j);
+        uSqr = bgk_ma2_collision_base(f, rhoBar, j, omega, (T)1);
+    }
     /// RegularizedBGKdynamics::collide isoThermalDynamics.hh:1588-1602
     PLB_HD static void collide_rlb(T* f, T omega, T& rhoBar, T& uSqr) {
         T j[3], PiNeq[6];
@@ -393,6 +442,7 @@ struct LB {
         if (TYPE == DYN_RLB) { collide_rlb(f, omega, rhoBar, uSqr); return true; }
         if (TYPE == DYN_TRT) { collide_trt(f, omega, rhoBar, uSqr); return true; }
         if (TYPE == DYN_SMAGO) { collide_smago(f, omega, preFactor, rhoBar, uSqr); return true; }
+        if (TYPE == DYN_INCBGK) { collide_incbgk(f, omega, rhoBar, uSqr); return true; }
         if (TYPE == DYN_BOUNCEBACK) { collide_bounceback(f); return false; }
         return false;   // NoDynamics core/dynamics.hh:968-972
     }
@@ -404,6 +454,7 @@ struct LB {
         case DYN_RLB:        collide_rlb(f, d.omega, rhoBar, uSqr); return true;
         case DYN_TRT:        collide_trt(f, d.omega, rhoBar, uSqr); return true;
         case DYN_SMAGO:      collide_smago(f, d.omega, d.preFactor, rhoBar, uSqr); return true;
+        case DYN_INCBGK:     collide_incbgk(f, d.omega, rhoBar, uSqr); return true;
         case DYN_BOUNCEBACK: collide_bounceback(f); return false;
         default:             return false;
         }
@@ -415,10 +466,11 @@ struct LB {
 
     /// Dynamics::computeEquilibrium(iPop, rhoBar, j, jSqr): identical for BGK / RLB / TRT /
     /// Smagorinsky (isoThermalDynamics.hh:341-346, :1619-1624, trtDynamics.hh:138-143,
-    /// smagorinskyDynamics.hh:322-328); BounceBack / NoDynamics return 0 (core/dynamics.hh:800-805).
+    /// smagorinskyDynamics.hh:322-328); BounceBack / NoDynamics return 0 (core/dynamics.hh:800-805); IncBGK uses
+    /// invRho0 = 1 (isoThermalDynamics.hh:1428-1435).
     PLB_HD static T computeEquilibrium(int type, int i, T rhoBar, const T j[3], T jSqr) {
         if (is_inert(type)) return (T)0;
-        const T invRho = invRhoOf(rhoBar);
+        const T invRho = type == DYN_INCBGK ? (T)1 : invRhoOf(rhoBar);
         return bgk_ma2_equilibrium(i, rhoBar, invRho, j, jSqr);
     }
 
@@ -470,11 +522,16 @@ struct LB {
 
     /// VelocityDirichletBoundaryDynamics::computeRhoBar boundaryCondition/boundaryDynamics.hh:639-668
     /// (the descriptors on this path carry no external force: the 0.5*force terms vanish)
-    PLB_HD static T veldir_rhoBar(const Bc<T>& b, const T* f) {
+    /// velIsJ: the base dynamics treats the velocity as momentum (Dynamics::velIsJ, true for IncBGKdynamics,
+    /// isoThermalDynamics.hh:1437-1440; composites forward it, core/dynamics.hh:424-426)
+    PLB_HD static bool vel_is_j(int baseType) { return baseType == DYN_INCBGK; }
+
+    PLB_HD static T veldir_rhoBar(const Bc<T>& b, const T* f, bool velIsJ) {
         const T rhoOnWall = sub_sum(f, b.dir, 0);
         const T rhoNormal = sub_sum(f, b.dir, b.ori);
         const T uN = b.dir == 0 ? b.u[0] : (b.dir == 1 ? b.u[1] : b.u[2]);
         const T velNormal = (T)b.ori * (uN - 0.5 * (T)0);
+        if (velIsJ) return (T)2 * rhoNormal + rhoOnWall - velNormal;
         return ((T)2 * rhoNormal + rhoOnWall - 1 * velNormal) / ((T)1 + velNormal);
     }
 
@@ -492,12 +549,12 @@ struct LB {
     PLB_HD static bool is_rho_plane(int kind) { return kind == BC_RHO_REG || kind == BC_RHO_ZH; }
 
     /// computeRhoBarJ of the plane boundary dynamics: velocity boundaryDynamics.hh:680-701, density :822-828
-    PLB_HD static void plane_rhoBar_j(const Bc<T>& b, const T* f, T& rhoBar, T j[3]) {
+    PLB_HD static void plane_rhoBar_j(const Bc<T>& b, const T* f, T& rhoBar, T j[3], bool velIsJ) {
         if (is_vel_plane(b.kind)) {
-            rhoBar = veldir_rhoBar(b, f);
+            rhoBar = veldir_rhoBar(b, f, velIsJ);
             const T rho = fullRho(rhoBar);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) j[d] = rho * (b.u[d] - 0.5 * (T)0);
+            for (int d = 0; d < 3; ++d) j[d] = velIsJ ? (b.u[d] - 0.5 * (T)0) : rho * (b.u[d] - 0.5 * (T)0);
         } else {
             rhoBar = b.rhoBar;
             rhodir_j(b, f, j);
@@ -538,7 +595,7 @@ struct LB {
         // axis-aligned one) share the transverse-momentum correction: 4 for D3Q19, 8 for D3Q27.
         constexpr int nDiag = (Q == 19) ? 4 : 8;
         T rhoBar, j[3];
-        plane_rhoBar_j(b, f, rhoBar, j);
+        plane_rhoBar_j(b, f, rhoBar, j, vel_is_j(baseType));
         const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
 #pragma unroll
         for (int i = 1; i < Q; ++i) if (cdir(i, b.dir) == b.ori) {
@@ -573,7 +630,7 @@ struct LB {
     PLB_HD static void complete_populations(int baseType, const Bc<T>& b, T* f) {
         if (b.kind == BC_VEL_REG || b.kind == BC_RHO_REG) {
             T rhoBar, j[3], PiNeq[6];
-            plane_rhoBar_j(b, f, rhoBar, j);
+            plane_rhoBar_j(b, f, rhoBar, j, vel_is_j(baseType));
             const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
             boundary_PiNeq(baseType, b, f, rhoBar, j, jSqr, PiNeq);
             regularize(baseType, f, rhoBar, j, jSqr, PiNeq);
@@ -590,7 +647,7 @@ struct LB {
     ///  edges/corners fall through to the base dynamics (:83-87).
     PLB_HD static T cell_density(const Dyn<T>& d, bool hasBc, const Bc<T>& b, const T* f) {
         if (hasBc) {
-            if (is_vel_plane(b.kind)) return fullRho(veldir_rhoBar(b, f));
+            if (is_vel_plane(b.kind)) return fullRho(veldir_rhoBar(b, f, vel_is_j(d.type)));
             if (is_rho_plane(b.kind)) return fullRho(b.rhoBar);
         }
         if (is_inert(d.type)) return d.rho;
@@ -614,13 +671,19 @@ struct LB {
                 const T invRho = invRhoOf(b.rhoBar);
                 rhodir_j(b, f, u);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { u[k] *= invRho; u[k] += 0.5 * (T)0; }
+                for (int k = 0; k < 3; ++k) { if (!vel_is_j(d.type)) u[k] *= invRho; u[k] += 0.5 * (T)0; }
                 return;
             }
             u[0] = b.u[0]; u[1] = b.u[1]; u[2] = b.u[2];
             return;
         }
         if (is_inert(d.type)) { u[0] = u[1] = u[2] = (T)0; return; }
+        if (d.type == DYN_INCBGK) {            // IncBGKdynamics::computeVelocity isoThermalDynamics.hh:1389-1396: u = j * invRho0
+            T dummyRhoBar;
+            get_rhoBar_j(f, dummyRhoBar, u);
+            u[0] *= (T)1; u[1] *= (T)1; u[2] *= (T)1;
+            return;
+        }
         get_j(f, u);
         const T invRho = invRhoOf(get_rhoBar(f));
         u[0] *= invRho; u[1] *= invRho; u[2] *= invRho;
@@ -634,7 +697,7 @@ struct LB {
     /// boundaryDynamics.hh:639-668; density planes :254-257; StoreVelocityDynamics :342-346.
     PLB_HD static T cell_rhoBar(const Dyn<T>& d, bool hasBc, const Bc<T>& b, const T* f) {
         if (hasBc) {
-            if (is_vel_plane(b.kind)) return veldir_rhoBar(b, f);
+            if (is_vel_plane(b.kind)) return veldir_rhoBar(b, f, vel_is_j(d.type));
             if (is_rho_plane(b.kind)) return b.rhoBar;
             return rhoBarOf(cell_density(d, hasBc, b, f));
         }

@@ -190,6 +190,12 @@ CASES = {
     "periodic_bgk_q27_f32":     (lambda: periodic_box(8, 7, 9, 30, "BGK", 1.5, q=27, prec="f32"), "full"),
     "periodic_rlb_q27":         (lambda: periodic_box(8, 7, 9, 30, "RLB", 1.5, q=27), "full"),
     "periodic_trt_f32":         (lambda: periodic_box(8, 7, 9, 30, "TRT", 1.5, prec="f32"), "full"),
+    # IncBGKdynamics (the dynamics of the fork's own application, viscosityTest): bulk, under regularized / Zou-He boundaries,
+    # around BounceBack voxels, D3Q27 and fp32
+    "cavity_incbgk_10x9x8":     (lambda: cavity(10, 9, 8, 40, dyn="INCBGK"), "full"),
+    "cavity_incbgk_q27_f32":    (lambda: cavity(8, 8, 9, 30, dyn="INCBGK", q=27, prec="f32"), "full"),
+    "obstacle_incbgk_zouhe":    (lambda: obstacle(20, 10, 9, 40, dyn="INCBGK", omega=1.6), "full"),
+    "periodic_incbgk_q27":      (lambda: periodic_box(8, 7, 9, 30, "INCBGK", 1.7, q=27), "full"),
     # edge cases
     "mixed_omega_11x8x9":       (lambda: mixed_omega(11, 8, 9, 40), "full"),
     "inlet_outlet_local":       (lambda: inlet_outlet_local(12, 9, 8, 40), "full"),

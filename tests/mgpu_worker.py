@@ -18,7 +18,8 @@ from dist_engine import DistEngine  # noqa: E402
 from scenario import replay, run_oracle  # noqa: E402
 
 NAMES = ["cavity_bgk_12", "cavity_zouhe_10x9x8", "channel_trt_16x12x10", "channel_smago_q27_f32",
-         "obstacle_zouhe_24x12x10", "mixed_omega_11x8x9", "periodic_rlb_q27", "periodic_trt_f32", "inlet_outlet_local"]
+         "obstacle_zouhe_24x12x10", "mixed_omega_11x8x9", "periodic_rlb_q27", "periodic_trt_f32", "inlet_outlet_local",
+         "cavity_incbgk_10x9x8"]
 
 
 def main():

@@ -28,7 +28,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_DRIVER = os.path.join(ORACLE_DIR, "_ref", "ref_driver")
 REF_DRIVER_F32 = os.path.join(ORACLE_DIR, "_ref", "ref_driver_f32")
 
-DYN = {"BGK": 0, "RLB": 1, "TRT": 2, "SMAGO": 3, "BB": 4, "NODYN": 5}
+DYN = {"BGK": 0, "RLB": 1, "TRT": 2, "SMAGO": 3, "BB": 4, "NODYN": 5, "INCBGK": 6}
 BC = {"local": 0, "zouhe": 1}
 
 

@@ -52,11 +52,13 @@ def test_cavity3d_cpp_matches_oracle(shape, q):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("model,prec", [("trt", "f64"), ("smago27", "f32")])
+@pytest.mark.parametrize("model,prec", [("trt", "f64"), ("smago27", "f32"), ("incbgk", "f64")])
 def test_channel3d_cpp_matches_oracle(model, prec):
     out = subprocess.run([_exe("channel3d"), "16", "12", "10", "40", model, prec], check=True, capture_output=True, text=True).stdout
     if model == "trt":
         sc = channel(16, 12, 10, 40)
+    elif model == "incbgk":
+        sc = channel(16, 12, 10, 40, dyn="INCBGK")
     else:
         sc = channel(16, 12, 10, 40, dyn="SMAGO", omega=1.9, q=27, cs=0.14, prec="f32")
     want = run_oracle(sc)["stats"][-1]

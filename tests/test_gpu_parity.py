@@ -99,6 +99,8 @@ SLAB_CASES = {
     "mixed_omega_11x8x9": 3,
     "inlet_outlet_local": 2,
     "thin_4x5x3": 2,
+    "cavity_incbgk_10x9x8": 3,
+    "obstacle_incbgk_zouhe": 4,
 }
 
 
