@@ -320,17 +320,23 @@ __device__ __forceinline__ void reduce_stats(double sRho, double sU, double mU, 
 /// completePopulations of a plane boundary cell with (direction, orientation) turned into compile-time
 /// constants, as the reference's templates <direction, orientation> have them
 /// (WrappedLocalBoundaryFunctional3D::process boundaryCondition/wrappedLocalBoundaryProcessor3D.hh:42-62).
-template <class T, int Q>
-__device__ __forceinline__ void complete_by_face(int baseType, Bc<T> b, T* f) {
+template <class T, int Q, bool INC>
+__device__ __forceinline__ void complete_by_face_as(int baseType, Bc<T> b, T* f) {
     using L = LB<T, Q>;
     switch (b.dir * 2 + (b.ori > 0 ? 1 : 0)) {
-    case 0: b.dir = 0; b.ori = -1; L::complete_populations(baseType, b, f); break;
-    case 1: b.dir = 0; b.ori = +1; L::complete_populations(baseType, b, f); break;
-    case 2: b.dir = 1; b.ori = -1; L::complete_populations(baseType, b, f); break;
-    case 3: b.dir = 1; b.ori = +1; L::complete_populations(baseType, b, f); break;
-    case 4: b.dir = 2; b.ori = -1; L::complete_populations(baseType, b, f); break;
-    default: b.dir = 2; b.ori = +1; L::complete_populations(baseType, b, f); break;
+    case 0: b.dir = 0; b.ori = -1; L::template complete_populations<INC>(baseType, b, f); break;
+    case 1: b.dir = 0; b.ori = +1; L::template complete_populations<INC>(baseType, b, f); break;
+    case 2: b.dir = 1; b.ori = -1; L::template complete_populations<INC>(baseType, b, f); break;
+    case 3: b.dir = 1; b.ori = +1; L::template complete_populations<INC>(baseType, b, f); break;
+    case 4: b.dir = 2; b.ori = -1; L::template complete_populations<INC>(baseType, b, f); break;
+    default: b.dir = 2; b.ori = +1; L::template complete_populations<INC>(baseType, b, f); break;
     }
+}
+template <class T, int Q>
+__device__ __forceinline__ void complete_by_face(int baseType, const Bc<T>& b, T* f) {
+    // IncBGK as base dynamics (velIsJ, invRho0) is its own instantiation: the usual one stays as lean as it was
+    if (baseType == DYN_INCBGK) complete_by_face_as<T, Q, true>(baseType, b, f);
+    else complete_by_face_as<T, Q, false>(baseType, b, f);
 }
 
 /// Out-of-line form for the sweep and the on-the-fly readers: the populations travel through local

@@ -468,10 +468,16 @@ struct LB {
     /// Smagorinsky (isoThermalDynamics.hh:341-346, :1619-1624, trtDynamics.hh:138-143,
     /// smagorinskyDynamics.hh:322-328); BounceBack / NoDynamics return 0 (core/dynamics.hh:800-805); IncBGK uses
     /// invRho0 = 1 (isoThermalDynamics.hh:1428-1435).
-    PLB_HD static T computeEquilibrium(int type, int i, T rhoBar, const T j[3], T jSqr) {
+    /// INC: the base dynamics is IncBGK -- a compile-time fact in the plane-completion family below, so that the common
+    /// (compressible) instantiation carries no trace of it
+    template <bool INC>
+    PLB_HD static T computeEquilibriumT(int type, int i, T rhoBar, const T j[3], T jSqr) {
         if (is_inert(type)) return (T)0;
-        const T invRho = type == DYN_INCBGK ? (T)1 : invRhoOf(rhoBar);
+        const T invRho = INC ? (T)1 : invRhoOf(rhoBar);
         return bgk_ma2_equilibrium(i, rhoBar, invRho, j, jSqr);
+    }
+    PLB_HD static T computeEquilibrium(int type, int i, T rhoBar, const T j[3], T jSqr) {
+        return type == DYN_INCBGK ? computeEquilibriumT<true>(type, i, rhoBar, j, jSqr) : computeEquilibriumT<false>(type, i, rhoBar, j, jSqr);
     }
 
     /// latticeBoltzmann/offEquilibriumTemplates.h:91-114 (generic; no 3D specialisation exists)
@@ -494,17 +500,22 @@ struct LB {
 
     /// IsoThermalBulkDynamics::regularize basicDynamics/isoThermalDynamics.hh:54-70;
     /// BounceBack/NoDynamics::regularize are no-ops (core/dynamics.hh:807-811, :986-990)
-    PLB_HD static void regularize(int type, T* f, T rhoBar, const T j[3], T jSqr, const T PiNeq[6]) {
+    template <bool INC>
+    PLB_HD static void regularizeT(int type, T* f, T rhoBar, const T j[3], T jSqr, const T PiNeq[6]) {
         if (is_inert(type)) return;
-        f[0] = computeEquilibrium(type, 0, rhoBar, j, jSqr) + fromPiToFneq(0, PiNeq);
+        f[0] = computeEquilibriumT<INC>(type, 0, rhoBar, j, jSqr) + fromPiToFneq(0, PiNeq);
 #pragma unroll
         for (int i = 1; i <= H; ++i) {
-            f[i] = computeEquilibrium(type, i, rhoBar, j, jSqr);
-            f[i + H] = computeEquilibrium(type, i + H, rhoBar, j, jSqr);
+            f[i] = computeEquilibriumT<INC>(type, i, rhoBar, j, jSqr);
+            f[i + H] = computeEquilibriumT<INC>(type, i + H, rhoBar, j, jSqr);
             const T fNeq = fromPiToFneq(i, PiNeq);
             f[i] += fNeq;
             f[i + H] += fNeq;
         }
+    }
+    PLB_HD static void regularize(int type, T* f, T rhoBar, const T j[3], T jSqr, const T PiNeq[6]) {
+        if (type == DYN_INCBGK) regularizeT<true>(type, f, rhoBar, j, jSqr, PiNeq);
+        else regularizeT<false>(type, f, rhoBar, j, jSqr, PiNeq);
     }
 
     // ---------------------------------------------------------------- plane boundary dynamics
@@ -562,13 +573,14 @@ struct LB {
     }
 
     /// boundaryTemplates<..>::compute_PiNeq boundaryCondition/boundaryTemplates.h:45-87
+    template <bool INC>
     PLB_HD static void boundary_PiNeq(int baseType, const Bc<T>& b, const T* f, T rhoBar, const T j[3], T jSqr, T PiNeq[6]) {
         T fNeq[Q];
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
             const int cd = cdir(i, b.dir);
-            if (cd == 0) fNeq[i] = f[i] - computeEquilibrium(baseType, i, rhoBar, j, jSqr);
-            else if (cd == b.ori) fNeq[i] = f[i] - computeEquilibrium(baseType, i, rhoBar, j, jSqr);
+            if (cd == 0) fNeq[i] = f[i] - computeEquilibriumT<INC>(baseType, i, rhoBar, j, jSqr);
+            else if (cd == b.ori) fNeq[i] = f[i] - computeEquilibriumT<INC>(baseType, i, rhoBar, j, jSqr);
             else fNeq[i] = (T)0;
         }
         int iPi = 0;
@@ -590,18 +602,19 @@ struct LB {
     }
 
     /// ZouHeClosure boundaryCondition/zouHeDynamics.hh:43-115
+    template <bool INC>
     PLB_HD static void zouhe_closure(int baseType, const Bc<T>& b, T* f) {
         // missing populations = opposites of subIndex<dir,ori>; the diagonal ones (all but the single
         // axis-aligned one) share the transverse-momentum correction: 4 for D3Q19, 8 for D3Q27.
         constexpr int nDiag = (Q == 19) ? 4 : 8;
         T rhoBar, j[3];
-        plane_rhoBar_j(b, f, rhoBar, j, vel_is_j(baseType));
+        plane_rhoBar_j(b, f, rhoBar, j, INC);
         const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
 #pragma unroll
         for (int i = 1; i < Q; ++i) if (cdir(i, b.dir) == b.ori) {
             // pop = opp(i) is missing, its opposite i is known
-            f[opp(i)] = f[i] - computeEquilibrium(baseType, i, rhoBar, j, jSqr)
-                             + computeEquilibrium(baseType, opp(i), rhoBar, j, jSqr);
+            f[opp(i)] = f[i] - computeEquilibriumT<INC>(baseType, i, rhoBar, j, jSqr)
+                             + computeEquilibriumT<INC>(baseType, opp(i), rhoBar, j, jSqr);
         }
         // momentTemplates::compute_rho_uLb momentTemplates3D.h:437-445
         T falseRhoBar, falseJ[3], falseU[3], diff[3];
@@ -627,15 +640,16 @@ struct LB {
     /// RegularizedVelocity/DensityBoundaryDynamics regularizedBoundaryDynamics.hh:94-109, :166-181;
     /// ZouHeVelocity/PressureDynamics zouHeDynamics.hh:166-169, :222-225.  StoreVelocityDynamics
     /// (edges, corners) inherits the empty completePopulations (boundaryDynamics.hh:185-187).
+    template <bool INC>
     PLB_HD static void complete_populations(int baseType, const Bc<T>& b, T* f) {
         if (b.kind == BC_VEL_REG || b.kind == BC_RHO_REG) {
             T rhoBar, j[3], PiNeq[6];
-            plane_rhoBar_j(b, f, rhoBar, j, vel_is_j(baseType));
+            plane_rhoBar_j(b, f, rhoBar, j, INC);
             const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
-            boundary_PiNeq(baseType, b, f, rhoBar, j, jSqr, PiNeq);
-            regularize(baseType, f, rhoBar, j, jSqr, PiNeq);
+            boundary_PiNeq<INC>(baseType, b, f, rhoBar, j, jSqr, PiNeq);
+            regularizeT<INC>(baseType, f, rhoBar, j, jSqr, PiNeq);
         } else if (b.kind == BC_VEL_ZH || b.kind == BC_RHO_ZH) {
-            zouhe_closure(baseType, b, f);
+            zouhe_closure<INC>(baseType, b, f);
         }
     }
 
