@@ -15,6 +15,7 @@
 #include <vector>
 #include "engine.h"
 #include "kernels.cuh"
+#include "sweep_launch.cuh"
 #include "nccl_dyn.h"
 
 namespace plb200 {
@@ -897,7 +898,6 @@ private:
 
     template <int MAIN, bool GEN, bool ODD, bool PLANES>
     void launch_sweep_with(Slab& sl, SweepArgs<T>& a, int mainIdx) {
-        auto kern = sweep_kernel<T, Q, MAIN, GEN, ODD, PLANES>;
         constexpr int threads = sweep_threads(ODD);
         const int nTiles = (a.cellEnd - a.cellBegin + threads - 1) / threads;
         int grid = std::max(1, std::min(nTiles, numSMs_ * sweep_grid_factor(ODD)));
@@ -915,7 +915,7 @@ private:
             while (profEvents_.size() < profUsed_ + 2) { cudaEvent_t e; PLB_CUDA(cudaEventCreate(&e)); profEvents_.push_back(e); }
             PLB_CUDA(cudaEventRecord(profEvents_[profUsed_], stream_));
         }
-        kern<<<grid, threads, 0, stream_>>>(a);
+        launch_sweep_kernel<T, Q, MAIN, GEN, ODD, PLANES>(grid, stream_, a);
         launched();
         if (prof) { PLB_CUDA(cudaEventRecord(profEvents_[profUsed_ + 1], stream_)); profUsed_ += 2; }
     }

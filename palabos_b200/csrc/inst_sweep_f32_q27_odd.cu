@@ -1,0 +1,7 @@
+// palabos_b200/csrc/inst_sweep_f32_q27_odd.cu -- the odd half of the sweep for T = float, D3Q27 (see sweep_launch.cuh)
+#define PLB_SWEEP_DEFINE_LAUNCH
+#include "sweep_launch.cuh"
+
+namespace plb200 {
+PLB_INSTANTIATE_SWEEPS(float, 27, true)
+}  // namespace plb200

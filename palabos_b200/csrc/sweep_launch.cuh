@@ -1,0 +1,35 @@
+// palabos_b200/csrc/sweep_launch.cuh -- the sweep kernels are compiled in translation units of their own
+// (inst_sweep_*.cu: one per value type, velocity set and AA half), so that the build spreads over all cores;
+// the engine only sees this declaration.
+#pragma once
+#include "kernels.cuh"
+
+namespace plb200 {
+
+/// sweep_kernel<T,Q,MAIN,GENERIC,ODD,PLANES><<<grid, sweep_threads(ODD), 0, stream>>>(a)
+template <class T, int Q, int MAIN, bool GENERIC, bool ODD, bool PLANES>
+void launch_sweep_kernel(int grid, cudaStream_t stream, const SweepArgs<T>& a);
+
+#ifdef PLB_SWEEP_DEFINE_LAUNCH
+template <class T, int Q, int MAIN, bool GENERIC, bool ODD, bool PLANES>
+void launch_sweep_kernel(int grid, cudaStream_t stream, const SweepArgs<T>& a) {
+    sweep_kernel<T, Q, MAIN, GENERIC, ODD, PLANES><<<grid, sweep_threads(ODD), 0, stream>>>(a);
+}
+/// every combination the engine launches (LatticeImpl::launch_sweep): the five collision models compiled in as the
+/// background dynamics, and the generic form that reads the model from the dynamics table; with and without fused planes
+#define PLB_INSTANTIATE_SWEEPS(T, Q, ODD)                                                        \
+    template void launch_sweep_kernel<T, Q, DYN_BGK, false, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);    \
+    template void launch_sweep_kernel<T, Q, DYN_BGK, false, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);     \
+    template void launch_sweep_kernel<T, Q, DYN_RLB, false, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);    \
+    template void launch_sweep_kernel<T, Q, DYN_RLB, false, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);     \
+    template void launch_sweep_kernel<T, Q, DYN_TRT, false, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);    \
+    template void launch_sweep_kernel<T, Q, DYN_TRT, false, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);     \
+    template void launch_sweep_kernel<T, Q, DYN_SMAGO, false, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);  \
+    template void launch_sweep_kernel<T, Q, DYN_SMAGO, false, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);   \
+    template void launch_sweep_kernel<T, Q, DYN_INCBGK, false, ODD, false>(int, cudaStream_t, const SweepArgs<T>&); \
+    template void launch_sweep_kernel<T, Q, DYN_INCBGK, false, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);  \
+    template void launch_sweep_kernel<T, Q, DYN_BGK, true, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);     \
+    template void launch_sweep_kernel<T, Q, DYN_BGK, true, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);
+#endif
+
+}  // namespace plb200
