@@ -320,6 +320,51 @@ int plbo_collide_and_stream(plbo_lattice* L, int n) {
     return 1;
 }
 
+/* ---- the external-moment sweep, see ext_step in plb_oracle_impl.h ---- */
+
+/* generateMultiScalarField / generateMultiTensorField<3> + the two integrateProcessingFunctional calls, src/variables.hh:475-486 */
+int plbo_enable_external_rhoj(plbo_lattice* L) {
+    size_t n = (size_t)NX(L) * NY(L) * NZ(L);
+    if (L->prec == 8) { if (!L->d->ext) L->d->ext = (double*)calloc(4 * n, sizeof(double)); }
+    else              { if (!L->s->ext) L->s->ext = (float*)calloc(4 * n, sizeof(float)); }
+    return 1;
+}
+static int has_ext(plbo_lattice* L) { return DISPATCH(L, L->d->ext != 0, L->s->ext != 0); }
+
+/* n x { lattice.executeInternalProcessors(); lattice.incrementTime(); } viscosityTest/src/test.cpp:64-65 */
+int plbo_execute_internal_processors(plbo_lattice* L, int n) {
+    int k;
+    if (!has_ext(L)) return fail("external rhoBar / j fields are not enabled");
+    for (k = 0; k < n; ++k) { if (L->prec == 8) ext_step_f64(L->d); else ext_step_f32(L->s); }
+    return 1;
+}
+
+/* applyProcessingFunctional(new BoxRhoBarJfunctional3D, box, rhoBarJarg) src/variables.hh:650 */
+int plbo_apply_rhobar_j(plbo_lattice* L, const int box[6]) {
+    if (!has_ext(L)) return fail("external rhoBar / j fields are not enabled");
+    if (!box_ok(L, box)) return fail("box outside the lattice");
+    if (L->prec == 8) box_rhoBar_j_f64(L->d, box); else box_rhoBar_j_f32(L->s, box);
+    return 1;
+}
+
+/* the fields as T [cells of box][rhoBar, jx, jy, jz] */
+static int transfer_ext(plbo_lattice* L, const int box[6], void* data, size_t bytes, int up) {
+    int x, y, z;
+    size_t k = 0, esz = (size_t)L->prec;
+    if (!has_ext(L)) return fail("external rhoBar / j fields are not enabled");
+    if (!box_ok(L, box)) return fail("box outside the lattice");
+    if (bytes != box_cells(box) * 4 * esz) return fail("buffer size does not match the box");
+    for (x = box[0]; x <= box[1]; ++x) for (y = box[2]; y <= box[3]; ++y) for (z = box[4]; z <= box[5]; ++z, ++k) {
+        size_t cell = ((size_t)x * NY(L) + y) * NZ(L) + z;
+        char* fld = L->prec == 8 ? (char*)(L->d->ext + cell * 4) : (char*)(L->s->ext + cell * 4);
+        if (up) memcpy(fld, (char*)data + k * 4 * esz, 4 * esz);
+        else    memcpy((char*)data + k * 4 * esz, fld, 4 * esz);
+    }
+    return 1;
+}
+int plbo_upload_rhobar_j(plbo_lattice* L, const int box[6], const void* data, size_t bytes) { return transfer_ext(L, box, (void*)data, bytes, 1); }
+int plbo_download_rhobar_j(plbo_lattice* L, const int box[6], void* data, size_t bytes) { return transfer_ext(L, box, data, bytes, 0); }
+
 /* out3 = { average rhoBar, average uSqr, max uSqr } (core/latticeStatistics.h:32-34) */
 int plbo_get_stored_statistics(plbo_lattice* L, double out3[3], uint64_t* n) {
     if (L->prec == 8) { out3[0] = L->d->avRhoBar; out3[1] = L->d->avUSqr; out3[2] = L->d->maxUSqr; if (n) *n = L->d->numCells; }

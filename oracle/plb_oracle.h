@@ -57,6 +57,16 @@ int plbo_compute_average_energy(plbo_lattice* L, const int box[6], double* out);
 int plbo_compute_average_density(plbo_lattice* L, const int box[6], double* out);
 int plbo_compute_density_velocity(plbo_lattice* L, const int box[6], void* rho_u, size_t bytes);
 
+/* External-moment sweep: ExternalRhoJcollideAndStream3D at level 0 + BoxRhoBarJfunctional3D at
+ * level 3 (basicDynamics/dynamicsProcessor3D.hh:41-195, dataProcessors/dataAnalysisFunctional3D.hh:528-548).  The lattice
+ * must have been created one cell larger on every non-periodic side, with plbo_set_statistics_box = the bulk: the
+ * extra layer is the reference's envelope, which this sweep collides and streams (tests/scenario.py does the shift). */
+int plbo_enable_external_rhoj(plbo_lattice* L);
+int plbo_execute_internal_processors(plbo_lattice* L, int n_steps);
+int plbo_apply_rhobar_j(plbo_lattice* L, const int box[6]);
+int plbo_upload_rhobar_j(plbo_lattice* L, const int box[6], const void* data, size_t bytes);
+int plbo_download_rhobar_j(plbo_lattice* L, const int box[6], void* data, size_t bytes);
+
 /* per-cell functors, exported so that unit tests can check the device functors one by one */
 int plbo_collide_cell(int q, int precision_bytes, int dynamics, double p1, double p2,
                       void* f, double* rhoBar_uSqr);

@@ -24,6 +24,7 @@ typedef struct {
     SFX(Bc)* bcs; int nBc, capBc;
     Proc* procs; int nProc, capProc;
     int statBox[6];
+    REAL* ext;                   /* external rhoBar / j fields [x][y][z][rhoBar,jx,jy,jz] (ScalarField3D + TensorField3D<3>) or NULL */
     double tmpSumRhoBar, tmpSumUSqr, tmpMaxUSqr; uint64_t tmpN;   /* running (core/blockStatistics.cpp:205-229) */
     double avRhoBar, avUSqr, maxUSqr; uint64_t numCells;          /* public, after evaluate() (:77-120) */
 } SFX(Lat);
@@ -121,6 +122,32 @@ static void SFX(rhoBar_j_PiNeq)(int q, const REAL* f, REAL cs2, REAL* rhoBar, RE
     PiNeq[0] = xp+xm - cs2*(*rhoBar) - invRho*j[0]*j[0];
     PiNeq[3] = yp+ym - cs2*(*rhoBar) - invRho*j[1]*j[1];
     PiNeq[5] = zp+zm - cs2*(*rhoBar) - invRho*j[2]*j[2];
+    if (q == 19) {
+        PiNeq[1] = f[4] - f[5] + f[13] - f[14] - invRho*j[0]*j[1];
+        PiNeq[2] = f[6] - f[7] + f[15] - f[16] - invRho*j[0]*j[2];
+        PiNeq[4] = f[8] - f[9] + f[17] - f[18] - invRho*j[1]*j[2];
+    } else {
+        PiNeq[1] = f[4] - f[5] + f[10] + f[11] - f[12] - f[13]
+                   + f[17] - f[18] + f[23] + f[24] - f[25] - f[26]
+                   - invRho*j[0]*j[1];
+        PiNeq[2] = f[6] - f[7] + f[10] - f[11] + f[12] - f[13]
+                   + f[19] - f[20] + f[23] - f[24] + f[25] - f[26]
+                   - invRho*j[0]*j[2];
+        PiNeq[4] = f[8] - f[9] + f[10] - f[11] - f[12] + f[13]
+                   + f[21] - f[22] + f[23] - f[24] - f[25] + f[26]
+                   -invRho*j[1]*j[2];
+    }
+}
+
+/* momentTemplates<T,Descriptor>::compute_PiNeq(cell, rhoBar, j, PiNeq) latticeBoltzmann/momentTemplates.h:118-123 ->
+ * momentTemplatesImpl::compute_PiNeq(f, rhoBar, j, PiNeq, invRho) momentTemplates3D.h:482-497 (D3Q19), :191-212 (D3Q27):
+ * the off-equilibrium stress from the populations and EXTERNALLY supplied moments. */
+static void SFX(compute_PiNeq)(int q, const REAL* f, REAL cs2, REAL rhoBar, const REAL j[3], REAL PiNeq[6]) {
+    REAL xm, xp, ym, yp, zm, zp, invRho = INVRHO(rhoBar);
+    SFX(partial_rho)(q, f, &xm, 0, &xp, &ym, &yp, &zm, &zp);
+    PiNeq[0] = xp+xm - cs2*rhoBar - invRho*j[0]*j[0];
+    PiNeq[3] = yp+ym - cs2*rhoBar - invRho*j[1]*j[1];
+    PiNeq[5] = zp+zm - cs2*rhoBar - invRho*j[2]*j[2];
     if (q == 19) {
         PiNeq[1] = f[4] - f[5] + f[13] - f[14] - invRho*j[0]*j[1];
         PiNeq[2] = f[6] - f[7] + f[15] - f[16] - invRho*j[0]*j[2];
@@ -425,6 +452,61 @@ static int SFX(collide_cell)(const SFX(Lat)* L, const SFX(Dyn)* d, REAL* f, REAL
     return 1;
 }
 
+/* Dynamics::collideExternal(cell, rhoBar, j, thetaBar, stat) with moments taken from fields (basicDynamics/
+ * dynamicsProcessor3D.hh:41-76): BGK isoThermalDynamics.hh:333-338, IncBGK :1422-1427, RegularizedBGK :1605-1615,
+ * TRT complexDynamics/trtDynamics.hh:102-134, SmagorinskyBGK smagorinskyDynamics.hh:306-320, BounceBack
+ * core/dynamics.hh:793-799, NoDynamics :974-978.  (Statistics are not restated: the fork's application never evaluates
+ * them in this mode -- executeInternalProcessors() + incrementTime(), viscosityTest/src/test.cpp:64-65.) */
+static void SFX(collide_external_cell)(const SFX(Lat)* L, const SFX(Dyn)* d, REAL* f, REAL rhoBar, const REAL j[3]) {
+    const int q = L->q, h = q / 2;
+    REAL PiNeq[6];
+    int i;
+    switch (d->type) {
+    case PLBO_DYN_BGK:
+        SFX(bgk_ma2_collision)(L, f, rhoBar, j, d->omega);
+        break;
+    case PLBO_DYN_INCBGK:
+        SFX(bgk_ma2_collision_base)(L, f, rhoBar, j, d->omega, (REAL)1);
+        break;
+    case PLBO_DYN_RLB: {
+        REAL invRho;
+        SFX(compute_PiNeq)(q, f, L->cs2, rhoBar, j, PiNeq);
+        invRho = INVRHO(rhoBar);
+        SFX(rlb_collision)(L, f, rhoBar, invRho, j, PiNeq, d->omega);
+        break; }
+    case PLBO_DYN_TRT: {
+        const REAL sPlus = d->omega;
+        const REAL sMinus = (REAL)1.1;
+        REAL eq[27], eq_plus[14], eq_minus[14], f_plus[14], f_minus[14], jSqr, invRho;
+        jSqr = j[0]*j[0] + j[1]*j[1] + j[2]*j[2];
+        invRho = INVRHO(rhoBar);
+        SFX(bgk_ma2_equilibria)(L, rhoBar, invRho, j, jSqr, eq);
+        for (i = 1; i <= h; ++i) {
+            eq_plus[i]  = 0.5*(eq[i] + eq[i+h]);
+            eq_minus[i] = 0.5*(eq[i] - eq[i+h]);
+            f_plus[i]   = 0.5*(f[i] + f[i+h]);
+            f_minus[i]  = 0.5*(f[i] - f[i+h]);
+        }
+        f[0] += -sPlus*f[0] + sPlus*eq[0];
+        for (i = 1; i <= h; ++i) {
+            f[i]   += -sPlus*(f_plus[i]-eq_plus[i]) - sMinus*(f_minus[i]-eq_minus[i]);
+            f[i+h] += -sPlus*(f_plus[i]-eq_plus[i]) + sMinus*(f_minus[i]-eq_minus[i]);
+        }
+        break; }
+    case PLBO_DYN_SMAGO: {
+        REAL omega;
+        SFX(compute_PiNeq)(q, f, L->cs2, rhoBar, j, PiNeq);
+        omega = SFX(smago_omega)(d->omega, d->preFactor, rhoBar, PiNeq);
+        SFX(bgk_ma2_collision)(L, f, rhoBar, j, omega);
+        break; }
+    case PLBO_DYN_BOUNCEBACK:
+        for (i = 1; i <= h; ++i) { REAL tmp = f[i]; f[i] = f[i+h]; f[i+h] = tmp; }
+        break;
+    default:
+        break;
+    }
+}
+
 /* ------------------------------------------------------------- regularization ---- */
 
 /* latticeBoltzmann/offEquilibriumTemplates.h:91-114 (generic; no 3D specialisation exists) */
@@ -655,6 +737,42 @@ static REAL SFX(cell_rhoBar)(const SFX(Lat)* L, size_t cell) {
     return SFX(get_rhoBar)(L->q, f);
 }
 
+/* Dynamics::computeRhoBarJ of whatever sits on the cell (what BoxRhoBarJfunctional3D stores,
+ * dataProcessors/dataAnalysisFunctional3D.hh:528-548):
+ *  bulk get_rhoBar_j core/dynamics.hh:357-361; BounceBack rhoBar(rho), 0 :880-885; NoDynamics 1 - SkordosFactor, 0 :1061-1066;
+ *  velocity planes boundaryDynamics.hh:682-701; density planes :816-822;
+ *  StoreVelocityDynamics (edges, corners) rho = computeDensity, j = rho * velocity :348-359 */
+static void SFX(cell_rhoBar_j)(const SFX(Lat)* L, size_t cell, REAL* rhoBar, REAL j[3]) {
+    const REAL* f = L->f + cell * L->q;
+    const SFX(Dyn)* d = SFX(dyn_of)(L, cell);
+    int bi = L->bcIdx[cell], k;
+    if (bi >= 0) {
+        const SFX(Bc)* b = &L->bcs[bi];
+        if (b->kind == BC_STORE_VEL) {
+            REAL rho = SFX(cell_density)(L, cell);
+            *rhoBar = RHOBAR(rho);
+            for (k = 0; k < 3; ++k) j[k] = rho * (b->u[k] - 0.5*(REAL)0);
+        } else {
+            SFX(plane_rhoBar_j)(L, b, f, rhoBar, j, VEL_IS_J(d));
+        }
+        return;
+    }
+    if (d->type == PLBO_DYN_BOUNCEBACK) { *rhoBar = RHOBAR(d->rho); j[0] = j[1] = j[2] = (REAL)0; return; }
+    if (d->type == PLBO_DYN_NODYNAMICS) { *rhoBar = (REAL)1 - (REAL)1; j[0] = j[1] = j[2] = (REAL)0; return; }
+    SFX(get_rhoBar_j)(L->q, f, rhoBar, j);
+}
+
+/* BoxRhoBarJfunctional3D::processGenericBlocks dataAnalysisFunctional3D.hh:528-548 (cells of the bulk only) */
+static void SFX(box_rhoBar_j)(SFX(Lat)* L, const int box[6]) {
+    int x, y, z;
+    for (x = box[0]; x <= box[1]; ++x) for (y = box[2]; y <= box[3]; ++y) for (z = box[4]; z <= box[5]; ++z) {
+        size_t cell = CELL(L, x, y, z);
+        const int* b = L->statBox;
+        if (x < b[0] || x > b[1] || y < b[2] || y > b[3] || z < b[4] || z > b[5]) continue;
+        SFX(cell_rhoBar_j)(L, cell, &L->ext[4*cell], &L->ext[4*cell + 1]);
+    }
+}
+
 /* ------------------------------------------------ non-local boundary processors ---- */
 
 /* common tail of Outer{Edge,Corner}Functional3D::processCell
@@ -797,6 +915,39 @@ static void SFX(step)(SFX(Lat)* L) {
     L->tmpSumRhoBar = 0.; L->tmpSumUSqr = 0.; L->tmpMaxUSqr = -DBL_MAX; L->tmpN = 0;
 }
 
+/* One executeInternalProcessors() + incrementTime() of a lattice that carries ExternalRhoJcollideAndStream3D at level 0
+ * and BoxRhoBarJfunctional3D at level 3 (src/variables.hh:485-486, viscosityTest/src/test.cpp:64-65).  The sweep
+ * (basicDynamics/dynamicsProcessor3D.hh:108-195) works on the bulk ENLARGED by the vicinity: the whole array of this
+ * oracle lattice, which the caller has created one cell larger on every non-periodic side (the reference's envelope;
+ * statBox = the bulk).  Cells of that shell collide with the field values found there -- zero, nothing ever writes
+ * them -- and stream like any other cell; on the rim of the enlarged box a population stays in the opposite slot
+ * (collide()+revert() :41-57, bounds-checked boundaryStream :80-104).  Then the boundary condition's level-0 processors
+ * (integrated after the sweep), then the moments of the post-stream populations into the fields. */
+static void SFX(ext_step)(SFX(Lat)* L) {
+    const int q = L->q, h = q / 2, nx = L->nx, ny = L->ny, nz = L->nz;
+    int x, y, z, i;
+    REAL* tmp;
+    for (x = 0; x < nx; ++x) for (y = 0; y < ny; ++y) for (z = 0; z < nz; ++z) {
+        size_t cell = CELL(L, x, y, z);
+        SFX(collide_external_cell)(L, SFX(dyn_of)(L, cell), L->f + cell * q, L->ext[4*cell], &L->ext[4*cell + 1]);
+    }
+    for (x = 0; x < nx; ++x) for (y = 0; y < ny; ++y) for (z = 0; z < nz; ++z) {
+        size_t cell = CELL(L, x, y, z);
+        L->g[cell * q] = L->f[cell * q];
+        for (i = 1; i < q; ++i) {
+            int sx = x - L->c[i][0], sy = y - L->c[i][1], sz = z - L->c[i][2], ok = 1;
+            if (sx < 0 || sx >= nx) { if (L->per[0]) sx = (sx + nx) % nx; else ok = 0; }
+            if (sy < 0 || sy >= ny) { if (L->per[1]) sy = (sy + ny) % ny; else ok = 0; }
+            if (sz < 0 || sz >= nz) { if (L->per[2]) sz = (sz + nz) % nz; else ok = 0; }
+            if (ok) L->g[cell * q + i] = L->f[CELL(L, sx, sy, sz) * q + i];
+            else    L->g[cell * q + i] = L->f[cell * q + (i <= h ? i + h : i - h)];
+        }
+    }
+    tmp = L->f; L->f = L->g; L->g = tmp;
+    SFX(execute_processors)(L);
+    SFX(box_rhoBar_j)(L, L->statBox);
+}
+
 /* -------------------------------------------------------------------- set-up ---- */
 
 static SFX(Lat)* SFX(create)(int q, int nx, int ny, int nz) {
@@ -815,7 +966,7 @@ static SFX(Lat)* SFX(create)(int q, int nx, int ny, int nz) {
 }
 
 static void SFX(destroy)(SFX(Lat)* L) {
-    free(L->f); free(L->g); free(L->dynIdx); free(L->bcIdx); free(L->bcs); free(L->procs); free(L);
+    free(L->f); free(L->g); free(L->ext); free(L->dynIdx); free(L->bcIdx); free(L->bcs); free(L->procs); free(L);
 }
 
 static int SFX(find_dyn)(SFX(Lat)* L, int type, double p1, double p2) {

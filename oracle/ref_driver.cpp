@@ -72,7 +72,11 @@ static Box3D readBox(std::istringstream& in) {
 struct FieldRhoU {
     FieldRhoU(std::vector<double> const& d, Box3D b) : data(d), box(b) {}
     void operator()(plint iX, plint iY, plint iZ, T& rho, Array<T,3>& u) const {
-        size_t idx = ((size_t)(iX - box.x0) * box.getNy() + (iY - box.y0)) * box.getNz() + (iZ - box.z0);
+        // the reference evaluates the functor in the periodic envelope as well (coordinates -1 and n): a tabulated
+        // field answers there with its periodic image
+        plint nx = box.getNx(), ny = box.getNy(), nz = box.getNz();
+        plint x = ((iX - box.x0) % nx + nx) % nx, y = ((iY - box.y0) % ny + ny) % ny, z = ((iZ - box.z0) % nz + nz) % nz;
+        size_t idx = ((size_t)x * ny + y) * nz + z;
         rho = (T)data[4*idx];
         u[0] = (T)data[4*idx+1]; u[1] = (T)data[4*idx+2]; u[2] = (T)data[4*idx+3];
     }
@@ -188,6 +192,10 @@ static int runScenario(std::vector<std::string> const& lines, size_t first,
     MultiBlockLattice3D<T,D>& lattice = *latPtr;
     std::vector<OnLatticeBoundaryCondition3D<T,D>*> bcs;
     plint iter = 0;
+    // the three blocks ExternalRhoJcollideAndStream3D works on (src/variables.hh:475-486 of the fork's application)
+    MultiScalarField3D<T>* rhoBarField = 0;
+    MultiTensorField3D<T,3>* jField = 0;
+    std::vector<MultiBlock3D*> rhoBarJarg;
 
     for (size_t iL = first; iL < lines.size(); ++iL) {
         std::istringstream in(lines[iL]);
@@ -198,6 +206,55 @@ static int runScenario(std::vector<std::string> const& lines, size_t first,
             lattice.periodicity().toggle(0, px != 0);
             lattice.periodicity().toggle(1, py != 0);
             lattice.periodicity().toggle(2, pz != 0);
+        } else if (cmd == "ext_integrate") {
+            // src/variables.hh:475-486: rhoBar / j fields generated from the lattice, the external-moment sweep at
+            // level 0 and the moment computation at level 3 (order of the calls matters: what is integrated later at
+            // level 0 -- the boundary condition's processors -- runs after the sweep)
+            rhoBarField = generateMultiScalarField<T>((MultiBlock3D&)lattice, 1).release();
+            rhoBarField->toggleInternalStatistics(false);
+            jField = generateMultiTensorField<T,3>((MultiBlock3D&)lattice, 1).release();
+            jField->toggleInternalStatistics(false);
+            for (int d = 0; d < 3; ++d) {
+                rhoBarField->periodicity().toggle(d, lattice.periodicity().get(d));
+                jField->periodicity().toggle(d, lattice.periodicity().get(d));
+            }
+            rhoBarJarg.clear();
+            rhoBarJarg.push_back(&lattice); rhoBarJarg.push_back(rhoBarField); rhoBarJarg.push_back(jField);
+            integrateProcessingFunctional(new ExternalRhoJcollideAndStream3D<T,D>(), lattice.getBoundingBox(), rhoBarJarg, 0);
+            integrateProcessingFunctional(new BoxRhoBarJfunctional3D<T,D>(), lattice.getBoundingBox(), rhoBarJarg, 3);
+        } else if (cmd == "ext_apply") {
+            // applyProcessingFunctional(new BoxRhoBarJfunctional3D, box, rhoBarJarg) src/variables.hh:650
+            Box3D box = readBox(in);
+            if (!rhoBarField) fail("ext_apply before ext_integrate");
+            applyProcessingFunctional(new BoxRhoBarJfunctional3D<T,D>(), box, rhoBarJarg);
+        } else if (cmd == "ext_exec") {
+            // viscosityTest/src/test.cpp:64-65: the time step of the fork's application
+            plint n; in >> n;
+            if (!rhoBarField) fail("ext_exec before ext_integrate");
+            for (plint i = 0; i < n; ++i) { lattice.executeInternalProcessors(); lattice.incrementTime(); }
+            iter += n;
+        } else if (cmd == "ext_add_j") {
+            // what a momentum-forcing processor does to the j field between two steps
+            Box3D box = readBox(in); double dj[3]; in >> dj[0] >> dj[1] >> dj[2];
+            if (!jField) fail("ext_add_j before ext_integrate");
+            for (plint x = box.x0; x <= box.x1; ++x) for (plint y = box.y0; y <= box.y1; ++y) for (plint z = box.z0; z <= box.z1; ++z) {
+                Array<T,3>& j = jField->get(x, y, z);
+                j[0] += (T)dj[0]; j[1] += (T)dj[1]; j[2] += (T)dj[2];
+            }
+            jField->duplicateOverlaps(modif::staticVariables);
+        } else if (cmd == "dump_rhobar_j") {
+            std::string file; in >> file;
+            if (!rhoBarField) fail("dump_rhobar_j before ext_integrate");
+            std::vector<T> d((size_t)nx * ny * nz * 4);
+            for (plint x = 0; x < nx; ++x) for (plint y = 0; y < ny; ++y) for (plint z = 0; z < nz; ++z) {
+                Array<T,3> const& j = jField->get(x, y, z);
+                size_t o = (((size_t)x * ny + y) * nz + z) * 4;
+                d[o] = rhoBarField->get(x, y, z); d[o+1] = j[0]; d[o+2] = j[1]; d[o+3] = j[2];
+            }
+            FILE* fp = std::fopen(file.c_str(), "wb");
+            if (!fp) fail("cannot write " + file);
+            std::fwrite(d.data(), sizeof(T), d.size(), fp);
+            std::fclose(fp);
         } else if (cmd == "dynamics") {
             Box3D box = readBox(in);
             std::string kind; double a = 0, b = 0; in >> kind >> a >> b;

@@ -155,6 +155,91 @@ def inlet_outlet_local(nx, ny, nz, steps):
     return sc
 
 
+# ---- the external-moment sweep: the time loop of the fork's own application -------------------
+# src/variables.hh:475-486 integrates ExternalRhoJcollideAndStream3D at level 0 and BoxRhoBarJfunctional3D at level 3 on
+# {lattice, rhoBar, j}; :650 fills the fields once; viscosityTest/src/test.cpp:64-65 steps with executeInternalProcessors() +
+# incrementTime().  ext_add_j stands for the processors that force the momentum field between two steps.
+
+
+def ext_finish(sc, steps, add_j):
+    nx, ny, nz = sc.nx, sc.ny, sc.nz
+    sc.ext_apply()
+    sc.dump_rhobar_j("rj_init")
+    first = steps // 2
+    sc.ext_exec(first)
+    if add_j:
+        sc.ext_add_j((1, max(1, nx // 2), 1, ny - 2, max(1, nz // 3), nz - 2), (1e-3, -5e-4, 2.5e-4))
+    sc.ext_exec(steps - first)
+    return sc.stats().dump("f_end").dump_rhobar_j("rj_end").dump_rho_u("rho_u_end")
+
+
+def ext_cavity(nx, ny, nz, steps, dyn="INCBGK", q=19, prec="f64", model="local", add_j=True, initialize=False):
+    u_max, re = 0.02, 100.0
+    omega = 1.0 / (3 * u_max * ny / re + 0.5)
+    sc = Scenario(q, prec, nx, ny, nz, dyn, omega, 0.14 if dyn == "SMAGO" else 0.0)
+    sc.ext_integrate()
+    sc.bc_box(model)
+    sc.set_velocity(sc.box, (0, 0, 0))
+    sc.set_velocity((1, nx - 2, 1, ny - 2, nz - 1, nz - 1), (u_max, 0, 0))
+    sc.init_eq(sc.box, 1.0, (0, 0, 0))
+    if initialize:
+        sc.ext_apply()
+        sc.initialize()        # MultiBlock3D::initialize = executeInternalProcessors: a whole step in this mode
+    return ext_finish(sc, steps, add_j)
+
+
+def ext_channel(nx, ny, nz, steps, dyn="TRT", omega=1.2, q=19, prec="f64", cs=0.0, perturb=0.01, add_j=True):
+    """BounceBack walls ON the rim of the lattice: what streams in from the reference's envelope layer (collided with
+    the zero moments found there) matters."""
+    sc = Scenario(q, prec, nx, ny, nz, dyn, omega, cs)
+    sc.periodic(1, 0, 1)
+    sc.ext_integrate()
+    sc.dynamics((0, nx - 1, 0, 0, 0, nz - 1), "BB", 1.0)
+    sc.dynamics((0, nx - 1, ny - 1, ny - 1, 0, nz - 1), "BB", 1.0)
+    sc.dynamics((2, 3, 2, 3, 1, 2), "NODYN", 1.0)
+    sc.init_eq_field(sc.box, poiseuille_profile(nx, ny, nz, 0.05, perturb=perturb))
+    return ext_finish(sc, steps, add_j)
+
+
+def ext_open(nx, ny, nz, steps, dyn="BGK", omega=1.5, q=19, prec="f64"):
+    """No boundary condition at all on a non-periodic lattice: bulk cells on the rim exchange populations with the
+    envelope layer every step."""
+    sc = Scenario(q, prec, nx, ny, nz, dyn, omega, 0.0)
+    sc.periodic(0, 1, 0)
+    sc.ext_integrate()
+    sc.dynamics((2, nx // 2, 1, ny - 2, 2, nz - 3), dyn, 1.7)
+    ru = poiseuille_profile(nx, ny, nz, 0.0, perturb=0.02)
+    ru[..., 1] += 0.02
+    sc.init_eq_field(sc.box, ru)
+    return ext_finish(sc, steps, True)
+
+
+def ext_obstacle(nx, ny, nz, steps, dyn="INCBGK", omega=1.6, model="zouhe"):
+    sc = Scenario(19, "f64", nx, ny, nz, dyn, omega, 0.0)
+    sc.ext_integrate()
+    sc.bc_vel(model, 0, -1, (0, 0, 1, ny - 2, 1, nz - 2))
+    sc.bc_pres(model, 0, +1, (nx - 1, nx - 1, 1, ny - 2, 1, nz - 2))
+    sc.dynamics((0, nx - 1, 0, 0, 0, nz - 1), "BB", 1.0)
+    sc.dynamics((0, nx - 1, ny - 1, ny - 1, 0, nz - 1), "BB", 1.0)
+    sc.dynamics((0, nx - 1, 0, ny - 1, 0, 0), "BB", 1.0)
+    sc.dynamics((0, nx - 1, 0, ny - 1, nz - 1, nz - 1), "BB", 1.0)
+    sc.dynamics_mask(sphere_mask(nx, ny, nz, nx // 3, ny / 2 - 0.5, nz / 2 - 0.5, min(ny, nz) / 5.0), 1, "BB", 1.0)
+    sc.set_velocity(sc.box, (0.03, 0, 0))
+    sc.set_density(sc.box, 1.0)
+    sc.init_eq(sc.box, 1.0, (0.03, 0, 0))
+    return ext_finish(sc, steps, False)
+
+
+def ext_periodic(nx, ny, nz, steps, dyn, omega, q=19, prec="f64", cs=0.0):
+    sc = Scenario(q, prec, nx, ny, nz, dyn, omega, cs)
+    sc.periodic(1, 1, 1)
+    sc.ext_integrate()
+    ru = poiseuille_profile(nx, ny, nz, 0.0, perturb=0.02)
+    ru[..., 1] += 0.03
+    sc.init_eq_field(sc.box, ru)
+    return ext_finish(sc, steps, True)
+
+
 # name -> (builder, how to store the reference outcome: "full" dumps, or "probe" = sha256 + sampled cells)
 CASES = {
     # configs[0]-style cavity, all dynamics on the path
@@ -196,6 +281,19 @@ CASES = {
     "cavity_incbgk_q27_f32":    (lambda: cavity(8, 8, 9, 30, dyn="INCBGK", q=27, prec="f32"), "full"),
     "obstacle_incbgk_zouhe":    (lambda: obstacle(20, 10, 9, 40, dyn="INCBGK", omega=1.6), "full"),
     "periodic_incbgk_q27":      (lambda: periodic_box(8, 7, 9, 30, "INCBGK", 1.7, q=27), "full"),
+    # the external-moment sweep (ExternalRhoJcollideAndStream3D + BoxRhoBarJfunctional3D): the fork's own time loop
+    "ext_cavity_incbgk":        (lambda: ext_cavity(10, 9, 8, 40), "full"),
+    "ext_cavity_bgk_init":      (lambda: ext_cavity(9, 8, 10, 30, dyn="BGK", initialize=True), "full"),
+    "ext_cavity_rlb_zouhe":     (lambda: ext_cavity(8, 9, 10, 30, dyn="RLB", model="zouhe"), "full"),
+    "ext_cavity_smago_q27_f32": (lambda: ext_cavity(8, 8, 9, 30, dyn="SMAGO", q=27, prec="f32"), "full"),
+    "ext_channel_trt":          (lambda: ext_channel(12, 9, 8, 40), "full"),
+    "ext_channel_smago_q27":    (lambda: ext_channel(10, 8, 8, 30, dyn="SMAGO", omega=1.9, q=27, cs=0.14), "full"),
+    "ext_channel_bgk_f32":      (lambda: ext_channel(10, 8, 9, 30, dyn="BGK", omega=1.4, prec="f32"), "full"),
+    "ext_open_bgk":             (lambda: ext_open(11, 8, 9, 30), "full"),
+    "ext_open_incbgk_q27":      (lambda: ext_open(9, 8, 8, 30, dyn="INCBGK", q=27), "full"),
+    "ext_obstacle_incbgk":      (lambda: ext_obstacle(20, 10, 9, 40), "full"),
+    "ext_periodic_trt_q27":     (lambda: ext_periodic(8, 7, 9, 30, "TRT", 1.5, q=27), "full"),
+    "ext_periodic_rlb_f32":     (lambda: ext_periodic(8, 7, 9, 30, "RLB", 1.5, prec="f32"), "full"),
     # edge cases
     "mixed_omega_11x8x9":       (lambda: mixed_omega(11, 8, 9, 40), "full"),
     "inlet_outlet_local":       (lambda: inlet_outlet_local(12, 9, 8, 40), "full"),

@@ -115,6 +115,41 @@ class Scenario:
     def dump_rho_u(self, name):
         return self._add("dump_rho_u", name)
 
+    # ---- the external-moment sweep of the fork's application (src/variables.hh:475-486, viscosityTest/src/test.cpp:64-65)
+
+    @property
+    def external(self):
+        return any(op[0] == "ext_integrate" for op in self.ops)
+
+    @property
+    def periodicity(self):
+        """Periodicity in force when the fields are integrated (the enveloped engines fix it at creation)."""
+        per = (0, 0, 0)
+        for op in self.ops:
+            if op[0] == "periodic":
+                per = op[1:]
+            if op[0] == "ext_integrate":
+                break
+        return per
+
+    def ext_integrate(self):
+        """rhoBar / j fields + ExternalRhoJcollideAndStream3D at level 0 + BoxRhoBarJfunctional3D at level 3; must precede
+        the boundary set-up (whose level-0 processors then run after the sweep) and follow the periodicity toggles."""
+        assert all(op[0] == "periodic" for op in self.ops), "ext_integrate comes right after the periodicity toggles"
+        return self._add("ext_integrate")
+
+    def ext_apply(self, box=None):
+        return self._add("ext_apply", tuple(box or self.box))
+
+    def ext_exec(self, n):
+        return self._add("ext_exec", int(n))
+
+    def ext_add_j(self, box, dj):
+        return self._add("ext_add_j", tuple(box), tuple(float(v) for v in dj))
+
+    def dump_rhobar_j(self, name):
+        return self._add("dump_rhobar_j", name)
+
 
 # ----------------------------------------------------------------------------- reference
 
@@ -166,6 +201,17 @@ def run_reference(sc: Scenario, timed_steps=None):
                 lines.append("upload %s" % fn)
             elif k == "initialize":
                 lines.append("initialize")
+            elif k == "ext_integrate":
+                lines.append("ext_integrate")
+            elif k == "ext_apply":
+                lines.append("ext_apply %s" % fmt(op[1]))
+            elif k == "ext_exec":
+                lines.append("ext_exec %d" % op[1])
+            elif k == "ext_add_j":
+                lines.append("ext_add_j %s %s" % (fmt(op[1]), fmt(op[2])))
+            elif k == "dump_rhobar_j":
+                dumps.append((k, op[1]))
+                lines.append("dump_rhobar_j %s.bin" % op[1])
             elif k == "run":
                 lines.append("run %d" % op[1])
             elif k == "stats":
@@ -195,7 +241,7 @@ def run_reference(sc: Scenario, timed_steps=None):
         res["stats"] = np.array(res["stats"], dtype=np.float64).reshape(-1, 6)
         for kind, name in dumps:
             a = np.fromfile(os.path.join(tmp, name + ".bin"), dtype=sc.dtype)
-            res[name] = a.reshape(sc.nx, sc.ny, sc.nz, sc.q if kind == "dump" else 4)
+            res[name] = a.reshape(sc.nx, sc.ny, sc.nz, sc.q if kind == "dump" else 4)   # dump_rho_u, dump_rhobar_j: 4
         for fn, key in files:
             res[key] = np.frombuffer(open(os.path.join(tmp, fn), "rb").read(), dtype=np.uint8)
         return res
@@ -313,6 +359,26 @@ class OracleEngine:
     def collide_and_stream(self, n=1):
         self._ck(self.lib.plbo_collide_and_stream(self.h, int(n)))
 
+    def enable_external_rhoj(self):
+        self._ck(self.lib.plbo_enable_external_rhoj(self.h))
+
+    def execute_internal_processors(self, n=1):
+        self._ck(self.lib.plbo_execute_internal_processors(self.h, int(n)))
+
+    def apply_rhobar_j(self, box=None):
+        self._ck(self.lib.plbo_apply_rhobar_j(self.h, _box(box or full_box(self.nx, self.ny, self.nz))))
+
+    def upload_rhobar_j(self, fld, box=None):
+        box = box or full_box(self.nx, self.ny, self.nz)
+        fld = np.ascontiguousarray(fld, dtype=self.dtype)
+        self._ck(self.lib.plbo_upload_rhobar_j(self.h, _box(box), fld.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(fld.nbytes)))
+
+    def download_rhobar_j(self, box=None):
+        box = box or full_box(self.nx, self.ny, self.nz)
+        out = np.empty((box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1, 4), dtype=self.dtype)
+        self._ck(self.lib.plbo_download_rhobar_j(self.h, _box(box), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(out.nbytes)))
+        return out
+
     def stored_statistics(self):
         out = (ctypes.c_double * 3)()
         n = ctypes.c_uint64()
@@ -387,6 +453,19 @@ def replay(sc: Scenario, engine):
             engine.upload(op[1])
         elif k == "initialize":
             engine.initialize()
+        elif k == "ext_integrate":
+            engine.enable_external_rhoj()
+        elif k == "ext_apply":
+            engine.apply_rhobar_j(op[1])
+        elif k == "ext_exec":
+            engine.execute_internal_processors(op[1])
+            it += op[1]
+        elif k == "ext_add_j":
+            fld = engine.download_rhobar_j(op[1])
+            fld[..., 1:] += np.asarray(op[2], dtype=fld.dtype)
+            engine.upload_rhobar_j(fld, op[1])
+        elif k == "dump_rhobar_j":
+            res[op[1]] = engine.download_rhobar_j()
         elif k == "run":
             engine.collide_and_stream(op[1])
             it += op[1]
@@ -404,8 +483,116 @@ def replay(sc: Scenario, engine):
     return res
 
 
+class EnvelopedOracle:
+    """The oracle lattice of a scenario that uses the external-moment sweep: one cell larger on every non-periodic
+    side (the reference's envelope, which ExternalRhoJcollideAndStream3D collides and streams,
+    basicDynamics/dynamicsProcessor3D.hh:118-119), user coordinates shifted accordingly.  The CUDA engine does the same
+    shift behind plb_b200_create_enveloped."""
+
+    def __init__(self, q, prec, nx, ny, nz, dyn, p1, p2, periodic):
+        self.per = tuple(int(bool(p)) for p in periodic)
+        self.off = tuple(0 if p else 1 for p in self.per)
+        self.nx, self.ny, self.nz, self.q = nx, ny, nz, q
+        self.inner = OracleEngine(q, prec, nx + 2 * self.off[0], ny + 2 * self.off[1], nz + 2 * self.off[2], dyn, p1, p2)
+        self.inner.set_periodicity(*self.per)
+        self.inner.set_statistics_box(self._b(full_box(nx, ny, nz)))
+        self.dtype = self.inner.dtype
+
+    def close(self):
+        self.inner.close()
+
+    def _b(self, box):
+        o = self.off
+        box = box or full_box(self.nx, self.ny, self.nz)
+        return (box[0] + o[0], box[1] + o[0], box[2] + o[1], box[3] + o[1], box[4] + o[2], box[5] + o[2])
+
+    def set_periodicity(self, px, py, pz):
+        if (int(bool(px)), int(bool(py)), int(bool(pz))) != self.per:
+            raise RuntimeError("an enveloped lattice keeps the periodicity it was created with")
+
+    def define_dynamics(self, box, *a):
+        self.inner.define_dynamics(self._b(box), *a)
+
+    def define_dynamics_mask(self, mask, flag, *a):
+        o = self.off
+        big = np.full((self.inner.nx, self.inner.ny, self.inner.nz), flag + 1, dtype=np.int32)
+        big[o[0]:o[0] + self.nx, o[1]:o[1] + self.ny, o[2]:o[2] + self.nz] = mask
+        self.inner.define_dynamics_mask(big, flag, *a)
+
+    def set_velocity_condition_on_block_boundaries(self, model, block, app):
+        self.inner.set_velocity_condition_on_block_boundaries(model, self._b(block), self._b(app))
+
+    def add_velocity_boundary(self, model, d, o, box):
+        self.inner.add_velocity_boundary(model, d, o, self._b(box))
+
+    def add_pressure_boundary(self, model, d, o, box):
+        self.inner.add_pressure_boundary(model, d, o, self._b(box))
+
+    def add_external_velocity_edge(self, model, plane, n1, n2, box):
+        self.inner.add_external_velocity_edge(model, plane, n1, n2, self._b(box))
+
+    def add_external_velocity_corner(self, model, xn, yn, zn, x, y, z):
+        self.inner.add_external_velocity_corner(model, xn, yn, zn, x + self.off[0], y + self.off[1], z + self.off[2])
+
+    def set_boundary_velocity(self, box, u):
+        self.inner.set_boundary_velocity(self._b(box), u)
+
+    def set_boundary_density(self, box, rho):
+        self.inner.set_boundary_density(self._b(box), rho)
+
+    def initialize_at_equilibrium(self, box, rho, u):
+        self.inner.initialize_at_equilibrium(self._b(box), rho, u)
+
+    def initialize_at_equilibrium_field(self, box, rho_u):
+        self.inner.initialize_at_equilibrium_field(self._b(box), rho_u)
+
+    def upload(self, pops, box=None):
+        self.inner.upload(pops, self._b(box))
+
+    def download(self, box=None):
+        return self.inner.download(self._b(box))
+
+    def initialize(self):
+        # MultiBlock3D::initialize = executeInternalProcessors (multiBlock/multiBlock3D.cpp:330-332): with the sweep
+        # integrated as a processor this is a whole step
+        self.inner.execute_internal_processors(1)
+
+    def collide_and_stream(self, n=1):
+        raise RuntimeError("a lattice with the external-moment sweep is stepped by execute_internal_processors")
+
+    def enable_external_rhoj(self):
+        self.inner.enable_external_rhoj()
+
+    def execute_internal_processors(self, n=1):
+        self.inner.execute_internal_processors(n)
+
+    def apply_rhobar_j(self, box=None):
+        self.inner.apply_rhobar_j(self._b(box))
+
+    def upload_rhobar_j(self, fld, box=None):
+        self.inner.upload_rhobar_j(fld, self._b(box))
+
+    def download_rhobar_j(self, box=None):
+        return self.inner.download_rhobar_j(self._b(box))
+
+    def stored_statistics(self):
+        return self.inner.stored_statistics()
+
+    def compute_average_energy(self, box=None):
+        return self.inner.compute_average_energy(self._b(box))
+
+    def compute_average_density(self, box=None):
+        return self.inner.compute_average_density(self._b(box))
+
+    def compute_density_velocity(self, box=None):
+        return self.inner.compute_density_velocity(self._b(box))
+
+
 def run_oracle(sc: Scenario):
-    eng = OracleEngine(sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2)
+    if sc.external:
+        eng = EnvelopedOracle(sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2, sc.periodicity)
+    else:
+        eng = OracleEngine(sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2)
     try:
         return replay(sc, eng)
     finally:
