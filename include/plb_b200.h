@@ -59,6 +59,20 @@ plb_b200_lattice* plb_b200_create(int q, int precision_bytes, int nx, int ny, in
 plb_b200_lattice* plb_b200_create_distributed(int q, int precision_bytes, int nx, int ny, int nz,
                                               int dynamics, double p1, double p2,
                                               int rank, int n_ranks, int slabs_per_rank);
+/* A lattice that is stepped by the external-moment sweep of the fork's own application:
+ *   generateMultiScalarField / generateMultiTensorField<3>(lattice, envelopeWidth)                 src/variables.hh:475-479
+ *   integrateProcessingFunctional(new ExternalRhoJcollideAndStream3D, bbox, {lattice,rhoBar,j}, 0)  src/variables.hh:485
+ *   integrateProcessingFunctional(new BoxRhoBarJfunctional3D,        bbox, {lattice,rhoBar,j}, 3)  src/variables.hh:486
+ * That sweep works on the bulk ENLARGED by one cell (basicDynamics/dynamicsProcessor3D.hh:118-119): it collides the
+ * reference's envelope layer -- with the zero moments found there -- and streams it into the rim of the lattice.  The engine
+ * therefore allocates one extra layer on every non-periodic side (x slabs as usual) and shifts every box of this ABI; the
+ * caller keeps the coordinates of its own nx x ny x nz lattice.  Periodicity is fixed here (the envelope of a periodic
+ * direction is the periodic image, handled by index wrap).  The boundary condition is set up afterwards: its level-0
+ * processors then run after the sweep, the order this engine implements.  Step with plb_b200_execute_internal_processors. */
+plb_b200_lattice* plb_b200_create_enveloped(int q, int precision_bytes, int nx, int ny, int nz,
+                                            int dynamics, double p1, double p2,
+                                            int periodic_x, int periodic_y, int periodic_z,
+                                            int rank, int n_ranks, int slabs_per_rank);
 void plb_b200_destroy(plb_b200_lattice* L);
 const char* plb_b200_last_error(void);
 int plb_b200_abi_version(void);
@@ -132,6 +146,19 @@ size_t plb_b200_local_bytes(plb_b200_lattice* L, const int box[6]);
 /* n x MultiBlockLattice3D::collideAndStream() multiBlock/multiBlockLattice3D.hh:318-360: fused
  * collide+stream sweep, halo exchange, level-0 boundary processors, statistics.  Asynchronous. */
 int plb_b200_collide_and_stream(plb_b200_lattice* L, int n_steps);
+/* n x { lattice.executeInternalProcessors(); lattice.incrementTime(); } viscosityTest/src/test.cpp:64-65 -- the time step of
+ * a lattice made by plb_b200_create_enveloped: sweep with rhoBar and j read from the fields (Dynamics::collideExternal,
+ * basicDynamics/dynamicsProcessor3D.hh:41-195), halo exchange, level-0 boundary processors, then Dynamics::computeRhoBarJ
+ * of every cell of the lattice into the fields (dataProcessors/dataAnalysisFunctional3D.hh:528-548).  The internal
+ * statistics are not evaluated, as in the reference's loop.  plb_b200_initialize on such a lattice is one of these steps
+ * (MultiBlock3D::initialize = executeInternalProcessors, multiBlock/multiBlock3D.cpp:330-332). */
+int plb_b200_execute_internal_processors(plb_b200_lattice* L, int n_steps);
+/* applyProcessingFunctional(new BoxRhoBarJfunctional3D, box, rhoBarJarg) src/variables.hh:650 */
+int plb_b200_apply_rhobar_j(plb_b200_lattice* L, const int box[6]);
+/* the rhoBar (ScalarField3D) and j (TensorField3D<3>) fields, e.g. for the processors that force the momentum between two
+ * steps: host memory, T [cells of box][rhoBar, jx, jy, jz] (the part of the box this rank owns, as plb_b200_upload) */
+int plb_b200_upload_rhobar_j(plb_b200_lattice* L, const int box[6], const void* data, size_t bytes);
+int plb_b200_download_rhobar_j(plb_b200_lattice* L, const int box[6], void* data, size_t bytes);
 /* block until everything queued for this lattice has run */
 int plb_b200_synchronize(plb_b200_lattice* L);
 

@@ -40,6 +40,8 @@ SYMBOLS = [
     "plb_b200_boundary_stages", "plb_b200_profile_sweeps", "plb_b200_profile_read", "plb_b200_coproc_add_domain", "plb_b200_coproc_send",
     "plb_b200_coproc_receive", "plb_b200_coproc_collide_and_stream", "plb_b200_coproc_remove_domain",
     "plb_b200_save_binary_block", "plb_b200_load_binary_block",
+    "plb_b200_create_enveloped", "plb_b200_execute_internal_processors", "plb_b200_apply_rhobar_j",
+    "plb_b200_upload_rhobar_j", "plb_b200_download_rhobar_j",
     "plb_b200_voxelize", "plb_b200_stl_read", "plb_b200_stl_free", "plb_b200_mesh_to_lattice",
 ]
 
@@ -68,6 +70,12 @@ def lib():
         L.plb_b200_create.argtypes = [ci] * 6 + [cd] * 2
         L.plb_b200_create_distributed.restype = vp
         L.plb_b200_create_distributed.argtypes = [ci] * 6 + [cd] * 2 + [ci] * 3
+        L.plb_b200_create_enveloped.restype = vp
+        L.plb_b200_create_enveloped.argtypes = [ci] * 6 + [cd] * 2 + [ci] * 6
+        L.plb_b200_execute_internal_processors.argtypes = [vp, ci]
+        L.plb_b200_apply_rhobar_j.argtypes = [vp, vp]
+        L.plb_b200_upload_rhobar_j.argtypes = [vp, vp, vp, ctypes.c_size_t]
+        L.plb_b200_download_rhobar_j.argtypes = [vp, vp, vp, ctypes.c_size_t]
         L.plb_b200_destroy.restype = None
         L.plb_b200_destroy.argtypes = [vp]
         L.plb_b200_last_error.restype = ctypes.c_char_p
@@ -189,13 +197,19 @@ def comm_unique_id():
 class Lattice:
     """One MultiBlockLattice3D<T,Descriptor> on the GPU(s), through the C-ABI."""
 
-    def __init__(self, q, prec, nx, ny, nz, dyn, p1, p2=0.0, rank=0, n_ranks=1, slabs_per_rank=1):
+    def __init__(self, q, prec, nx, ny, nz, dyn, p1, p2=0.0, rank=0, n_ranks=1, slabs_per_rank=1, enveloped_periodic=None):
+        """enveloped_periodic=(px,py,pz): a lattice stepped by the external-moment sweep (plb_b200_create_enveloped)"""
         self.lib = lib()
         self.q, self.prec, self.nx, self.ny, self.nz = q, prec, nx, ny, nz
         self.rank, self.n_ranks, self.slabs_per_rank = rank, n_ranks, slabs_per_rank
         self.dtype = np.float64 if prec == "f64" else np.float32
-        self.h = ctypes.c_void_p(self.lib.plb_b200_create_distributed(
-            q, 8 if prec == "f64" else 4, nx, ny, nz, DYN[dyn], p1, p2, rank, n_ranks, slabs_per_rank))
+        if enveloped_periodic is not None:
+            px, py, pz = [int(bool(p)) for p in enveloped_periodic]
+            self.h = ctypes.c_void_p(self.lib.plb_b200_create_enveloped(
+                q, 8 if prec == "f64" else 4, nx, ny, nz, DYN[dyn], p1, p2, px, py, pz, rank, n_ranks, slabs_per_rank))
+        else:
+            self.h = ctypes.c_void_p(self.lib.plb_b200_create_distributed(
+                q, 8 if prec == "f64" else 4, nx, ny, nz, DYN[dyn], p1, p2, rank, n_ranks, slabs_per_rank))
         if not self.h:
             raise PlbError(self.lib.plb_b200_last_error().decode())
 
@@ -293,6 +307,29 @@ class Lattice:
 
     def collide_and_stream(self, n=1):
         self._ck(self.lib.plb_b200_collide_and_stream(self.h, int(n)))
+
+    def enable_external_rhoj(self):
+        """the fields and the two functionals are part of plb_b200_create_enveloped; nothing left to do"""
+
+    def execute_internal_processors(self, n=1):
+        self._ck(self.lib.plb_b200_execute_internal_processors(self.h, int(n)))
+
+    def apply_rhobar_j(self, box=None):
+        self._ck(self.lib.plb_b200_apply_rhobar_j(self.h, _box(box or self.box)))
+
+    def upload_rhobar_j(self, fld, box=None):
+        fld = np.ascontiguousarray(fld, dtype=self.dtype)
+        self._ck(self.lib.plb_b200_upload_rhobar_j(self.h, _box(box or self.box), fld.ctypes.data_as(ctypes.c_void_p), fld.nbytes))
+
+    def download_rhobar_j(self, box=None):
+        box = box or self.box
+        if self.n_ranks == 1:
+            shape = (box[1] - box[0] + 1, box[3] - box[2] + 1, box[5] - box[4] + 1, 4)
+        else:
+            shape = (self.local_cells(box), 4)
+        out = np.empty(shape, dtype=self.dtype)
+        self._ck(self.lib.plb_b200_download_rhobar_j(self.h, _box(box), out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
+        return out
 
     def synchronize(self):
         self._ck(self.lib.plb_b200_synchronize(self.h))

@@ -15,16 +15,32 @@
 
 using namespace plb200;
 
-struct plb_b200_lattice { LatticeBase* impl; CreateDesc desc; };
+/// desc holds the USER's lattice; off = width of the envelope layer in front of it inside the engine lattice
+/// (plb_b200_create_enveloped; 0 otherwise).  Every box that crosses the ABI is shifted by it.
+struct plb_b200_lattice { LatticeBase* impl; CreateDesc desc; int off[3]; int per[3]; bool enveloped; };
+
+namespace {
+struct SBox {
+    int v[6];
+    SBox(const plb_b200_lattice* L, const int b[6]) {
+        if (!b) throw PlbError("null box");
+        for (int k = 0; k < 6; ++k) v[k] = b[k] + L->off[k / 2];
+        // a box must lie inside the user's lattice: the envelope layer is not addressable
+        if (L->enveloped && !(b[0] >= 0 && b[1] < L->desc.nx && b[2] >= 0 && b[3] < L->desc.ny && b[4] >= 0 && b[5] < L->desc.nz))
+            throw PlbError("box outside the lattice");
+    }
+    operator const int*() const { return v; }
+};
+}  // namespace
 
 static thread_local std::string g_err;
 
 static int fail(const std::string& m) { g_err = m; return 0; }
 namespace plb200 { int set_last_error(const std::string& m) { return fail(m); } }
 
-#define PLB_TRY(L, body)                                           \
+#define PLB_TRY(L, ...)                                            \
     if (!(L) || !(L)->impl) return fail("null lattice handle");    \
-    try { body; return 1; }                                        \
+    try { __VA_ARGS__; return 1; }                                 \
     catch (const std::exception& e) { return fail(e.what()); }     \
     catch (...) { return fail("unknown error"); }
 
@@ -46,6 +62,9 @@ plb_b200_lattice* plb_b200_create_distributed(int q, int prec, int nx, int ny, i
         plb_b200_lattice* L = new plb_b200_lattice;
         L->impl = impl;
         L->desc = d;
+        L->off[0] = L->off[1] = L->off[2] = 0;
+        L->per[0] = L->per[1] = L->per[2] = 0;
+        L->enveloped = false;
         return L;
     } catch (const std::exception& e) { fail(e.what()); return nullptr; }
     catch (...) { fail("unknown error"); return nullptr; }
@@ -53,6 +72,25 @@ plb_b200_lattice* plb_b200_create_distributed(int q, int prec, int nx, int ny, i
 
 plb_b200_lattice* plb_b200_create(int q, int prec, int nx, int ny, int nz, int dynamics, double p1, double p2) {
     return plb_b200_create_distributed(q, prec, nx, ny, nz, dynamics, p1, p2, 0, 1, 1);
+}
+
+plb_b200_lattice* plb_b200_create_enveloped(int q, int prec, int nx, int ny, int nz, int dynamics, double p1, double p2,
+                                            int px, int py, int pz, int rank, int nRanks, int slabsPerRank) {
+    const int per[3] = {px != 0, py != 0, pz != 0};
+    const int off[3] = {per[0] ? 0 : 1, per[1] ? 0 : 1, per[2] ? 0 : 1};
+    if (nx < 1 || ny < 1 || nz < 1) { fail("bad lattice descriptor"); return nullptr; }
+    plb_b200_lattice* L = plb_b200_create_distributed(q, prec, nx + 2 * off[0], ny + 2 * off[1], nz + 2 * off[2],
+                                                      dynamics, p1, p2, rank, nRanks, slabsPerRank);
+    if (!L) return nullptr;
+    try {
+        L->desc.nx = nx; L->desc.ny = ny; L->desc.nz = nz;
+        for (int k = 0; k < 3; ++k) { L->off[k] = off[k]; L->per[k] = per[k]; }
+        L->enveloped = true;
+        L->impl->set_periodicity(per[0], per[1], per[2]);
+        const int bulk[6] = {0, nx - 1, 0, ny - 1, 0, nz - 1};
+        L->impl->enable_external_rhoj(SBox(L, bulk));
+        return L;
+    } catch (const std::exception& e) { fail(e.what()); plb_b200_destroy(L); return nullptr; }
 }
 
 void plb_b200_destroy(plb_b200_lattice* L) {
@@ -180,7 +218,7 @@ int plb_b200_save_binary_block(plb_b200_lattice* L, const char* path) {
         std::vector<unsigned char> buf;
         for_chunks(L, [&](const int box[6], size_t bytes) {
             buf.resize(bytes);
-            L->impl->download(box, buf.data(), bytes);
+            L->impl->download(SBox(L, box), buf.data(), bytes);
             enc.write(buf.data(), bytes);
         });
         enc.finish();
@@ -207,7 +245,7 @@ int plb_b200_load_binary_block(plb_b200_lattice* L, const char* path) {
         for_chunks(L, [&](const int box[6], size_t bytes) {
             buf.resize(bytes);
             dec.read(buf.data(), bytes);
-            L->impl->upload(box, buf.data(), bytes);
+            L->impl->upload(SBox(L, box), buf.data(), bytes);
         });
         std::fclose(fp);
         return 1;
@@ -215,68 +253,95 @@ int plb_b200_load_binary_block(plb_b200_lattice* L, const char* path) {
 }
 
 int plb_b200_set_stream(plb_b200_lattice* L, void* s) { PLB_TRY(L, L->impl->set_stream((cudaStream_t)s)) }
-int plb_b200_set_periodicity(plb_b200_lattice* L, int px, int py, int pz) { PLB_TRY(L, L->impl->set_periodicity(px, py, pz)) }
+int plb_b200_set_periodicity(plb_b200_lattice* L, int px, int py, int pz) {
+    PLB_TRY(L, {
+        if (L->enveloped && ((px != 0) != L->per[0] || (py != 0) != L->per[1] || (pz != 0) != L->per[2]))
+            throw PlbError("an enveloped lattice keeps the periodicity it was created with");
+        L->impl->set_periodicity(px, py, pz);
+    })
+}
 int plb_b200_toggle_internal_statistics(plb_b200_lattice* L, int on) { PLB_TRY(L, L->impl->toggle_statistics(on != 0)) }
 int plb_b200_define_dynamics_box(plb_b200_lattice* L, const int box[6], int dyn, double p1, double p2) {
-    PLB_TRY(L, L->impl->define_dynamics_box(box, dyn, p1, p2))
+    PLB_TRY(L, L->impl->define_dynamics_box(SBox(L, box), dyn, p1, p2))
 }
 int plb_b200_define_dynamics_mask(plb_b200_lattice* L, const int32_t* mask, int flag, int dyn, double p1, double p2) {
-    PLB_TRY(L, L->impl->define_dynamics_mask(mask, flag, dyn, p1, p2))
+    PLB_TRY(L, {
+        if (!L->enveloped) { L->impl->define_dynamics_mask(mask, flag, dyn, p1, p2); }
+        else {
+            // the mask of the user's lattice inside one of the engine lattice; the envelope layer never carries the flag
+            if (!mask) throw PlbError("null mask");
+            const CreateDesc& d = L->desc;
+            const int NY = d.ny + 2 * L->off[1], NZ = d.nz + 2 * L->off[2], NX = d.nx + 2 * L->off[0];
+            std::vector<int32_t> big((size_t)NX * NY * NZ, flag == 0 ? 1 : 0);
+            for (int x = 0; x < d.nx; ++x) for (int y = 0; y < d.ny; ++y)
+                std::memcpy(&big[((size_t)(x + L->off[0]) * NY + (y + L->off[1])) * NZ + L->off[2]],
+                            &mask[((size_t)x * d.ny + y) * d.nz], (size_t)d.nz * sizeof(int32_t));
+            L->impl->define_dynamics_mask(big.data(), flag, dyn, p1, p2);
+        }
+    })
 }
 int plb_b200_add_velocity_boundary(plb_b200_lattice* L, int model, int dir, int ori, const int box[6]) {
-    PLB_TRY(L, L->impl->add_velocity_boundary(model, dir, ori, box))
+    PLB_TRY(L, L->impl->add_velocity_boundary(model, dir, ori, SBox(L, box)))
 }
 int plb_b200_add_pressure_boundary(plb_b200_lattice* L, int model, int dir, int ori, const int box[6]) {
-    PLB_TRY(L, L->impl->add_pressure_boundary(model, dir, ori, box))
+    PLB_TRY(L, L->impl->add_pressure_boundary(model, dir, ori, SBox(L, box)))
 }
 int plb_b200_add_external_velocity_edge(plb_b200_lattice* L, int model, int plane, int n1, int n2, const int box[6]) {
-    PLB_TRY(L, L->impl->add_external_velocity_edge(model, plane, n1, n2, box))
+    PLB_TRY(L, L->impl->add_external_velocity_edge(model, plane, n1, n2, SBox(L, box)))
 }
 int plb_b200_add_external_velocity_corner(plb_b200_lattice* L, int model, int xn, int yn, int zn, int x, int y, int z) {
-    PLB_TRY(L, L->impl->add_external_velocity_corner(model, xn, yn, zn, x, y, z))
+    PLB_TRY(L, L->impl->add_external_velocity_corner(model, xn, yn, zn, x + L->off[0], y + L->off[1], z + L->off[2]))
 }
 int plb_b200_set_velocity_condition_on_block_boundaries(plb_b200_lattice* L, int model, const int block[6], const int app[6]) {
-    PLB_TRY(L, L->impl->set_velocity_condition_on_block_boundaries(model, block, app))
+    PLB_TRY(L, L->impl->set_velocity_condition_on_block_boundaries(model, SBox(L, block), SBox(L, app)))
 }
 int plb_b200_set_boundary_velocity(plb_b200_lattice* L, const int box[6], const double u[3]) {
-    PLB_TRY(L, L->impl->set_boundary_velocity(box, u))
+    PLB_TRY(L, L->impl->set_boundary_velocity(SBox(L, box), u))
 }
 int plb_b200_set_boundary_density(plb_b200_lattice* L, const int box[6], double rho) {
-    PLB_TRY(L, L->impl->set_boundary_density(box, rho))
+    PLB_TRY(L, L->impl->set_boundary_density(SBox(L, box), rho))
 }
 int plb_b200_initialize_at_equilibrium(plb_b200_lattice* L, const int box[6], double rho, const double u[3]) {
-    PLB_TRY(L, L->impl->initialize_at_equilibrium(box, rho, u))
+    PLB_TRY(L, L->impl->initialize_at_equilibrium(SBox(L, box), rho, u))
 }
 int plb_b200_initialize_at_equilibrium_field(plb_b200_lattice* L, const int box[6], const double* ru) {
-    PLB_TRY(L, L->impl->initialize_at_equilibrium_field(box, ru))
+    PLB_TRY(L, L->impl->initialize_at_equilibrium_field(SBox(L, box), ru))
 }
 int plb_b200_initialize(plb_b200_lattice* L) { PLB_TRY(L, L->impl->initialize()) }
 
 int plb_b200_upload(plb_b200_lattice* L, const int box[6], const void* data, size_t bytes) {
-    PLB_TRY(L, L->impl->upload(box, data, bytes))
+    PLB_TRY(L, L->impl->upload(SBox(L, box), data, bytes))
 }
 int plb_b200_download(plb_b200_lattice* L, const int box[6], void* data, size_t bytes) {
-    PLB_TRY(L, L->impl->download(box, data, bytes))
+    PLB_TRY(L, L->impl->download(SBox(L, box), data, bytes))
 }
 size_t plb_b200_local_bytes(plb_b200_lattice* L, const int box[6]) {
     if (!L || !L->impl) { fail("null lattice handle"); return 0; }
-    try { return L->impl->local_bytes(box); } catch (const std::exception& e) { fail(e.what()); return 0; }
+    try { return L->impl->local_bytes(SBox(L, box)); } catch (const std::exception& e) { fail(e.what()); return 0; }
 }
 
 int plb_b200_collide_and_stream(plb_b200_lattice* L, int n) { PLB_TRY(L, L->impl->collide_and_stream(n)) }
+int plb_b200_execute_internal_processors(plb_b200_lattice* L, int n) { PLB_TRY(L, L->impl->execute_internal_processors(n)) }
+int plb_b200_apply_rhobar_j(plb_b200_lattice* L, const int box[6]) { PLB_TRY(L, L->impl->apply_rhobar_j(SBox(L, box))) }
+int plb_b200_upload_rhobar_j(plb_b200_lattice* L, const int box[6], const void* data, size_t bytes) {
+    PLB_TRY(L, L->impl->transfer_rhobar_j(SBox(L, box), const_cast<void*>(data), bytes, true))
+}
+int plb_b200_download_rhobar_j(plb_b200_lattice* L, const int box[6], void* data, size_t bytes) {
+    PLB_TRY(L, L->impl->transfer_rhobar_j(SBox(L, box), data, bytes, false))
+}
 int plb_b200_synchronize(plb_b200_lattice* L) { PLB_TRY(L, L->impl->synchronize()) }
 
 int plb_b200_get_stored_statistics(plb_b200_lattice* L, double out3[3], uint64_t* n) {
     PLB_TRY(L, L->impl->stored_statistics(out3, n))
 }
 int plb_b200_compute_average_energy(plb_b200_lattice* L, const int box[6], double* out) {
-    PLB_TRY(L, *out = L->impl->average_energy(box))
+    PLB_TRY(L, *out = L->impl->average_energy(SBox(L, box)))
 }
 int plb_b200_compute_average_density(plb_b200_lattice* L, const int box[6], double* out) {
-    PLB_TRY(L, *out = L->impl->average_density(box))
+    PLB_TRY(L, *out = L->impl->average_density(SBox(L, box)))
 }
 int plb_b200_compute_density_velocity(plb_b200_lattice* L, const int box[6], void* out, size_t bytes) {
-    PLB_TRY(L, L->impl->density_velocity(box, out, bytes))
+    PLB_TRY(L, L->impl->density_velocity(SBox(L, box), out, bytes))
 }
 
 uint64_t plb_b200_launch_count(plb_b200_lattice* L) { return (L && L->impl) ? L->impl->launch_count() : 0; }

@@ -51,6 +51,10 @@ public:
     virtual void upload(const int box[6], const void* data, size_t bytes) = 0;
     virtual void download(const int box[6], void* data, size_t bytes) = 0;
     virtual void collide_and_stream(int n) = 0;
+    virtual void enable_external_rhoj(const int bulk[6]) = 0;
+    virtual void execute_internal_processors(int n) = 0;
+    virtual void apply_rhobar_j(const int box[6]) = 0;
+    virtual void transfer_rhobar_j(const int box[6], void* data, size_t bytes, bool up) = 0;
     virtual void synchronize() = 0;
     virtual void stored_statistics(double out3[3], uint64_t* n) = 0;
     virtual double average_energy(const int box[6]) = 0;

@@ -43,6 +43,7 @@ class LatticeImpl : public LatticeBase {
         Bc<T>* dBcs = nullptr; size_t dBcsCap = 0;
         Item* dItems = nullptr; size_t dItemsCap = 0;
         double* dPartials = nullptr; int partialsCap = 0;
+        T* dExt = nullptr;                 ///< external-moment sweep: rhoBar [cellsStore] | j_x | j_y | j_z, zero where nothing writes
         double* dStats = nullptr;          ///< [3 launches][4]: a step sweeps a slab in up to three launches (5.)
         int statSlots = 0;                 ///< launches of the last step
         unsigned int* dTicket = nullptr;
@@ -76,6 +77,8 @@ class LatticeImpl : public LatticeBase {
     bool fused_ = false;                     ///< stage-0 plane items are completed by the next sweep, not by plane_stage_kernel
     bool pending_ = false;                   ///< ... and that completion is currently outstanding in storage
     bool statsOn_ = true;
+    bool ext_ = false;                       ///< the lattice is stepped by ExternalRhoJcollideAndStream3D + BoxRhoBarJfunctional3D
+    int bulk_[6] = {0, 0, 0, 0, 0, 0};       ///< ... whose level-3 domain is this box (the user's lattice; the rest is envelope)
     bool anySetup_ = false;
     bool stepped_ = false;
     cudaStream_t stream_ = 0;
@@ -140,7 +143,7 @@ public:
     ~LatticeImpl() override {
         cudaStreamSynchronize(stream_);
         for (Slab& sl : slabs_) {
-            cudaFree(sl.F); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems); cudaFree(sl.dSparse);
+            cudaFree(sl.F); cudaFree(sl.dExt); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems); cudaFree(sl.dSparse);
             cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket);
         }
         cudaFree(dDyns_); cudaFree(dStage_); cudaFree(dReduce_);
@@ -366,8 +369,85 @@ public:
 
     /// lattice.initialize(): MultiBlock3D::initialize -> executeInternalProcessors (multiBlock/multiBlock3D.cpp:486-510)
     void initialize() override {
+        // MultiBlock3D::initialize = executeInternalProcessors (multiBlock/multiBlock3D.cpp:330-332): with the sweep integrated
+        // as a level-0 processor this is a whole step
+        if (ext_) { advance(1, true); return; }
         sync_setup();
         run_processors();
+    }
+
+    // ----------------------------------------------------- the external-moment sweep
+
+    /// generateMultiScalarField / generateMultiTensorField<3> + integrateProcessingFunctional(ExternalRhoJcollideAndStream3D, .., 0)
+    /// + integrateProcessingFunctional(BoxRhoBarJfunctional3D, .., 3) of the fork's application (src/variables.hh:475-486).
+    /// `bulk`: the box the two functionals were integrated on -- the user's lattice; what lies outside is the envelope
+    /// layer which the sweep collides (with the zero moments found there) and streams, dynamicsProcessor3D.hh:118-119.
+    void enable_external_rhoj(const int bulk[6]) override {
+        check_box(bulk);
+        if (!procs_.empty())
+            throw PlbError("integrate the external-moment sweep before the boundary condition (its level-0 processors then run after the sweep, as this engine does)");
+        for (Slab& sl : slabs_) {
+            if (sl.dExt) continue;
+            sl.dExt = (T*)dev_alloc(4 * (size_t)sl.cellsStore * sizeof(T));
+            PLB_CUDA(cudaMemsetAsync(sl.dExt, 0, 4 * (size_t)sl.cellsStore * sizeof(T), stream_));
+        }
+        std::memcpy(bulk_, bulk, sizeof bulk_);
+        ext_ = true;
+        allowFuse_ = false;                    // BoxRhoBarJ reads the completed populations right after the processors
+        for (Slab& sl : slabs_) sl.dirtySched = true;
+    }
+
+    /// n x { lattice.executeInternalProcessors(); lattice.incrementTime(); } (viscosityTest/src/test.cpp:64-65)
+    void execute_internal_processors(int n) override {
+        if (!ext_) throw PlbError("no external-moment sweep is integrated in this lattice");
+        advance(n, true);
+    }
+
+    /// applyProcessingFunctional(new BoxRhoBarJfunctional3D, box, rhoBarJarg) (src/variables.hh:650)
+    void apply_rhobar_j(const int box[6]) override {
+        if (!ext_) throw PlbError("no external-moment sweep is integrated in this lattice");
+        check_box(box);
+        int b[6];
+        if (!intersect(box, bulk_, b)) return;
+        sync_setup();
+        materialize();
+        for (Slab& sl : slabs_) {
+            BoxL lb;
+            if (!local_box(sl, b, lb)) continue;
+            rhobar_j_kernel<T, Q><<<(unsigned)((lb.cells() + 127) / 128), 128, 0, stream_>>>(ctx(sl), lb, sl.dExt, sl.cellsStore);
+            launched();
+        }
+    }
+
+    /// the rhoBar / j fields across the ABI: T [cells of the box owned by this rank][rhoBar, jx, jy, jz]
+    void transfer_rhobar_j(const int box[6], void* data, size_t bytes, bool up) override {
+        if (!ext_) throw PlbError("no external-moment sweep is integrated in this lattice");
+        check_box(box);
+        if (bytes != local_bytes(box) / Q * 4) throw PlbError("buffer size does not match the box");
+        char* host = (char*)data;
+        for (Slab& sl : slabs_) {
+            BoxL b;
+            if (!local_box(sl, box, b)) continue;
+            const size_t planeBytes = (size_t)b.ny() * b.nz() * 4 * sizeof(T);
+            const int planesPerChunk = (int)std::max<size_t>(1, STAGE_BYTES / planeBytes);
+            for (int X = b.X0; X <= b.X1; X += planesPerChunk) {
+                BoxL cb = b;
+                cb.X0 = X; cb.X1 = std::min(b.X1, X + planesPerChunk - 1);
+                const size_t nb = (size_t)cb.cells() * 4 * sizeof(T);
+                T* st = (T*)stage(nb);
+                const unsigned grid = (unsigned)((cb.cells() + 127) / 128);
+                if (up) {
+                    PLB_CUDA(cudaMemcpyAsync(st, host, nb, cudaMemcpyHostToDevice, stream_));
+                    ext_transfer_kernel<T, true><<<grid, 128, 0, stream_>>>(geo(sl), cb, sl.dExt, sl.cellsStore, st);
+                } else {
+                    ext_transfer_kernel<T, false><<<grid, 128, 0, stream_>>>(geo(sl), cb, sl.dExt, sl.cellsStore, st);
+                    PLB_CUDA(cudaMemcpyAsync(host, st, nb, cudaMemcpyDeviceToHost, stream_));
+                }
+                launched();
+                PLB_CUDA(cudaStreamSynchronize(stream_));
+                host += nb;
+            }
+        }
     }
 
     // ---------------------------------------------------------------------------- data in/out
@@ -411,6 +491,12 @@ public:
 
     /// n x MultiBlockLattice3D::collideAndStream() (multiBlock/multiBlockLattice3D.hh:318-360)
     void collide_and_stream(int n) override {
+        if (ext_) throw PlbError("a lattice that carries the external-moment sweep is stepped by execute_internal_processors");
+        advance(n, false);
+    }
+
+    /// the step; ext: the sweep takes rhoBar and j from the fields and the fields are recomputed at the end (level 3)
+    void advance(int n, bool ext) {
         if (n < 0) throw PlbError("negative step count");
         if (desc_.nRanks > 1 && !comm_) throw PlbError("plb_b200_comm_init must be called before stepping a multi-rank lattice");
         sync_setup();
@@ -454,7 +540,16 @@ public:
             }
             exchange_unpack();
             run_processors();
-            stepped_ = true;
+            if (ext) {
+                for (Slab& sl : slabs_) {
+                    BoxL lb;
+                    if (!local_box(sl, bulk_, lb)) continue;
+                    rhobar_j_kernel<T, Q><<<(unsigned)((lb.cells() + 127) / 128), 128, 0, stream_>>>(ctx(sl), lb, sl.dExt, sl.cellsStore);
+                    launched();
+                }
+            } else {
+                stepped_ = true;
+            }
         }
     }
 
@@ -936,6 +1031,14 @@ private:
         a.omega = dyns_[0].omega; a.preFactor = dyns_[0].preFactor;
         a.gatherStats = statsOn_ ? 1 : 0;
         a.partials = nullptr; a.ticket = sl.dTicket; a.statsOut = sl.dStats + 4 * slot;
+        a.ext = sl.dExt; a.extStride = sl.cellsStore;
+        if (ext_) {
+            // the statistics of this mode are never evaluated by the reference's loop (executeInternalProcessors + incrementTime)
+            a.gatherStats = 0;
+            if (swapped_) launch_sweep_with<DYN_EXTERNAL, true, true, false>(sl, a, 6);
+            else launch_sweep_with<DYN_EXTERNAL, true, false, false>(sl, a, 6);
+            return;
+        }
         bool generic = L::is_inert(dyns_[0].type);
         for (size_t k = 1; k < dyns_.size(); ++k) if (!L::is_inert(dyns_[k].type)) generic = true;
         const bool odd = swapped_;

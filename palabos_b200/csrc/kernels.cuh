@@ -262,6 +262,8 @@ struct SweepArgs {
     double* partials;         ///< [gridDim.x][4] per-block partial sums
     unsigned int* ticket;     ///< arrival counter for the last-block reduction
     double* statsOut;         ///< [4] sum rhoBar, sum uSqr, max uSqr, cell count of this launch
+    const T* ext;             ///< MAIN == DYN_EXTERNAL: rhoBar [cells] followed by j_x, j_y, j_z [cells] each (extStride apart)
+    long long extStride;
 };
 
 /// Deterministic block reduction of the BlockStatistics accumulators (core/blockStatistics.cpp:205-229:
@@ -393,7 +395,16 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
         k &= KIND_MASK;
         T rhoBar = (T)0, uSqr = (T)0;
         bool took;
-        if (!GENERIC) {
+        if constexpr (MAIN == DYN_EXTERNAL) {
+            // ExternalRhoJcollideAndStream3D (basicDynamics/dynamicsProcessor3D.hh:41-76): rhoBar and j come from the fields
+            static_assert(MAIN != DYN_EXTERNAL || GENERIC, "the external-moment sweep reads the dynamics table");
+            const Dyn<T> d = a.dyns[k];
+            T j[3];
+            const T rb = a.ext[c];
+            j[0] = a.ext[a.extStride + c]; j[1] = a.ext[2 * a.extStride + c]; j[2] = a.ext[3 * a.extStride + c];
+            L::collide_external(d, f, rb, j);
+            took = false;
+        } else if (!GENERIC) {
             if (k == 0) {
                 took = L::template collide_as<MAIN>(f, a.omega, a.preFactor, rhoBar, uSqr);
             } else {
@@ -782,6 +793,50 @@ __global__ void density_velocity_kernel(CellCtx<T> cx, BoxL box, T* out) {
     out[4 * k] = L::cell_density(v.d, v.hasBc, v.b, v.f);
     L::cell_velocity(v.d, v.hasBc, v.b, v.f, u);
     out[4 * k + 1] = u[0]; out[4 * k + 2] = u[1]; out[4 * k + 3] = u[2];
+}
+
+/// BoxRhoBarJfunctional3D::processGenericBlocks (dataProcessors/dataAnalysisFunctional3D.hh:528-548): Dynamics::computeRhoBarJ
+/// of every cell of a box into the fields  ext = rhoBar [cells] | j_x | j_y | j_z  (stride apart, storage cell index)
+template <class T, int Q>
+__global__ void __launch_bounds__(128) rhobar_j_kernel(CellCtx<T> cx, BoxL box, T* ext, long long stride) {
+    using L = LB<T, Q>;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= box.cells()) return;
+    int X, y, z;
+    const int c = box_cell(cx.g, box, k, X, y, z);
+    const int kb = cx.kind[c];
+    const Dyn<T> d = cx.dyns[kb & KIND_MASK];
+    const int bi = cx.bcIdx[c];
+    const bool hasBc = bi >= 0;
+    Bc<T> b;
+    if (hasBc) b = cx.bcs[bi];
+    else { b.kind = -1; b.dir = 0; b.ori = 1; b.u[0] = b.u[1] = b.u[2] = (T)0; b.rhoBar = (T)0; }
+    T f[Q];
+    if (L::rhoBar_j_reads_pops(d.type, hasBc, b.kind)) {
+        const Nbr n = make_nbr(cx.g, X, y, z);
+        CellIO<T, Q>::load(cx.F, cx.g, n, c, cx.swapped, f);
+        if (cx.pending && (kb & KIND_PLANE) && hasBc) complete_pending<T, Q>(d.type, cx.bcs, bi, f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) f[i] = (T)0;
+    }
+    T rhoBar, j[3];
+    L::cell_rhoBar_j(d, hasBc, b, f, rhoBar, j);
+    ext[c] = rhoBar; ext[stride + c] = j[0]; ext[2 * stride + c] = j[1]; ext[3 * stride + c] = j[2];
+}
+
+/// the fields across the ABI: wire = T [cells of the box][rhoBar, jx, jy, jz]
+template <class T, bool UP>
+__global__ void ext_transfer_kernel(Geo g, BoxL box, T* ext, long long stride, T* wire) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= box.cells()) return;
+    int X, y, z;
+    const int c = box_cell(g, box, k, X, y, z);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        if (UP) ext[m * stride + c] = wire[4 * k + m];
+        else wire[4 * k + m] = ext[m * stride + c];
+    }
 }
 
 /// BoxSumEnergyFunctional3D (dataProcessors/dataAnalysisFunctional3D.hh:97-123: sum of |u|^2, double

@@ -14,6 +14,8 @@
 namespace plb200 {
 
 enum DynType : int { DYN_BGK = 0, DYN_RLB = 1, DYN_TRT = 2, DYN_SMAGO = 3, DYN_BOUNCEBACK = 4, DYN_NODYNAMICS = 5, DYN_INCBGK = 6 };
+/// not a dynamics: the MAIN argument of the sweep instantiation that collides with externally supplied moments (collide_external)
+constexpr int DYN_EXTERNAL = 100;
 enum BcKind : int { BC_VEL_REG = 0, BC_RHO_REG = 1, BC_VEL_ZH = 2, BC_RHO_ZH = 3, BC_STORE_VEL = 4 };
 enum ProcClass : int { PROC_PLANE = 0, PROC_EDGE = 1, PROC_CORNER = 2 };
 
@@ -143,6 +145,32 @@ struct LB {
         Partial p = partial_rho(f);
         rhoBar = p.xm + p.x0 + p.xp;
         j[0] = (p.xp - p.xm); j[1] = (p.yp - p.ym); j[2] = (p.zp - p.zm);
+        const T invRho = invRhoOf(rhoBar);
+        PiNeq[0] = p.xp + p.xm - cs2() * rhoBar - invRho * j[0] * j[0];
+        PiNeq[3] = p.yp + p.ym - cs2() * rhoBar - invRho * j[1] * j[1];
+        PiNeq[5] = p.zp + p.zm - cs2() * rhoBar - invRho * j[2] * j[2];
+        if constexpr (Q == 19) {
+            PiNeq[1] = f[4] - f[5] + f[13] - f[14] - invRho * j[0] * j[1];
+            PiNeq[2] = f[6] - f[7] + f[15] - f[16] - invRho * j[0] * j[2];
+            PiNeq[4] = f[8] - f[9] + f[17] - f[18] - invRho * j[1] * j[2];
+        } else {
+            PiNeq[1] = f[4] - f[5] + f[10] + f[11] - f[12] - f[13]
+                     + f[17] - f[18] + f[23] + f[24] - f[25] - f[26]
+                     - invRho * j[0] * j[1];
+            PiNeq[2] = f[6] - f[7] + f[10] - f[11] + f[12] - f[13]
+                     + f[19] - f[20] + f[23] - f[24] + f[25] - f[26]
+                     - invRho * j[0] * j[2];
+            PiNeq[4] = f[8] - f[9] + f[10] - f[11] - f[12] + f[13]
+                     + f[21] - f[22] + f[23] - f[24] - f[25] + f[26]
+                     - invRho * j[1] * j[2];
+        }
+    }
+
+    /// momentTemplates::compute_PiNeq(cell, rhoBar, j, PiNeq) latticeBoltzmann/momentTemplates.h:118-123 ->
+    /// momentTemplatesImpl::compute_PiNeq(f, rhoBar, j, PiNeq, invRho) momentTemplates3D.h:482-497 (D3Q19), :191-212 (D3Q27):
+    /// the off-equilibrium stress from the populations and externally supplied moments
+    PLB_HD static void compute_PiNeq(const T* f, T rhoBar, const T j[3], T PiNeq[6]) {
+        Partial p = partial_rho(f);
         const T invRho = invRhoOf(rhoBar);
         PiNeq[0] = p.xp + p.xm - cs2() * rhoBar - invRho * j[0] * j[0];
         PiNeq[3] = p.yp + p.ym - cs2() * rhoBar - invRho * j[1] * j[1];
@@ -460,6 +488,50 @@ struct LB {
         }
     }
 
+    /// Dynamics::collideExternal(cell, rhoBar, j, thetaBar, stat): the collision with moments taken from fields instead of
+    /// the populations (ExternalRhoJcollideAndStream3D, basicDynamics/dynamicsProcessor3D.hh:41-76).  BGK
+    /// isoThermalDynamics.hh:333-338, IncBGK :1422-1427, RegularizedBGK :1605-1615, TRT complexDynamics/trtDynamics.hh:102-134,
+    /// SmagorinskyBGK smagorinskyDynamics.hh:306-320, BounceBack core/dynamics.hh:793-799, NoDynamics :974-978; a boundary
+    /// composite forwards to its base dynamics (core/dynamics.hh:478-484).
+    PLB_HD static void collide_external(const Dyn<T>& d, T* f, T rhoBar, const T j[3]) {
+        switch (d.type) {
+        case DYN_BGK:    bgk_ma2_collision(f, rhoBar, j, d.omega); break;
+        case DYN_INCBGK: bgk_ma2_collision_base(f, rhoBar, j, d.omega, (T)1); break;
+        case DYN_RLB: {
+            T PiNeq[6];
+            compute_PiNeq(f, rhoBar, j, PiNeq);
+            const T invRho = invRhoOf(rhoBar);
+            rlb_collision(f, rhoBar, invRho, j, PiNeq, d.omega);
+            break; }
+        case DYN_TRT: {
+            const T sPlus = d.omega;
+            const T sMinus = (T)1.1;
+            T eq[Q];
+            const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+            const T invRho = invRhoOf(rhoBar);
+            bgk_ma2_equilibria(rhoBar, invRho, j, jSqr, eq);
+            f[0] += -sPlus * f[0] + sPlus * eq[0];
+#pragma unroll
+            for (int i = 1; i <= H; ++i) {
+                const T eq_plus = 0.5 * (eq[i] + eq[i + H]);
+                const T eq_minus = 0.5 * (eq[i] - eq[i + H]);
+                const T f_plus = 0.5 * (f[i] + f[i + H]);
+                const T f_minus = 0.5 * (f[i] - f[i + H]);
+                f[i]     += -sPlus * (f_plus - eq_plus) - sMinus * (f_minus - eq_minus);
+                f[i + H] += -sPlus * (f_plus - eq_plus) + sMinus * (f_minus - eq_minus);
+            }
+            break; }
+        case DYN_SMAGO: {
+            T PiNeq[6];
+            compute_PiNeq(f, rhoBar, j, PiNeq);
+            const T omega = smago_omega(d.omega, d.preFactor, rhoBar, PiNeq);
+            bgk_ma2_collision(f, rhoBar, j, omega);
+            break; }
+        case DYN_BOUNCEBACK: collide_bounceback(f); break;
+        default: break;
+        }
+    }
+
     // ------------------------------------------------------------------------ regularization
 
     PLB_HD static bool is_inert(int type) { return type == DYN_BOUNCEBACK || type == DYN_NODYNAMICS; }
@@ -717,6 +789,31 @@ struct LB {
         }
         if (is_inert(d.type)) return rhoBarOf(d.rho);
         return get_rhoBar(f);
+    }
+
+    /// Dynamics::computeRhoBarJ of whatever sits on the cell -- what BoxRhoBarJfunctional3D stores
+    /// (dataProcessors/dataAnalysisFunctional3D.hh:528-548): bulk get_rhoBar_j core/dynamics.hh:357-361; BounceBack rhoBar(rho), 0
+    /// :880-885; NoDynamics 1 - SkordosFactor, 0 :1061-1066; velocity planes boundaryDynamics.hh:682-701; density planes :816-822;
+    /// StoreVelocityDynamics (edges, corners) rho = computeDensity, j = rho * velocity :348-359
+    PLB_HD static void cell_rhoBar_j(const Dyn<T>& d, bool hasBc, const Bc<T>& b, const T* f, T& rhoBar, T j[3]) {
+        if (hasBc) {
+            if (b.kind == BC_STORE_VEL) {
+                const T rho = cell_density(d, hasBc, b, f);
+                rhoBar = rhoBarOf(rho);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) j[k] = rho * (b.u[k] - 0.5 * (T)0);
+            } else {
+                plane_rhoBar_j(b, f, rhoBar, j, vel_is_j(d.type));
+            }
+            return;
+        }
+        if (d.type == DYN_BOUNCEBACK) { rhoBar = rhoBarOf(d.rho); j[0] = j[1] = j[2] = (T)0; return; }
+        if (d.type == DYN_NODYNAMICS) { rhoBar = (T)1 - (T)1; j[0] = j[1] = j[2] = (T)0; return; }
+        get_rhoBar_j(f, rhoBar, j);
+    }
+    PLB_HD static bool rhoBar_j_reads_pops(int dynType, bool hasBc, int bcKind) {
+        if (hasBc) return bcKind == BC_STORE_VEL ? !is_inert(dynType) : true;
+        return !is_inert(dynType);
     }
 
     /// iniCellAtEquilibrium core/cell.hh:124-132

@@ -16,7 +16,8 @@ void launch_sweep_kernel(int grid, cudaStream_t stream, const SweepArgs<T>& a) {
     sweep_kernel<T, Q, MAIN, GENERIC, ODD, PLANES><<<grid, sweep_threads(ODD), 0, stream>>>(a);
 }
 /// every combination the engine launches (LatticeImpl::launch_sweep): the five collision models compiled in as the
-/// background dynamics, and the generic form that reads the model from the dynamics table; with and without fused planes
+/// background dynamics, and the generic form that reads the model from the dynamics table; with and without fused planes;
+/// the external-moment sweep (moments from the rhoBar / j fields, plane boundaries completed eagerly)
 #define PLB_INSTANTIATE_SWEEPS(T, Q, ODD)                                                        \
     template void launch_sweep_kernel<T, Q, DYN_BGK, false, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);    \
     template void launch_sweep_kernel<T, Q, DYN_BGK, false, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);     \
@@ -29,7 +30,8 @@ void launch_sweep_kernel(int grid, cudaStream_t stream, const SweepArgs<T>& a) {
     template void launch_sweep_kernel<T, Q, DYN_INCBGK, false, ODD, false>(int, cudaStream_t, const SweepArgs<T>&); \
     template void launch_sweep_kernel<T, Q, DYN_INCBGK, false, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);  \
     template void launch_sweep_kernel<T, Q, DYN_BGK, true, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);     \
-    template void launch_sweep_kernel<T, Q, DYN_BGK, true, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);
+    template void launch_sweep_kernel<T, Q, DYN_BGK, true, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);      \
+    template void launch_sweep_kernel<T, Q, DYN_EXTERNAL, true, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);
 #endif
 
 }  // namespace plb200
