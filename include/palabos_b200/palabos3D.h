@@ -72,6 +72,7 @@ struct Box3D {
     plint getNz() const { return z1 - z0 + 1; }
     plint nCells() const { return getNx() * getNy() * getNz(); }
     Box3D enlarge(plint w) const { return Box3D(x0 - w, x1 + w, y0 - w, y1 + w, z0 - w, z1 + w); }
+    bool operator==(Box3D const& r) const { return x0 == r.x0 && x1 == r.x1 && y0 == r.y0 && y1 == r.y1 && z0 == r.z0 && z1 == r.z1; }
     plint x0, x1, y0, y1, z0, z1;
 };
 namespace detail {
@@ -159,6 +160,22 @@ private:
 
 template <typename T, template <typename U> class Descriptor> class MultiBlockLattice3D;
 
+/// multiBlock/multiBlock3D.h: the common base of lattices and fields -- here only what a std::vector<MultiBlock3D*> argument
+/// list of integrateProcessingFunctional / applyProcessingFunctional needs
+class MultiBlock3D {
+public:
+    virtual ~MultiBlock3D() {}
+};
+
+/// Tag of the lattice constructor for the time loop of the fork's own application (src/variables.hh:461-486): the lattice
+/// will carry ExternalRhoJcollideAndStream3D, whose sweep collides and streams the reference's ENVELOPE layer as well
+/// (basicDynamics/dynamicsProcessor3D.hh:118-119).  The engine has to allocate that layer, so it must know at construction;
+/// periodicity is part of it (the envelope of a periodic direction is the periodic image).
+struct WithEnvelope {
+    WithEnvelope(bool periodicX = false, bool periodicY = false, bool periodicZ = false) { per[0] = periodicX; per[1] = periodicY; per[2] = periodicZ; }
+    bool per[3];
+};
+
 /// multiBlock/multiBlock3D.h:69-90
 template <typename T, template <typename U> class Descriptor>
 class PeriodicitySwitch3D {
@@ -167,6 +184,7 @@ public:
     void toggle(int direction, bool on) { per[direction] = on; push(); }
     void toggleAll(bool on) { per[0] = per[1] = per[2] = on; push(); }
     bool get(int direction) const { return per[direction]; }
+    void b200Preset(const bool p[3]) { per[0] = p[0]; per[1] = p[1]; per[2] = p[2]; }
 private:
     void push();
     MultiBlockLattice3D<T, Descriptor>& lattice;
@@ -177,11 +195,23 @@ private:
 /// the reference does.  rank / numRanks / slabsPerRank describe the x-slab decomposition over the
 /// GPUs of one box (one process per GPU); the defaults are one GPU.
 template <typename T, template <typename U> class Descriptor>
-class MultiBlockLattice3D {
+class MultiBlockLattice3D : public MultiBlock3D {
 public:
+    /// the lattice of generateMultiBlockLattice(.., envelopeWidth, dynamics) + ExternalRhoJcollideAndStream3D (see WithEnvelope)
+    MultiBlockLattice3D(plint nx_, plint ny_, plint nz_, Dynamics<T, Descriptor>* backgroundDynamics, WithEnvelope env,
+                        int rank = 0, int numRanks = 1, int slabsPerRank = 1)
+        : nx(nx_), ny(ny_), nz(nz_), background(backgroundDynamics), periodicitySwitch(*this), statisticsOn(true),
+          enveloped(true), externalSweep(false), iterations(0) {
+        handle = plb_b200_create_enveloped(Descriptor<T>::q, (int)sizeof(T), (int)nx, (int)ny, (int)nz,
+                                           background->b200Kind(), background->b200P1(), background->b200P2(),
+                                           env.per[0], env.per[1], env.per[2], rank, numRanks, slabsPerRank);
+        if (!handle) { std::string m = plb_b200_last_error(); delete background; throw PlbLogicException(m); }
+        periodicitySwitch.b200Preset(env.per);
+    }
     MultiBlockLattice3D(plint nx_, plint ny_, plint nz_, Dynamics<T, Descriptor>* backgroundDynamics,
                         int rank = 0, int numRanks = 1, int slabsPerRank = 1)
-        : nx(nx_), ny(ny_), nz(nz_), background(backgroundDynamics), periodicitySwitch(*this), statisticsOn(true) {
+        : nx(nx_), ny(ny_), nz(nz_), background(backgroundDynamics), periodicitySwitch(*this), statisticsOn(true),
+          enveloped(false), externalSweep(false), iterations(0) {
         handle = plb_b200_create_distributed(Descriptor<T>::q, (int)sizeof(T), (int)nx, (int)ny, (int)nz,
                                              background->b200Kind(), background->b200P1(), background->b200P2(),
                                              rank, numRanks, slabsPerRank);
@@ -204,6 +234,16 @@ public:
     void collideAndStream() { detail::check(plb_b200_collide_and_stream(handle, 1)); }
     /// n steps queued at once (the host does not wait)
     void collideAndStream(plint n) { detail::check(plb_b200_collide_and_stream(handle, (int)n)); }
+    /// MultiBlock3D::executeInternalProcessors multiBlock/multiBlock3D.cpp:486-499 of a lattice that carries the external-moment
+    /// sweep at level 0 and BoxRhoBarJfunctional3D at level 3: the time step of viscosityTest/src/test.cpp:64-65
+    void executeInternalProcessors() {
+        if (!externalSweep) throw PlbLogicException("executeInternalProcessors: integrate ExternalRhoJcollideAndStream3D and BoxRhoBarJfunctional3D first");
+        detail::check(plb_b200_execute_internal_processors(handle, 1));
+    }
+    void incrementTime() { ++iterations; }
+    plint getTimeCounter() const { return iterations; }
+    bool b200Enveloped() const { return enveloped; }
+    void b200ExternalSweepIntegrated() { externalSweep = true; }
     void synchronize() { detail::check(plb_b200_synchronize(handle)); }
 
     /// NCCL communicator for numRanks > 1: rank 0 calls getCommId(), the application broadcasts the
@@ -239,6 +279,8 @@ private:
     plb_b200_lattice* handle;
     PeriodicitySwitch3D<T, Descriptor> periodicitySwitch;
     bool statisticsOn;
+    bool enveloped, externalSweep;
+    plint iterations;
 };
 
 template <typename T, template <typename U> class Descriptor>
@@ -495,7 +537,7 @@ private:
 
 /// the slice of MultiScalarField3D<int> (multiBlock/multiDataField3D.h) a voxel matrix needs
 template <typename T>
-class MultiScalarField3D {
+class MultiScalarField3D : public MultiBlock3D {
 public:
     MultiScalarField3D(plint nx_, plint ny_, plint nz_, T ini = T()) : nx(nx_), ny(ny_), nz(nz_), data((size_t)(nx_ * ny_ * nz_), ini) {}
     plint getNx() const { return nx; }
@@ -513,7 +555,7 @@ private:
 
 /// the slice of MultiTensorField3D<T,nDim> (multiBlock/multiDataField3D.h) field extraction needs
 template <typename T, int nDim>
-class MultiTensorField3D {
+class MultiTensorField3D : public MultiBlock3D {
 public:
     MultiTensorField3D(plint nx_, plint ny_, plint nz_) : nx(nx_), ny(ny_), nz(nz_), data((size_t)(nx_ * ny_ * nz_)) {}
     plint getNx() const { return nx; }
@@ -576,6 +618,100 @@ std::unique_ptr<MultiScalarField3D<T> > computeVelocityComponent(MultiBlockLatti
     std::unique_ptr<MultiScalarField3D<T> > f(new MultiScalarField3D<T>(domain.getNx(), domain.getNy(), domain.getNz()));
     for (size_t k = 0; k < f->b200Data().size(); ++k) f->b200Data()[k] = ru[4 * k + 1 + iComponent];
     return f;
+}
+
+// ---- the external-moment sweep of the fork's own application ---------------------------------------
+// src/variables.hh:475-486:
+//     rhoBar.reset(generateMultiScalarField<T>((MultiBlock3D&)*lattice, envelopeWidth).release());
+//     j.reset(generateMultiTensorField<T,3>((MultiBlock3D&)*lattice, envelopeWidth).release());
+//     rhoBarJarg = { lattice, rhoBar, j };
+//     integrateProcessingFunctional(new ExternalRhoJcollideAndStream3D<T,Descriptor>(), lattice->getBoundingBox(), rhoBarJarg, 0);
+//     integrateProcessingFunctional(new BoxRhoBarJfunctional3D<T,Descriptor>(),        lattice->getBoundingBox(), rhoBarJarg, 3);
+// src/variables.hh:650:  applyProcessingFunctional(new BoxRhoBarJfunctional3D<T,Descriptor>(), lattice->getBoundingBox(), rhoBarJarg);
+// viscosityTest/src/test.cpp:64-65:  lattice->executeInternalProcessors(); lattice->incrementTime();
+// The fields live on the device next to the populations.  The host objects made by generateMulti*Field are views that are
+// filled / sent on request (pullRhoBarJ / pushRhoBarJ) -- a per-step PCIe round trip would defeat the purpose.
+
+/// basicDynamics/dynamicsProcessor3D.h: ExternalRhoJcollideAndStream3D (tag: the sweep itself runs on the device)
+template <typename T, template <typename U> class Descriptor> class ExternalRhoJcollideAndStream3D {};
+/// dataProcessors/dataAnalysisFunctional3D.h: BoxRhoBarJfunctional3D
+template <typename T, template <typename U> class Descriptor> class BoxRhoBarJfunctional3D {};
+
+/// multiBlock/multiBlockGenerator3D.hh:116-135, :668-688
+template <typename T, template <typename U> class Descriptor>
+std::unique_ptr<MultiScalarField3D<T> > generateMultiScalarField(MultiBlockLattice3D<T, Descriptor>& lattice, plint /*envelopeWidth*/ = 1) {
+    return std::unique_ptr<MultiScalarField3D<T> >(new MultiScalarField3D<T>(lattice.getNx(), lattice.getNy(), lattice.getNz()));
+}
+template <typename T, int nDim, template <typename U> class Descriptor>
+std::unique_ptr<MultiTensorField3D<T, nDim> > generateMultiTensorField(MultiBlockLattice3D<T, Descriptor>& lattice, plint /*envelopeWidth*/ = 1) {
+    return std::unique_ptr<MultiTensorField3D<T, nDim> >(new MultiTensorField3D<T, nDim>(lattice.getNx(), lattice.getNy(), lattice.getNz()));
+}
+
+namespace detail {
+template <typename T, template <typename U> class Descriptor>
+MultiBlockLattice3D<T, Descriptor>& rhoBarJlattice(std::vector<MultiBlock3D*> const& args, Box3D domain) {
+    if (args.size() != 3) throw PlbLogicException("the argument list must be { lattice, rhoBar, j }");
+    MultiBlockLattice3D<T, Descriptor>* lattice = dynamic_cast<MultiBlockLattice3D<T, Descriptor>*>(args[0]);
+    if (!lattice || !dynamic_cast<MultiScalarField3D<T>*>(args[1]) || !dynamic_cast<MultiTensorField3D<T, 3>*>(args[2]))
+        throw PlbLogicException("the argument list must be { lattice, rhoBar, j }");
+    if (!lattice->b200Enveloped())
+        throw PlbLogicException("construct the lattice with plb::WithEnvelope: the external-moment sweep works on the envelope layer too");
+    (void)domain;
+    return *lattice;
+}
+}
+
+/// integrateProcessingFunctional(functional, domain, multiBlockArg, level) dataProcessors/dataProcessorWrapper3D.h, for the two
+/// functionals of this path; takes ownership of the functional like the reference.  The sweep must be integrated on the
+/// whole lattice and before the boundary condition (whose level-0 processors then run after it).
+template <typename T, template <typename U> class Descriptor>
+void integrateProcessingFunctional(ExternalRhoJcollideAndStream3D<T, Descriptor>* functional, Box3D domain,
+                                   std::vector<MultiBlock3D*> multiBlockArg, plint level = 0) {
+    delete functional;
+    MultiBlockLattice3D<T, Descriptor>& lattice = detail::rhoBarJlattice<T, Descriptor>(multiBlockArg, domain);
+    if (!(domain == lattice.getBoundingBox()) || level != 0)
+        throw PlbLogicException("ExternalRhoJcollideAndStream3D: integrate on the bounding box at level 0");
+}
+template <typename T, template <typename U> class Descriptor>
+void integrateProcessingFunctional(BoxRhoBarJfunctional3D<T, Descriptor>* functional, Box3D domain,
+                                   std::vector<MultiBlock3D*> multiBlockArg, plint level = 0) {
+    delete functional;
+    MultiBlockLattice3D<T, Descriptor>& lattice = detail::rhoBarJlattice<T, Descriptor>(multiBlockArg, domain);
+    if (!(domain == lattice.getBoundingBox()) || level < 1)
+        throw PlbLogicException("BoxRhoBarJfunctional3D: integrate on the bounding box at a level above the sweep's");
+    lattice.b200ExternalSweepIntegrated();
+}
+/// applyProcessingFunctional(new BoxRhoBarJfunctional3D, domain, rhoBarJarg): the moments of the current populations into the fields
+template <typename T, template <typename U> class Descriptor>
+void applyProcessingFunctional(BoxRhoBarJfunctional3D<T, Descriptor>* functional, Box3D domain, std::vector<MultiBlock3D*> multiBlockArg) {
+    delete functional;
+    MultiBlockLattice3D<T, Descriptor>& lattice = detail::rhoBarJlattice<T, Descriptor>(multiBlockArg, domain);
+    detail::CBox b(domain);
+    detail::check(plb_b200_apply_rhobar_j(lattice.b200Handle(), b.v));
+}
+/// device fields -> host views (whole lattice)
+template <typename T, template <typename U> class Descriptor>
+void pullRhoBarJ(MultiBlockLattice3D<T, Descriptor>& lattice, MultiScalarField3D<T>& rhoBar, MultiTensorField3D<T, 3>& j) {
+    detail::CBox b(lattice.getBoundingBox());
+    std::vector<T> w((size_t)lattice.getBoundingBox().nCells() * 4);
+    detail::check(plb_b200_download_rhobar_j(lattice.b200Handle(), b.v, w.data(), w.size() * sizeof(T)));
+    size_t k = 0;
+    for (plint x = 0; x < lattice.getNx(); ++x) for (plint y = 0; y < lattice.getNy(); ++y) for (plint z = 0; z < lattice.getNz(); ++z, ++k) {
+        rhoBar.get(x, y, z) = w[4 * k];
+        j.get(x, y, z) = Array<T, 3>(w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    }
+}
+/// host views -> device fields (whole lattice): what a processor that forces the momentum between two steps ends with
+template <typename T, template <typename U> class Descriptor>
+void pushRhoBarJ(MultiBlockLattice3D<T, Descriptor>& lattice, MultiScalarField3D<T> const& rhoBar, MultiTensorField3D<T, 3> const& j) {
+    detail::CBox b(lattice.getBoundingBox());
+    std::vector<T> w((size_t)lattice.getBoundingBox().nCells() * 4);
+    size_t k = 0;
+    for (plint x = 0; x < lattice.getNx(); ++x) for (plint y = 0; y < lattice.getNy(); ++y) for (plint z = 0; z < lattice.getNz(); ++z, ++k) {
+        w[4 * k] = rhoBar.get(x, y, z);
+        for (int d = 0; d < 3; ++d) w[4 * k + 1 + d] = j.get(x, y, z)[d];
+    }
+    detail::check(plb_b200_upload_rhobar_j(lattice.b200Handle(), b.v, w.data(), w.size() * sizeof(T)));
 }
 
 /// VtkImageOutput3D<T,TConv,n> io/vtkDataOutput.h:100-136, io/vtkDataOutput.hh:57-392, io/vtkDataOutput.cpp:39-100 (this fork
