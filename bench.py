@@ -196,8 +196,10 @@ def our_arm(args):
     cavity = args.workload == "cavity"
     ext = args.workload == "ext_cavity"
     if ext:
-        # the sweep reads 4 more values per cell (rhoBar, j) than the plain one
-        BYTES_PER_LU = (2 * Q + 4) * 8
+        # nobody touches the fields between the steps of this workload, so the sweep recomputes the moments from the populations
+        # it gathers: 2*Q*8 bytes per cell like the plain sweep; PLB_B200_EXT_EXPLICIT=1 stores the
+        # fields after every step and reads them back (4 more values per cell in the sweep, and the moment pass)
+        BYTES_PER_LU = (2 * Q + (4 if os.environ.get("PLB_B200_EXT_EXPLICIT", "0")[:1] == "1" else 0)) * 8
         omega, p2 = cavity_omega(ny), 0.0
         what = ("3D lid-driven cavity D3Q19 IncBGK fp64 stepped by executeInternalProcessors(): ExternalRhoJcollideAndStream3D (level 0) + "
                 "BoxRhoBarJfunctional3D (level 3), %dx%dx%d (%d^3 per GPU) + the envelope layer, regularized velocity BC" % (nx, ny, nz, n))

@@ -44,6 +44,8 @@ class LatticeImpl : public LatticeBase {
         Item* dItems = nullptr; size_t dItemsCap = 0;
         double* dPartials = nullptr; int partialsCap = 0;
         T* dExt = nullptr;                 ///< external-moment sweep: rhoBar [cellsStore] | j_x | j_y | j_z, zero where nothing writes
+        int* dBcCells = nullptr; size_t dBcCellsCap = 0;   ///< ... cells that carry a boundary record (-1: dead record)
+        int nBcCells = 0;
         double* dStats = nullptr;          ///< [3 launches][4]: a step sweeps a slab in up to three launches (5.)
         int statSlots = 0;                 ///< launches of the last step
         unsigned int* dTicket = nullptr;
@@ -79,6 +81,9 @@ class LatticeImpl : public LatticeBase {
     bool statsOn_ = true;
     bool ext_ = false;                       ///< the lattice is stepped by ExternalRhoJcollideAndStream3D + BoxRhoBarJfunctional3D
     int bulk_[6] = {0, 0, 0, 0, 0, 0};       ///< ... whose level-3 domain is this box (the user's lattice; the rest is envelope)
+    bool extImplied_ = false;                ///< the fields are what BoxRhoBarJfunctional3D makes of the CURRENT populations: the fused sweep may recompute them
+    bool extComplete_ = true;                ///< the fields are stored for every cell (false: only for cells with boundary dynamics, the rest is implied)
+    bool extFuse_ = true;                    ///< PLB_B200_EXT_EXPLICIT=1 in the environment: always store and re-read the fields (A/B tests)
     bool anySetup_ = false;
     bool stepped_ = false;
     cudaStream_t stream_ = 0;
@@ -114,6 +119,7 @@ public:
         if ((long long)ny_ * nz_ >= (1ll << 30)) throw PlbError("y-z plane too large");
         if (const char* e = std::getenv("PLB_B200_EAGER_PLANES")) allowFuse_ = !(e[0] == '1');
         if (const char* e = std::getenv("PLB_B200_OVERLAP")) overlap_ = e[0] == '1' ? 1 : (e[0] == '0' ? 0 : -1);
+        if (const char* e = std::getenv("PLB_B200_EXT_EXPLICIT")) extFuse_ = !(e[0] == '1');
         add_dyn(d.dynamics, d.p1, d.p2);     // entry 0: the background dynamics
         for (int s = 0; s < d.slabsPerRank; ++s) {
             Slab sl;
@@ -143,7 +149,7 @@ public:
     ~LatticeImpl() override {
         cudaStreamSynchronize(stream_);
         for (Slab& sl : slabs_) {
-            cudaFree(sl.F); cudaFree(sl.dExt); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems); cudaFree(sl.dSparse);
+            cudaFree(sl.F); cudaFree(sl.dExt); cudaFree(sl.dBcCells); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems); cudaFree(sl.dSparse);
             cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket);
         }
         cudaFree(dDyns_); cudaFree(dStage_); cudaFree(dReduce_);
@@ -196,6 +202,7 @@ public:
 
     void define_dynamics_box(const int box[6], int dynamics, double p1, double p2) override {
         check_box(box);
+        ext_detach();
         const int idx = add_dyn(dynamics, p1, p2);
         anySetup_ = true;
         for (Slab& sl : slabs_) {
@@ -222,6 +229,7 @@ public:
 
     void define_dynamics_mask(const int32_t* mask, int flag, int dynamics, double p1, double p2) override {
         if (!mask) throw PlbError("null mask");
+        ext_detach();
         const int idx = add_dyn(dynamics, p1, p2);
         anySetup_ = true;
         for (Slab& sl : slabs_) {
@@ -329,6 +337,7 @@ public:
 
     void initialize_at_equilibrium(const int box[6], double rho, const double u[3]) override {
         check_box(box);
+        ext_detach();
         sync_setup();
         materialize();
         for (Slab& sl : slabs_) {
@@ -344,6 +353,7 @@ public:
     void initialize_at_equilibrium_field(const int box[6], const double* ru) override {
         check_box(box);
         if (!ru) throw PlbError("null field");
+        ext_detach();
         sync_setup();
         materialize();
         const long long rowCells = (long long)(box[3] - box[2] + 1) * (box[5] - box[4] + 1);
@@ -393,6 +403,7 @@ public:
         }
         std::memcpy(bulk_, bulk, sizeof bulk_);
         ext_ = true;
+        extImplied_ = false; extComplete_ = true;   // zero fields, as generateMultiScalarField / generateMultiTensorField leave them
         allowFuse_ = false;                    // BoxRhoBarJ reads the completed populations right after the processors
         for (Slab& sl : slabs_) sl.dirtySched = true;
     }
@@ -411,6 +422,15 @@ public:
         if (!intersect(box, bulk_, b)) return;
         sync_setup();
         materialize();
+        const bool whole = std::memcmp(b, bulk_, sizeof b) == 0;
+        if (!whole) ext_complete();            // the rest of the fields keeps its values
+        rhobar_j_box(b);
+        if (whole) extImplied_ = true;         // (a part: implied stays what it was -- the new values ARE the implied ones)
+        extComplete_ = true;
+    }
+
+    /// BoxRhoBarJ of the cells of a box, stored
+    void rhobar_j_box(const int b[6]) {
         for (Slab& sl : slabs_) {
             BoxL lb;
             if (!local_box(sl, b, lb)) continue;
@@ -418,12 +438,28 @@ public:
             launched();
         }
     }
+    /// store the implied part of the fields (only ever needed when somebody wants to see or change them)
+    void ext_complete() {
+        if (!ext_ || extComplete_) return;
+        sync_setup();
+        rhobar_j_box(bulk_);
+        extComplete_ = true;
+    }
+    /// the populations, the dynamics or the boundary set-up are about to change under the fields: from now on the fields are
+    /// data of their own (the reference's fields keep their values until the next level-3 pass)
+    void ext_detach() {
+        if (!ext_) return;
+        ext_complete();
+        extImplied_ = false;
+    }
 
     /// the rhoBar / j fields across the ABI: T [cells of the box owned by this rank][rhoBar, jx, jy, jz]
     void transfer_rhobar_j(const int box[6], void* data, size_t bytes, bool up) override {
         if (!ext_) throw PlbError("no external-moment sweep is integrated in this lattice");
         check_box(box);
         if (bytes != local_bytes(box) / Q * 4) throw PlbError("buffer size does not match the box");
+        ext_complete();
+        if (up) extImplied_ = false;           // the caller's values now: the next sweep reads them
         char* host = (char*)data;
         for (Slab& sl : slabs_) {
             BoxL b;
@@ -541,12 +577,20 @@ public:
             exchange_unpack();
             run_processors();
             if (ext) {
-                for (Slab& sl : slabs_) {
-                    BoxL lb;
-                    if (!local_box(sl, bulk_, lb)) continue;
-                    rhobar_j_kernel<T, Q><<<(unsigned)((lb.cells() + 127) / 128), 128, 0, stream_>>>(ctx(sl), lb, sl.dExt, sl.cellsStore);
-                    launched();
+                // level 3: BoxRhoBarJfunctional3D on the whole lattice.  Stored only for the cells with boundary dynamics; for the
+                // others the next sweep recomputes it from the populations it gathers (launch_sweep), or ext_complete() stores it
+                if (extFuse_) {
+                    for (Slab& sl : slabs_) {
+                        if (sl.nBcCells == 0) continue;
+                        rhobar_j_list_kernel<T, Q><<<(sl.nBcCells + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.dBcCells, sl.nBcCells, sl.dExt, sl.cellsStore);
+                        launched();
+                    }
+                    extComplete_ = false;
+                } else {
+                    rhobar_j_box(bulk_);
+                    extComplete_ = true;
                 }
+                extImplied_ = true;
             } else {
                 stepped_ = true;
             }
@@ -707,6 +751,7 @@ private:
     }
 
     void add_bc(int kind, int dir, int ori, const int box[6]) {
+        ext_detach();
         anySetup_ = true;
         for (Slab& sl : slabs_) {
             Group grp;
@@ -910,6 +955,8 @@ private:
         if (!anyDirty) return;
         materialize();                         // with the device state the completion was deferred under
         bool reflag = false;
+        bool structural = false;               // (external-moment sweep) which cells read their moments from the fields may have changed
+        for (Slab& sl : slabs_) structural = structural || sl.dirtyKind || sl.dirtyBcIndex || sl.dirtySched;
         if (dirtyDyns_) {
             PLB_CUDA(cudaMemcpyAsync(dDyns_, dyns_.data(), dyns_.size() * sizeof(Dyn<T>), cudaMemcpyHostToDevice, stream_));
             PLB_CUDA(cudaStreamSynchronize(stream_));
@@ -940,8 +987,22 @@ private:
                     PLB_CUDA(cudaMemcpyAsync(sl.dBcs, vals.data(), n * sizeof(Bc<T>), cudaMemcpyHostToDevice, stream_));
                     scatter_bc_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream_>>>(dCells, (int)n, sl.dBcIdx);
                     launched();
+                    if (ext_) {
+                        if (n > sl.dBcCellsCap) {
+                            if (sl.dBcCells) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dBcCells); devBytes_ -= sl.dBcCellsCap * sizeof(int); }
+                            sl.dBcCellsCap = n + n / 2 + 16;
+                            sl.dBcCells = (int*)dev_alloc(sl.dBcCellsCap * sizeof(int));
+                        }
+                        // owned planes only: the records on the ghost planes exist for the neighbour reads of the edge / corner processors
+                        std::vector<int> owned(cells);
+                        for (size_t r = 0; r < n; ++r)
+                            if (owned[r] >= 0 && (owned[r] < P_ || owned[r] >= (sl.nxl + 1) * P_)) owned[r] = -1;
+                        PLB_CUDA(cudaMemcpyAsync(sl.dBcCells, owned.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+                        PLB_CUDA(cudaStreamSynchronize(stream_));     // `owned` goes out of scope
+                    }
                     PLB_CUDA(cudaStreamSynchronize(stream_));
                 }
+                sl.nBcCells = (int)n;
                 sl.dirtyBcIndex = false;
                 sl.bcDirtyLo = sl.bcDirtyHi = 0;
             }
@@ -979,6 +1040,17 @@ private:
                         launched();
                     }
                 }
+            }
+        }
+        if (ext_ && structural) {
+            // KIND_PLANE means something else in this mode (plane completion is never fused here): "moments from the fields"
+            for (Slab& sl : slabs_) {
+                PLB_CUDA(cudaMemcpyAsync(sl.dKind, sl.hKind.data(), (size_t)sl.cellsStore, cudaMemcpyHostToDevice, stream_));
+                PLB_CUDA(cudaStreamSynchronize(stream_));
+                BoxL lb;
+                if (!local_box(sl, bulk_, lb)) { lb.X0 = 1; lb.X1 = 0; lb.y0 = lb.z0 = 0; lb.y1 = lb.z1 = -1; }
+                flag_ext_cells_kernel<<<(unsigned)((sl.cellsStore + 255) / 256), 256, 0, stream_>>>(sl.dKind, sl.dBcIdx, geo(sl), lb, (int)sl.cellsStore);
+                launched();
             }
         }
     }
@@ -1035,8 +1107,13 @@ private:
         if (ext_) {
             // the statistics of this mode are never evaluated by the reference's loop (executeInternalProcessors + incrementTime)
             a.gatherStats = 0;
-            if (swapped_) launch_sweep_with<DYN_EXTERNAL, true, true, false>(sl, a, 6);
-            else launch_sweep_with<DYN_EXTERNAL, true, false, false>(sl, a, 6);
+            if (extImplied_ && extFuse_) {
+                if (swapped_) launch_sweep_with<DYN_EXTERNAL_FUSED, true, true, false>(sl, a, 7);
+                else launch_sweep_with<DYN_EXTERNAL_FUSED, true, false, false>(sl, a, 7);
+            } else {
+                if (swapped_) launch_sweep_with<DYN_EXTERNAL, true, true, false>(sl, a, 6);
+                else launch_sweep_with<DYN_EXTERNAL, true, false, false>(sl, a, 6);
+            }
             return;
         }
         bool generic = L::is_inert(dyns_[0].type);
@@ -1167,6 +1244,7 @@ private:
         check_box(box);
         if (bytes != local_bytes(box)) throw PlbError("buffer size does not match the box");
         if (!data && bytes) throw PlbError("null buffer");
+        if (up) ext_detach();
         sync_setup();
         materialize();
         if (!copyStream_) {

@@ -392,16 +392,29 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
     };
     // Cell::collide, scatter, gatherStatistics
     auto collide_scatter = [&](int c, int k, bool interior, const Nbr& n, T* f) {
+        const int kRaw = k;
+        (void)kRaw;
         k &= KIND_MASK;
         T rhoBar = (T)0, uSqr = (T)0;
         bool took;
-        if constexpr (MAIN == DYN_EXTERNAL) {
-            // ExternalRhoJcollideAndStream3D (basicDynamics/dynamicsProcessor3D.hh:41-76): rhoBar and j come from the fields
-            static_assert(MAIN != DYN_EXTERNAL || GENERIC, "the external-moment sweep reads the dynamics table");
+        if constexpr (MAIN == DYN_EXTERNAL || MAIN == DYN_EXTERNAL_FUSED) {
+            // ExternalRhoJcollideAndStream3D (basicDynamics/dynamicsProcessor3D.hh:41-76): rhoBar and j come from the fields.
+            // DYN_EXTERNAL_FUSED: nobody has touched the fields since BoxRhoBarJfunctional3D filled them at the end of the
+            // previous step, so for a cell without boundary dynamics they hold Dynamics::computeRhoBarJ of the very
+            // populations this thread has just gathered -- recomputed here instead of stored and re-read (the moment
+            // pass and 64 B per cell of traffic go away).  Cells flagged KIND_PLANE (boundary dynamics: their moments follow
+            // the boundary formulas; envelope layer: zero for ever) still read the fields.
+            static_assert(GENERIC, "the external-moment sweep reads the dynamics table");
             const Dyn<T> d = a.dyns[k];
-            T j[3];
-            const T rb = a.ext[c];
-            j[0] = a.ext[a.extStride + c]; j[1] = a.ext[2 * a.extStride + c]; j[2] = a.ext[3 * a.extStride + c];
+            T rb, j[3];
+            if (MAIN == DYN_EXTERNAL || (kRaw & KIND_PLANE)) {
+                rb = a.ext[c];
+                j[0] = a.ext[a.extStride + c]; j[1] = a.ext[2 * a.extStride + c]; j[2] = a.ext[3 * a.extStride + c];
+            } else {
+                Bc<T> none;
+                none.kind = -1; none.dir = 0; none.ori = 1; none.u[0] = none.u[1] = none.u[2] = (T)0; none.rhoBar = (T)0;
+                L::cell_rhoBar_j(d, false, none, f, rb, j);
+            }
             L::collide_external(d, f, rb, j);
             took = false;
         } else if (!GENERIC) {
@@ -798,12 +811,43 @@ __global__ void density_velocity_kernel(CellCtx<T> cx, BoxL box, T* out) {
 /// BoxRhoBarJfunctional3D::processGenericBlocks (dataProcessors/dataAnalysisFunctional3D.hh:528-548): Dynamics::computeRhoBarJ
 /// of every cell of a box into the fields  ext = rhoBar [cells] | j_x | j_y | j_z  (stride apart, storage cell index)
 template <class T, int Q>
+__device__ __forceinline__ void rhobar_j_cell(const CellCtx<T>& cx, int c, int X, int y, int z, T* ext, long long stride);
+
+template <class T, int Q>
 __global__ void __launch_bounds__(128) rhobar_j_kernel(CellCtx<T> cx, BoxL box, T* ext, long long stride) {
-    using L = LB<T, Q>;
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= box.cells()) return;
     int X, y, z;
     const int c = box_cell(cx.g, box, k, X, y, z);
+    rhobar_j_cell<T, Q>(cx, c, X, y, z, ext, stride);
+}
+
+/// the same for a list of cells (those that carry boundary dynamics: the fused sweep recomputes the others itself)
+template <class T, int Q>
+__global__ void __launch_bounds__(128) rhobar_j_list_kernel(CellCtx<T> cx, const int* cells, int n, T* ext, long long stride) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int c = cells[t];
+    if (c < 0) return;
+    int X, y, z;
+    decode_cell(cx.g, c, X, y, z);
+    rhobar_j_cell<T, Q>(cx, c, X, y, z, ext, stride);
+}
+
+/// external-moment sweep: cells whose moments the fused sweep must read from the fields -- boundary dynamics on top,
+/// or outside the bulk box (the envelope layer)
+static __global__ void flag_ext_cells_kernel(uint8_t* kind, const int* bcIdx, Geo g, BoxL bulk, int nCells) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    int X, y, z;
+    decode_cell(g, c, X, y, z);
+    const bool inBulk = X >= bulk.X0 && X <= bulk.X1 && y >= bulk.y0 && y <= bulk.y1 && z >= bulk.z0 && z <= bulk.z1;
+    if (!inBulk || bcIdx[c] >= 0) kind[c] |= (uint8_t)KIND_PLANE;
+}
+
+template <class T, int Q>
+__device__ __forceinline__ void rhobar_j_cell(const CellCtx<T>& cx, int c, int X, int y, int z, T* ext, long long stride) {
+    using L = LB<T, Q>;
     const int kb = cx.kind[c];
     const Dyn<T> d = cx.dyns[kb & KIND_MASK];
     const int bi = cx.bcIdx[c];

@@ -16,6 +16,8 @@ namespace plb200 {
 enum DynType : int { DYN_BGK = 0, DYN_RLB = 1, DYN_TRT = 2, DYN_SMAGO = 3, DYN_BOUNCEBACK = 4, DYN_NODYNAMICS = 5, DYN_INCBGK = 6 };
 /// not a dynamics: the MAIN argument of the sweep instantiation that collides with externally supplied moments (collide_external)
 constexpr int DYN_EXTERNAL = 100;
+/// ... and the form that takes them from the fields only where they are not a function of the cell's own populations
+constexpr int DYN_EXTERNAL_FUSED = 101;
 enum BcKind : int { BC_VEL_REG = 0, BC_RHO_REG = 1, BC_VEL_ZH = 2, BC_RHO_ZH = 3, BC_STORE_VEL = 4 };
 enum ProcClass : int { PROC_PLANE = 0, PROC_EDGE = 1, PROC_CORNER = 2 };
 

@@ -240,6 +240,43 @@ def ext_periodic(nx, ny, nz, steps, dyn, omega, q=19, prec="f64", cs=0.0):
     return ext_finish(sc, steps, True)
 
 
+def ext_interleaved(nx=10, ny=8, nz=9):
+    """Everything a caller can do between two steps of the external-moment loop, interleaved with steps: read the fields,
+    overwrite the populations, change dynamics and boundary values, recompute the fields on a part of the lattice, force j.
+    (On the engine: every transition between 'fields implied by the populations' and 'fields are data of their own'.)"""
+    sc = Scenario(19, "f64", nx, ny, nz, "BGK", 1.45, 0.0)
+    sc.periodic(0, 0, 1)
+    sc.ext_integrate()
+    sc.bc_vel("local", 0, -1, (0, 0, 1, ny - 2, 0, nz - 1))
+    sc.bc_pres("zouhe", 0, +1, (nx - 1, nx - 1, 1, ny - 2, 0, nz - 1))
+    sc.dynamics((0, nx - 1, 0, 0, 0, nz - 1), "BB", 1.0)
+    sc.dynamics((0, nx - 1, ny - 1, ny - 1, 0, nz - 1), "BB", 1.0)
+    sc.set_velocity(sc.box, (0.02, 0, 0))
+    sc.set_density(sc.box, 1.0)
+    ru = poiseuille_profile(nx, ny, nz, 0.02, perturb=0.005)
+    sc.init_eq_field(sc.box, ru)
+    sc.ext_exec(2)                                  # zero fields: nobody has applied BoxRhoBarJ yet
+    sc.dump_rhobar_j("rj_a")
+    sc.ext_exec(3)
+    k = np.arange(nx * ny * nz * 19, dtype=np.float64).reshape(nx, ny, nz, 19)
+    sc.upload(1e-3 * np.sin(0.37 * k) * (1.0 / 19))  # populations replaced, fields keep the old moments
+    sc.ext_exec(2)
+    sc.dynamics((3, 5, 2, 4, 1, 3), "RLB", 1.2)
+    sc.dynamics((6, 7, 3, 4, 4, 6), "BB", 1.0)
+    sc.ext_exec(2)
+    sc.set_velocity((0, 0, 1, ny - 2, 0, nz - 1), (0.03, 0.001, 0))
+    sc.ext_exec(2)
+    sc.ext_add_j((2, 6, 1, 5, 2, 7), (5e-4, 0, -2e-4))
+    sc.ext_apply((4, nx - 1, 0, ny - 1, 0, 4))       # BoxRhoBarJ on a part: undoes the forcing there only
+    sc.dump_rhobar_j("rj_b")
+    sc.ext_exec(1)
+    sc.init_eq((1, 3, 1, 3, 1, 3), 1.02, (0.01, 0.0, -0.01))
+    sc.ext_exec(2)
+    sc.ext_apply()
+    sc.ext_exec(1)
+    return sc.stats().dump("f_end").dump_rhobar_j("rj_end").dump_rho_u("rho_u_end")
+
+
 # name -> (builder, how to store the reference outcome: "full" dumps, or "probe" = sha256 + sampled cells)
 CASES = {
     # configs[0]-style cavity, all dynamics on the path
@@ -294,6 +331,7 @@ CASES = {
     "ext_obstacle_incbgk":      (lambda: ext_obstacle(20, 10, 9, 40), "full"),
     "ext_periodic_trt_q27":     (lambda: ext_periodic(8, 7, 9, 30, "TRT", 1.5, q=27), "full"),
     "ext_periodic_rlb_f32":     (lambda: ext_periodic(8, 7, 9, 30, "RLB", 1.5, prec="f32"), "full"),
+    "ext_interleaved":          (lambda: ext_interleaved(), "full"),
     # edge cases
     "mixed_omega_11x8x9":       (lambda: mixed_omega(11, 8, 9, 40), "full"),
     "inlet_outlet_local":       (lambda: inlet_outlet_local(12, 9, 8, 40), "full"),

@@ -44,15 +44,35 @@ def gather_x(local, bounds, device=None):
 class DistEngine:
     """Same method names as palabos_b200.Lattice / OracleEngine, whole-lattice arrays in and out."""
 
-    def __init__(self, pb, q, prec, nx, ny, nz, dyn, p1, p2=0.0, slabs_per_rank=1, device=None):
+    def __init__(self, pb, q, prec, nx, ny, nz, dyn, p1, p2=0.0, slabs_per_rank=1, device=None, enveloped_periodic=None):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = device
-        self.lat = pb.Lattice(q, prec, nx, ny, nz, dyn, p1, p2, rank=self.rank, n_ranks=self.world, slabs_per_rank=slabs_per_rank)
+        self.lat = pb.Lattice(q, prec, nx, ny, nz, dyn, p1, p2, rank=self.rank, n_ranks=self.world, slabs_per_rank=slabs_per_rank,
+                              enveloped_periodic=enveloped_periodic)
         uid = [pb.comm_unique_id() if self.rank == 0 else None]
         dist.broadcast_object_list(uid, src=0, device=device)
         self.lat.comm_init(uid[0])
-        self.bounds = slab_bounds(nx, self.world, slabs_per_rank, pb.slab_range)
+        # an enveloped lattice (external-moment sweep) is decomposed with its envelope layer: engine plane = user plane + off
+        off = 1 if (enveloped_periodic is not None and not enveloped_periodic[0]) else 0
+        eng = slab_bounds(nx + 2 * off, self.world, slabs_per_rank, pb.slab_range)
+        self.bounds = [(max(lo - off, 0), min(hi - off, nx - 1)) for lo, hi in eng]
         self.nx, self.ny, self.nz, self.q = nx, ny, nz, q
+
+    def _box_bounds(self, box):
+        box = tuple(box or (0, self.nx - 1, 0, self.ny - 1, 0, self.nz - 1))
+        # per rank: the x-range of the box it owns, relative to the box (empty: hi < lo)
+        return box, [(max(lo, box[0]) - box[0], min(hi, box[1]) - box[0]) for lo, hi in self.bounds]
+
+    def upload_rhobar_j(self, fld, box=None):
+        box, bb = self._box_bounds(box)
+        lo, hi = bb[self.rank]
+        self.lat.upload_rhobar_j(np.ascontiguousarray(np.asarray(fld)[lo:hi + 1]) if hi >= lo else np.zeros((0, 4), dtype=self.lat.dtype), box)
+
+    def download_rhobar_j(self, box=None):
+        box, bb = self._box_bounds(box)
+        lo, hi = bb[self.rank]
+        local = self.lat.download_rhobar_j(box).reshape(max(hi - lo + 1, 0), box[3] - box[2] + 1, box[5] - box[4] + 1, 4)
+        return gather_x(local, [(l, max(h, l - 1)) for l, h in bb], self.device)
 
     def __getattr__(self, name):          # every set-up call is replicated on all ranks unchanged
         return getattr(self.lat, name)

@@ -347,7 +347,17 @@ def test_exchange_overlapped_with_the_interior_sweep_or_not(name, slabs, mode, m
 EXT = [n for n in CASES if n.startswith("ext_")]
 
 
-@pytest.mark.parametrize("name", ["ext_cavity_incbgk", "ext_channel_trt", "ext_open_bgk", "ext_channel_smago_q27", "ext_periodic_rlb_f32"])
+@pytest.mark.parametrize("name", EXT)
+def test_external_sweep_with_stored_fields(name, monkeypatch):
+    """The default path recomputes the moments of cells without boundary dynamics inside the sweep (they are a function of
+    the populations it gathers); PLB_B200_EXT_EXPLICIT=1 stores them after every step and reads them back, as the reference
+    does.  Both must reproduce the reference's dump."""
+    monkeypatch.setenv("PLB_B200_EXT_EXPLICIT", "1")
+    check_golden(name, run_gpu(CASES[name][0]()))
+
+
+@pytest.mark.parametrize("name", ["ext_cavity_incbgk", "ext_channel_trt", "ext_open_bgk", "ext_channel_smago_q27", "ext_periodic_rlb_f32",
+                                  "ext_interleaved"])
 @pytest.mark.parametrize("slabs", [2, 3])
 def test_external_sweep_on_slabs_is_bit_identical(name, slabs):
     """x-slabs (halo exchange between the rim sweeps and the interior sweep) give the populations and fields of one block"""
