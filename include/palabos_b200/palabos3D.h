@@ -446,6 +446,12 @@ template <typename T, template <typename U> class Descriptor>
 OnLatticeBoundaryCondition3D<T, Descriptor>* createLocalBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<T, Descriptor>(PLB_B200_BC_LOCAL); }
 template <typename T, template <typename U> class Descriptor>
 OnLatticeBoundaryCondition3D<T, Descriptor>* createZouHeBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<T, Descriptor>(PLB_B200_BC_ZOUHE); }
+/// boundaryCondition3D.hh:1170-1181: the dynamics-based managers -- in this fork both complete the plane populations inside
+/// collide() (regularized dynamics, no data processor); outer edges and corners as createLocalBoundaryCondition3D
+template <typename T, template <typename U> class Descriptor>
+OnLatticeBoundaryCondition3D<T, Descriptor>* createDynamicsBasedLocalBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<T, Descriptor>(PLB_B200_BC_DYNAMICS_LOCAL); }
+template <typename T, template <typename U> class Descriptor>
+OnLatticeBoundaryCondition3D<T, Descriptor>* createEquilibriumBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<T, Descriptor>(PLB_B200_BC_EQUILIBRIUM); }
 
 // ------------------------------------------------ the reference's plug-in (coProcessors/coProcessor3D.h)
 

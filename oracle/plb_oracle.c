@@ -140,6 +140,16 @@ static void add_proc(plbo_lattice* L, int cls, const int box[6], int a, int b, i
     if (L->prec == 8) add_proc_f64(L->d, cls, box, a, b, c); else add_proc_f32(L->s, cls, box, a, b, c);
 }
 
+/* Who completes the populations of a plane boundary cell.  Wrapped managers (createLocalBoundaryCondition3D,
+ * createZouHeBoundaryCondition3D): a WrappedLocalBoundaryFunctional3D processor at level 0, after streaming.  Dynamics-based
+ * managers (createDynamicsBasedLocalBoundaryCondition3D, createEquilibriumBoundaryCondition3D, boundaryCondition3D.hh:1170-1181:
+ * in this fork both hand out the regularized dynamics and NO functional, :712-747, :940-974): the dynamics itself at the
+ * beginning of collide() (automaticPrepareCollision, core/dynamics.hh:470-475). */
+static void plane_completion(plbo_lattice* L, int model, const int box[6]) {
+    if (model >= PLBO_BC_DYNLOCAL) { if (L->prec == 8) mark_auto_f64(L->d, box); else mark_auto_f32(L->s, box); }
+    else add_proc(L, PROC_PLANE, box, 0, 0, 0);
+}
+
 /* BoundaryConditionInstantiator3D::addVelocityBoundary boundaryInstantiator3D.h:1016-1070 with
  * WrappedRegularizedBoundaryManager3D (boundaryCondition3D.hh:825-840) or
  * WrappedZouHeBoundaryManager3D (zouHeBoundary3D.hh): composite dynamics on the cells, then the
@@ -147,15 +157,17 @@ static void add_proc(plbo_lattice* L, int cls, const int box[6], int a, int b, i
 int plbo_add_velocity_boundary(plbo_lattice* L, int model, int direction, int orientation, const int box[6]) {
     if (!box_ok(L, box)) return fail("box outside the lattice");
     if (direction < 0 || direction > 2 || (orientation != 1 && orientation != -1)) return fail("bad direction/orientation");
+    if (model < 0 || model > PLBO_BC_EQUILIBRIUM) return fail("unknown boundary condition model");
     if (!add_bc(L, model == PLBO_BC_ZOUHE ? BC_VEL_ZH : BC_VEL_REG, direction, orientation, box)) return 0;
-    add_proc(L, PROC_PLANE, box, 0, 0, 0);
+    plane_completion(L, model, box);
     return 1;
 }
 int plbo_add_pressure_boundary(plbo_lattice* L, int model, int direction, int orientation, const int box[6]) {
     if (!box_ok(L, box)) return fail("box outside the lattice");
     if (direction < 0 || direction > 2 || (orientation != 1 && orientation != -1)) return fail("bad direction/orientation");
+    if (model < 0 || model > PLBO_BC_EQUILIBRIUM) return fail("unknown boundary condition model");
     if (!add_bc(L, model == PLBO_BC_ZOUHE ? BC_RHO_ZH : BC_RHO_REG, direction, orientation, box)) return 0;
-    add_proc(L, PROC_PLANE, box, 0, 0, 0);
+    plane_completion(L, model, box);
     return 1;
 }
 /* addExternalVelocityEdge / Corner: StoreVelocityDynamics + Outer{Edge,Corner}Functional3D

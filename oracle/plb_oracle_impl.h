@@ -10,7 +10,7 @@
  */
 
 typedef struct { int type; REAL omega, cSmago, preFactor, rho; } SFX(Dyn);
-typedef struct { int kind, dir, ori; REAL u[3]; REAL rhoBar; } SFX(Bc);
+typedef struct { int kind, dir, ori; REAL u[3]; REAL rhoBar; int autoPrep; /* automaticPrepareCollision, core/dynamics.hh:470-475 */ } SFX(Bc);
 
 typedef struct {
     int q, nx, ny, nz, per[3];
@@ -887,6 +887,10 @@ static void SFX(step)(SFX(Lat)* L) {
     for (x = 0; x < nx; ++x) for (y = 0; y < ny; ++y) for (z = 0; z < nz; ++z) {
         size_t cell = CELL(L, x, y, z);
         REAL rhoBar, uSqr;
+        /* CompositeDynamics::collide core/dynamics.hh:470-475: a boundary dynamics that prepares the collision itself (the
+         * dynamics-based managers) completes the populations first */
+        if (L->bcIdx[cell] >= 0 && L->bcs[L->bcIdx[cell]].autoPrep)
+            SFX(complete_populations)(L, SFX(dyn_of)(L, cell), &L->bcs[L->bcIdx[cell]], L->f + cell * q);
         if (SFX(collide_cell)(L, SFX(dyn_of)(L, cell), L->f + cell * q, &rhoBar, &uSqr) && SFX(in_stat_box)(L, x, y, z)) {
             /* gatherStatistics core/latticeStatistics.h:36-45 (always double) */
             L->tmpSumRhoBar += (double)rhoBar;
@@ -929,6 +933,8 @@ static void SFX(ext_step)(SFX(Lat)* L) {
     REAL* tmp;
     for (x = 0; x < nx; ++x) for (y = 0; y < ny; ++y) for (z = 0; z < nz; ++z) {
         size_t cell = CELL(L, x, y, z);
+        if (L->bcIdx[cell] >= 0 && L->bcs[L->bcIdx[cell]].autoPrep)    /* CompositeDynamics::collideExternal core/dynamics.hh:478-484 */
+            SFX(complete_populations)(L, SFX(dyn_of)(L, cell), &L->bcs[L->bcIdx[cell]], L->f + cell * q);
         SFX(collide_external_cell)(L, SFX(dyn_of)(L, cell), L->f + cell * q, L->ext[4*cell], &L->ext[4*cell + 1]);
     }
     for (x = 0; x < nx; ++x) for (y = 0; y < ny; ++y) for (z = 0; z < nz; ++z) {
@@ -1000,6 +1006,14 @@ static int SFX(add_bc)(SFX(Lat)* L, int kind, int dir, int ori, const int box[6]
         L->bcIdx[cell] = L->nBc++;
     }
     return 1;
+}
+
+static void SFX(mark_auto)(SFX(Lat)* L, const int box[6]) {
+    int x, y, z;
+    for (x = box[0]; x <= box[1]; ++x) for (y = box[2]; y <= box[3]; ++y) for (z = box[4]; z <= box[5]; ++z) {
+        size_t cell = CELL(L, x, y, z);
+        if (L->bcIdx[cell] >= 0) L->bcs[L->bcIdx[cell]].autoPrep = 1;
+    }
 }
 
 static void SFX(add_proc)(SFX(Lat)* L, int cls, const int box[6], int a, int b, int c) {

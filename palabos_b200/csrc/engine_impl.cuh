@@ -49,6 +49,7 @@ class LatticeImpl : public LatticeBase {
         double* dStats = nullptr;          ///< [3 launches][4]: a step sweeps a slab in up to three launches (5.)
         int statSlots = 0;                 ///< launches of the last step
         unsigned int* dTicket = nullptr;
+        int nAuto = 0;                     ///< items [0, nAuto): plane cells that complete at collision time (never executed as a stage)
         std::vector<uint8_t> hKind;
         std::vector<BcRec> recs;
         std::vector<Group> groups;
@@ -76,6 +77,7 @@ class LatticeImpl : public LatticeBase {
     std::vector<Proc> procs_;
     bool swapped_ = false;
     bool allowFuse_ = true;                  ///< PLB_B200_EAGER_PLANES=1 in the environment turns the fusion off (A/B tests)
+    bool autoPlanes_ = false;                ///< some plane boundaries complete at collision time (dynamics-based models): those are the flagged cells, the wrapped ones run eagerly
     bool fused_ = false;                     ///< stage-0 plane items are completed by the next sweep, not by plane_stage_kernel
     bool pending_ = false;                   ///< ... and that completion is currently outstanding in storage
     bool statsOn_ = true;
@@ -258,13 +260,13 @@ public:
         check_box(box);
         check_dir_ori(dir, ori);
         add_bc(model == 1 ? BC_VEL_ZH : BC_VEL_REG, dir, ori, box);
-        add_proc(PROC_PLANE, box, 0, 0, 0);
+        add_proc(PROC_PLANE, box, auto_model(model), 0, 0);
     }
     void add_pressure_boundary(int model, int dir, int ori, const int box[6]) override {
         check_box(box);
         check_dir_ori(dir, ori);
         add_bc(model == 1 ? BC_RHO_ZH : BC_RHO_REG, dir, ori, box);
-        add_proc(PROC_PLANE, box, 0, 0, 0);
+        add_proc(PROC_PLANE, box, auto_model(model), 0, 0);
     }
     /// addExternalVelocityEdge / Corner: StoreVelocityDynamics + Outer{Edge,Corner}Functional3D
     /// (boundaryCondition3D.hh:861-877, :899-915; the Zou-He manager does the same)
@@ -777,6 +779,19 @@ private:
             if (grp.count) { sl.groups.push_back(grp); sl.dirtyBcIndex = sl.dirtySched = true; }
         }
     }
+    /// createDynamicsBasedLocalBoundaryCondition3D / createEquilibriumBoundaryCondition3D (boundaryCondition3D.hh:1170-1181;
+    /// in this fork both managers, :712-747 and :940-974, hand out the regularized dynamics WITHOUT a data processor): the
+    /// plane dynamics keep automaticPrepareCollision = true and complete the populations at the beginning of collide()
+    /// (CompositeDynamics::collide core/dynamics.hh:470-475) -- nothing runs after streaming, the cell holds raw
+    /// populations between two steps.  Here: a plane "processor" entry with a = 1, never executed; the sweep completes such
+    /// cells on load (the machinery of the lazy completion, permanently on, without the on-the-fly completion for readers).
+    int auto_model(int model) {
+        if (model < 0 || model > 3) throw PlbError("unknown boundary condition model");
+        if (model >= 2 && ext_) throw PlbError("dynamics-based boundary conditions are not available with the external-moment sweep");
+        if (model >= 2) autoPlanes_ = true;
+        return model >= 2 ? 1 : 0;
+    }
+
     void add_proc(int cls, const int box[6], int a, int b, int c) {
         Proc p;
         p.cls = cls; std::memcpy(p.box, box, sizeof p.box); p.a = a; p.b = b; p.c = c;
@@ -853,6 +868,13 @@ private:
                 };
                 if (p.cls == PROC_PLANE) {
                     if (!sl.cellToRec.count(cell)) continue;
+                    if (p.a == 1) {            // completes at collision time: no processor, no dependencies
+                        Item it;
+                        it.cell = cell; it.cls = (signed char)PROC_PLANE; it.a = 1; it.b = 0; it.c = 0;
+                        items.push_back(it);
+                        stageOf.push_back(-1);
+                        continue;
+                    }
                 } else if (p.cls == PROC_EDGE) {
                     const int d1 = (p.a + 1) % 3, d2 = (p.a + 2) % 3;
                     need_pops(neighbour(d1, -p.b), true, false);
@@ -879,24 +901,30 @@ private:
         }
         int nStages = 0;
         for (int s : stageOf) nStages = std::max(nStages, s + 1);
-        // bucket = 2*stage + (0 plane | 1 edge/corner)
-        std::vector<int> count(2 * nStages + 1, 0);
-        auto bucket = [&](size_t k) { return 2 * stageOf[k] + (items[k].cls == PROC_PLANE ? 0 : 1); };
-        for (size_t k = 0; k < items.size(); ++k) ++count[bucket(k) + 1];
-        for (int b = 0; b < 2 * nStages; ++b) count[b + 1] += count[b];
+        // bucket 0 = completes at collision time; then 1 + 2*stage + (0 plane | 1 edge/corner)
+        const int nBuckets = 1 + 2 * nStages;
+        std::vector<int> count0(nBuckets + 1, 0);
+        auto bucket = [&](size_t k) { return stageOf[k] < 0 ? 0 : 1 + 2 * stageOf[k] + (items[k].cls == PROC_PLANE ? 0 : 1); };
+        for (size_t k = 0; k < items.size(); ++k) ++count0[bucket(k) + 1];
+        for (int b = 0; b < nBuckets; ++b) count0[b + 1] += count0[b];
         std::vector<Item> sorted(items.size());
-        std::vector<int> cursor(count.begin(), count.begin() + 2 * nStages);
+        std::vector<int> cursor(count0.begin(), count0.begin() + nBuckets);
         for (size_t k = 0; k < items.size(); ++k) sorted[cursor[bucket(k)]++] = items[k];
+        sl.nAuto = count0[1];
+        // count[2*stage + (0|1)] as before; the cells the sweep completes on load: the automatic ones if the lattice has
+        // any (the wrapped ones then run eagerly), else the wrapped plane items of stage 0
+        const int* count = count0.data() + 1;
+        const int flagLo = autoPlanes_ ? 0 : (nStages > 0 ? count[0] : 0), flagHi = autoPlanes_ ? sl.nAuto : (nStages > 0 ? count[1] : 0);
         // stage-0 plane cells that do not (nearly) fill the 32-cell piece a warp of the sweep covers -- one
         // per warp on a z-face -- are listed for the sweep's list blocks together with the cells that
         // share their sector; see sweep_kernel
         std::vector<int> sparse;
-        if (nStages > 0 && count[1] > count[0]) {
+        if (flagHi > flagLo) {
             std::unordered_map<int, int> perPiece;
-            for (int k = count[0]; k < count[1]; ++k) ++perPiece[(sorted[k].cell - P_) / 32];
+            for (int k = flagLo; k < flagHi; ++k) ++perPiece[(sorted[k].cell - P_) / 32];
             const int G = PLB_SPARSE_GROUP;
             const int lo = P_, hi = (sl.nxl + 1) * P_;
-            for (int k = count[0]; k < count[1]; ++k) {
+            for (int k = flagLo; k < flagHi; ++k) {
                 const int cell = sorted[k].cell;
                 if (perPiece[(cell - P_) / 32] >= 16) continue;
                 const int g0 = cell / G * G;
@@ -1020,7 +1048,7 @@ private:
         if (reflag) {
             // fuse when every plane item is in stage 0, i.e. no processor of the reference's sequence
             // reads or writes a plane cell before its completion runs (then "complete on load" == eager)
-            fused_ = allowFuse_;
+            fused_ = allowFuse_ && !autoPlanes_;
             for (Slab& sl : slabs_)
                 for (size_t s = 1; s + 1 < sl.stageOffsets.size(); ++s)
                     if (sl.stageSplit[s] > sl.stageOffsets[s]) fused_ = false;
@@ -1030,10 +1058,11 @@ private:
                     PLB_CUDA(cudaStreamSynchronize(stream_));
                 }
                 sl.kindUnflagged = false;
-                if (!fused_ || sl.stageOffsets.size() < 2) continue;
-                const int n = sl.stageSplit[0] - sl.stageOffsets[0];
+                int first = 0, n = 0;
+                if (autoPlanes_) { first = 0; n = sl.nAuto; }
+                else if (fused_ && sl.stageOffsets.size() >= 2) { first = sl.stageOffsets[0]; n = sl.stageSplit[0] - sl.stageOffsets[0]; }
                 if (n > 0) {
-                    flag_plane_cells_kernel<<<(n + 255) / 256, 256, 0, stream_>>>(sl.dItems + sl.stageOffsets[0], n, sl.dKind);
+                    flag_plane_cells_kernel<<<(n + 255) / 256, 256, 0, stream_>>>(sl.dItems + first, n, sl.dKind);
                     launched();
                     if (sl.nSparse > 0) {
                         flag_sparse_cells_kernel<<<(sl.nSparse + 255) / 256, 256, 0, stream_>>>(sl.dSparse, sl.nSparse, sl.dKind);
@@ -1092,7 +1121,7 @@ private:
         SweepArgs<T> a;
         a.F = sl.F; a.kind = sl.dKind; a.dyns = dDyns_; a.g = geo(sl);
         a.bcIdx = sl.dBcIdx; a.bcs = sl.dBcs;
-        a.applyPlanes = (pending_ && sl.stageOffsets.size() >= 2 && sl.stageSplit[0] > sl.stageOffsets[0]) ? 1 : 0;
+        a.applyPlanes = ((pending_ && sl.stageOffsets.size() >= 2 && sl.stageSplit[0] > sl.stageOffsets[0]) || sl.nAuto > 0) ? 1 : 0;
         a.cellBegin = X0 * P_; a.cellEnd = (X1 + 1) * P_;
         a.sparseCells = sl.dSparse; a.nSparse = 0; a.nListBlocks = 0;
         if (a.applyPlanes && sl.nSparse > 0) {

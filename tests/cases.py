@@ -277,6 +277,35 @@ def ext_interleaved(nx=10, ny=8, nz=9):
     return sc.stats().dump("f_end").dump_rhobar_j("rj_end").dump_rho_u("rho_u_end")
 
 
+def inlet_outlet_mixed(nx, ny, nz, steps):
+    """Wrapped (processor-completed) and dynamics-based (collision-time) plane boundaries in one lattice: a regularized
+    velocity inlet completed by its processor, a dynamics-based pressure outlet, dynamics-based side walls with their outer
+    edges; BounceBack where nothing else sits."""
+    sc = Scenario(19, "f64", nx, ny, nz, "BGK", 1.55)
+    sc.bc_vel("local", 0, -1, (0, 0, 1, ny - 2, 1, nz - 2))
+    sc.bc_pres("dynlocal", 0, +1, (nx - 1, nx - 1, 1, ny - 2, 1, nz - 2))
+    sc.bc_vel("dynlocal", 1, -1, (1, nx - 2, 0, 0, 1, nz - 2))
+    sc.bc_vel("equilibrium", 1, +1, (1, nx - 2, ny - 1, ny - 1, 1, nz - 2))
+    sc.bc_vel("zouhe", 2, -1, (1, nx - 2, 1, ny - 2, 0, 0))
+    sc.bc_vel("dynlocal", 2, +1, (1, nx - 2, 1, ny - 2, nz - 1, nz - 1))
+    sc.bc_edge("dynlocal", 0, -1, -1, (1, nx - 2, 0, 0, 0, 0))
+    sc.bc_edge("local", 0, +1, +1, (1, nx - 2, ny - 1, ny - 1, nz - 1, nz - 1))
+    for wall in ((0, 0, 0, ny - 1, 0, 0), (0, 0, 0, ny - 1, nz - 1, nz - 1), (0, 0, 0, 0, 0, nz - 1), (0, 0, ny - 1, ny - 1, 0, nz - 1),
+                 (nx - 1, nx - 1, 0, ny - 1, 0, 0), (nx - 1, nx - 1, 0, ny - 1, nz - 1, nz - 1), (nx - 1, nx - 1, 0, 0, 0, nz - 1),
+                 (nx - 1, nx - 1, ny - 1, ny - 1, 0, nz - 1), (1, nx - 2, 0, 0, nz - 1, nz - 1), (1, nx - 2, ny - 1, ny - 1, 0, 0)):
+        sc.dynamics(wall, "BB", 1.0)
+    sc.set_velocity(sc.box, (0, 0, 0))
+    sc.set_velocity((0, 0, 1, ny - 2, 1, nz - 2), (0.02, 0.001, -0.002))
+    sc.set_density(sc.box, 1.005)
+    sc.init_eq(sc.box, 1.0, (0.01, 0, 0))
+    sc.initialize()
+    sc.dump("f_init")
+    sc.run(steps // 2).stats()
+    sc.set_velocity((0, 0, 1, ny - 2, 1, nz - 2), (0.025, 0.0, 0.001))
+    sc.run(steps - steps // 2).stats().dump("f_end").dump_rho_u("rho_u_end")
+    return sc
+
+
 # name -> (builder, how to store the reference outcome: "full" dumps, or "probe" = sha256 + sampled cells)
 CASES = {
     # configs[0]-style cavity, all dynamics on the path
@@ -332,6 +361,14 @@ CASES = {
     "ext_periodic_trt_q27":     (lambda: ext_periodic(8, 7, 9, 30, "TRT", 1.5, q=27), "full"),
     "ext_periodic_rlb_f32":     (lambda: ext_periodic(8, 7, 9, 30, "RLB", 1.5, prec="f32"), "full"),
     "ext_interleaved":          (lambda: ext_interleaved(), "full"),
+    # dynamics-based boundary managers (createDynamicsBasedLocalBoundaryCondition3D / createEquilibriumBoundaryCondition3D): the plane
+    # dynamics completes the populations at collision time, nothing runs after streaming
+    "cavity_dynlocal_10x9x8":   (lambda: cavity(10, 9, 8, 40, model="dynlocal", every=20), "full"),
+    "cavity_equilibrium_rlb":   (lambda: cavity(9, 8, 10, 30, dyn="RLB", model="equilibrium"), "full"),
+    "cavity_dynlocal_q27_f32":  (lambda: cavity(8, 8, 9, 30, q=27, prec="f32", model="dynlocal"), "full"),
+    "cavity_dynlocal_incbgk":   (lambda: cavity(8, 9, 10, 30, dyn="INCBGK", model="dynlocal"), "full"),
+    "obstacle_dynlocal":        (lambda: obstacle(20, 10, 9, 40, omega=1.4, model="dynlocal"), "full"),
+    "inlet_outlet_mixed_models": (lambda: inlet_outlet_mixed(12, 9, 8, 40), "full"),
     # edge cases
     "mixed_omega_11x8x9":       (lambda: mixed_omega(11, 8, 9, 40), "full"),
     "inlet_outlet_local":       (lambda: inlet_outlet_local(12, 9, 8, 40), "full"),

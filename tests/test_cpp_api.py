@@ -145,3 +145,18 @@ def test_external_rhoj3d_cpp_matches_the_unmodified_reference():
     assert re.search(r"Av\. energy (\S+)", out).group(1) == "%e" % gold["stats"][-1][4]
     assert re.search(r"Av\. density (\S+)", out).group(1) == "%e" % gold["stats"][-1][5]
     assert "iterations 40" in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["dynlocal", "equilibrium"])
+def test_cavity3d_cpp_dynamics_based_boundary_managers(model):
+    """createDynamicsBasedLocalBoundaryCondition3D / createEquilibriumBoundaryCondition3D of the C++ mirror against the dump of
+    the unmodified reference (in this fork the two managers are the same for planes, outer edges and corners)"""
+    nx, ny, nz = 10, 9, 8
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "cavity_dynlocal_10x9x8.npz"))
+    with tempfile.TemporaryDirectory() as tmp:
+        dump = os.path.join(tmp, "f.bin")
+        subprocess.run([_exe("cavity3d"), str(nx), str(ny), str(nz), "40", dump], check=True, capture_output=True, text=True,
+                       env=dict(os.environ, CAVITY3D_BC=model))
+        got = np.fromfile(dump, dtype=np.float64).reshape(nx, ny, nz, 19)
+    assert np.array_equal(got, gold["f_end_full"])

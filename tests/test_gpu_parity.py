@@ -103,6 +103,9 @@ SLAB_CASES = {
     "thin_4x5x3": 2,
     "cavity_incbgk_10x9x8": 3,
     "obstacle_incbgk_zouhe": 4,
+    "cavity_dynlocal_10x9x8": 3,
+    "obstacle_dynlocal": 4,
+    "inlet_outlet_mixed_models": 2,
 }
 
 
@@ -403,3 +406,38 @@ def test_external_sweep_without_touching_the_fields_equals_the_plain_sweep_in_th
     inner = (steps, nx - 1 - steps, steps, ny - 1 - steps, steps, nz - 1 - steps)
     assert np.array_equal(a.download(inner), b.download(inner))
     a.close(); b.close()
+
+
+def test_dynamics_based_planes_hold_raw_populations_between_steps():
+    """With the dynamics-based managers nothing runs after streaming: what download() returns for a plane cell is the raw
+    post-stream state, and the completion happens at collision time -- checked against the oracle cell by cell at every
+    step, with a change of the lid velocity on the way."""
+    import palabos_b200 as pb
+    from scenario import OracleEngine
+    nx, ny, nz = 9, 8, 7
+    engines = [pb.Lattice(19, "f64", nx, ny, nz, "BGK", 1.3), OracleEngine(19, "f64", nx, ny, nz, "BGK", 1.3)]
+    for e in engines:
+        box = (0, nx - 1, 0, ny - 1, 0, nz - 1)
+        e.set_velocity_condition_on_block_boundaries("dynlocal", box, box)
+        e.set_boundary_velocity(box, (0, 0, 0))
+        e.set_boundary_velocity((1, nx - 2, 1, ny - 2, nz - 1, nz - 1), (0.03, 0.01, 0))
+        e.initialize_at_equilibrium(box, 1.0, (0, 0, 0))
+        e.initialize()
+    for step in range(6):
+        for e in engines:
+            e.collide_and_stream(1)
+        assert np.array_equal(engines[0].download(), engines[1].download()), step
+        assert np.array_equal(engines[0].compute_density_velocity(), engines[1].compute_density_velocity()), step
+        if step == 2:
+            for e in engines:        # a new lid velocity takes effect at the next collision
+                e.set_boundary_velocity((1, nx - 2, 1, ny - 2, nz - 1, nz - 1), (0.02, -0.01, 0))
+    for e in engines:
+        e.close()
+
+
+def test_dynamics_based_model_is_refused_with_the_external_sweep():
+    import palabos_b200 as pb
+    env = pb.Lattice(19, "f64", 6, 5, 4, "BGK", 1.2, enveloped_periodic=(0, 0, 0))
+    with pytest.raises(pb.PlbError):
+        env.add_velocity_boundary("dynlocal", 0, -1, (0, 0, 1, 3, 1, 2))
+    env.close()
