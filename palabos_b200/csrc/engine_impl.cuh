@@ -84,7 +84,8 @@ class LatticeImpl : public LatticeBase {
     bool ext_ = false;                       ///< the lattice is stepped by ExternalRhoJcollideAndStream3D + BoxRhoBarJfunctional3D
     int bulk_[6] = {0, 0, 0, 0, 0, 0};       ///< ... whose level-3 domain is this box (the user's lattice; the rest is envelope)
     bool extImplied_ = false;                ///< the fields are what BoxRhoBarJfunctional3D makes of the CURRENT populations: the fused sweep may recompute them
-    bool extComplete_ = true;                ///< the fields are stored for every cell (false: only for cells with boundary dynamics, the rest is implied)
+    bool extComplete_ = true;                ///< the fields are stored for every cell (false: implied by the populations and the boundary records)
+    bool extBcStored_ = true;                ///< ... at least for the cells with boundary dynamics (stored under the records they were computed with)
     bool extFuse_ = true;                    ///< PLB_B200_EXT_EXPLICIT=1 in the environment: always store and re-read the fields (A/B tests)
     bool anySetup_ = false;
     bool stepped_ = false;
@@ -259,14 +260,16 @@ public:
     void add_velocity_boundary(int model, int dir, int ori, const int box[6]) override {
         check_box(box);
         check_dir_ori(dir, ori);
+        const int autoPrep = auto_model(model);
         add_bc(model == 1 ? BC_VEL_ZH : BC_VEL_REG, dir, ori, box);
-        add_proc(PROC_PLANE, box, auto_model(model), 0, 0);
+        add_proc(PROC_PLANE, box, autoPrep, 0, 0);
     }
     void add_pressure_boundary(int model, int dir, int ori, const int box[6]) override {
         check_box(box);
         check_dir_ori(dir, ori);
+        const int autoPrep = auto_model(model);
         add_bc(model == 1 ? BC_RHO_ZH : BC_RHO_REG, dir, ori, box);
-        add_proc(PROC_PLANE, box, auto_model(model), 0, 0);
+        add_proc(PROC_PLANE, box, autoPrep, 0, 0);
     }
     /// addExternalVelocityEdge / Corner: StoreVelocityDynamics + Outer{Edge,Corner}Functional3D
     /// (boundaryCondition3D.hh:861-877, :899-915; the Zou-He manager does the same)
@@ -405,8 +408,8 @@ public:
         }
         std::memcpy(bulk_, bulk, sizeof bulk_);
         ext_ = true;
-        extImplied_ = false; extComplete_ = true;   // zero fields, as generateMultiScalarField / generateMultiTensorField leave them
-        allowFuse_ = false;                    // BoxRhoBarJ reads the completed populations right after the processors
+        extImplied_ = false; extComplete_ = true; extBcStored_ = true;   // zero fields, as generateMultiScalarField / generateMultiTensorField leave them
+        if (!extFuse_) allowFuse_ = false;     // the stored-fields path reads completed populations right after the processors
         for (Slab& sl : slabs_) sl.dirtySched = true;
     }
 
@@ -428,7 +431,7 @@ public:
         if (!whole) ext_complete();            // the rest of the fields keeps its values
         rhobar_j_box(b);
         if (whole) extImplied_ = true;         // (a part: implied stays what it was -- the new values ARE the implied ones)
-        extComplete_ = true;
+        extComplete_ = true; extBcStored_ = true;
     }
 
     /// BoxRhoBarJ of the cells of a box, stored
@@ -444,8 +447,9 @@ public:
     void ext_complete() {
         if (!ext_ || extComplete_) return;
         sync_setup();
+        if (extComplete_) return;              // sync_setup had to store them itself (set-up changes were outstanding)
         rhobar_j_box(bulk_);
-        extComplete_ = true;
+        extComplete_ = true; extBcStored_ = true;
     }
     /// the populations, the dynamics or the boundary set-up are about to change under the fields: from now on the fields are
     /// data of their own (the reference's fields keep their values until the next level-3 pass)
@@ -539,6 +543,7 @@ public:
         if (desc_.nRanks > 1 && !comm_) throw PlbError("plb_b200_comm_init must be called before stepping a multi-rank lattice");
         sync_setup();
         for (int s = 0; s < n; ++s) {
+            if (ext && !(extImplied_ && extFuse_)) materialize();   // the stored-fields sweep has no completion on load
             // measured at 512^3 per GPU on 2 B200s: 7.18 ms per step overlapped against 7.26 (the split costs 0.03 ms of sweep time)
             const bool overlap = G_ > 1 && overlap_ != 0;
             if (!overlap) {
@@ -582,15 +587,10 @@ public:
                 // level 3: BoxRhoBarJfunctional3D on the whole lattice.  Stored only for the cells with boundary dynamics; for the
                 // others the next sweep recomputes it from the populations it gathers (launch_sweep), or ext_complete() stores it
                 if (extFuse_) {
-                    for (Slab& sl : slabs_) {
-                        if (sl.nBcCells == 0) continue;
-                        rhobar_j_list_kernel<T, Q><<<(sl.nBcCells + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.dBcCells, sl.nBcCells, sl.dExt, sl.cellsStore);
-                        launched();
-                    }
-                    extComplete_ = false;
+                    extComplete_ = false; extBcStored_ = false;     // all of it implied: nothing to run
                 } else {
                     rhobar_j_box(bulk_);
-                    extComplete_ = true;
+                    extComplete_ = true; extBcStored_ = true;
                 }
                 extImplied_ = true;
             } else {
@@ -985,6 +985,23 @@ private:
         bool reflag = false;
         bool structural = false;               // (external-moment sweep) which cells read their moments from the fields may have changed
         for (Slab& sl : slabs_) structural = structural || sl.dirtyKind || sl.dirtyBcIndex || sl.dirtySched;
+        if (ext_ && !extComplete_) {
+            // the implied moments are functions of the device state about to be replaced: store them first -- everything when
+            // dynamics / boundary cells change (the fields are then data of their own), the boundary cells when only
+            // values of their records do
+            if (structural) {
+                rhobar_j_box(bulk_);
+                extComplete_ = true; extBcStored_ = true; extImplied_ = false;
+            } else if (!extBcStored_) {
+                for (Slab& sl : slabs_) {
+                    if (sl.nBcCells == 0) continue;
+                    rhobar_j_list_kernel<T, Q><<<(sl.nBcCells + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.dBcCells, sl.nBcCells, sl.dExt, sl.cellsStore);
+                    launched();
+                }
+                extBcStored_ = true;
+            }
+        }
+        if (ext_ && structural) reflag = true;
         if (dirtyDyns_) {
             PLB_CUDA(cudaMemcpyAsync(dDyns_, dyns_.data(), dyns_.size() * sizeof(Dyn<T>), cudaMemcpyHostToDevice, stream_));
             PLB_CUDA(cudaStreamSynchronize(stream_));
@@ -1071,11 +1088,11 @@ private:
                 }
             }
         }
-        if (ext_ && structural) {
-            // KIND_PLANE means something else in this mode (plane completion is never fused here): "moments from the fields"
+        if (ext_ && (structural || reflag)) {
+            // KIND_PLANE means more in this mode: "boundary dynamics on top, or envelope layer" -- the cells whose moments are
+            // not those of a bulk cell (the block above has just restored the kind bytes and flagged the fused plane cells,
+            // a subset of these; completing a cell without a plane record is a no-op)
             for (Slab& sl : slabs_) {
-                PLB_CUDA(cudaMemcpyAsync(sl.dKind, sl.hKind.data(), (size_t)sl.cellsStore, cudaMemcpyHostToDevice, stream_));
-                PLB_CUDA(cudaStreamSynchronize(stream_));
                 BoxL lb;
                 if (!local_box(sl, bulk_, lb)) { lb.X0 = 1; lb.X1 = 0; lb.y0 = lb.z0 = 0; lb.y1 = lb.z1 = -1; }
                 flag_ext_cells_kernel<<<(unsigned)((sl.cellsStore + 255) / 256), 256, 0, stream_>>>(sl.dKind, sl.dBcIdx, geo(sl), lb, (int)sl.cellsStore);
@@ -1132,14 +1149,16 @@ private:
         a.omega = dyns_[0].omega; a.preFactor = dyns_[0].preFactor;
         a.gatherStats = statsOn_ ? 1 : 0;
         a.partials = nullptr; a.ticket = sl.dTicket; a.statsOut = sl.dStats + 4 * slot;
-        a.ext = sl.dExt; a.extStride = sl.cellsStore;
+        a.ext = sl.dExt; a.extStride = sl.cellsStore; a.extBcFromFields = 1;
         if (ext_) {
             // the statistics of this mode are never evaluated by the reference's loop (executeInternalProcessors + incrementTime)
             a.gatherStats = 0;
+            a.extBcFromFields = extBcStored_ ? 1 : 0;
             if (extImplied_ && extFuse_) {
-                if (swapped_) launch_sweep_with<DYN_EXTERNAL_FUSED, true, true, false>(sl, a, 7);
-                else launch_sweep_with<DYN_EXTERNAL_FUSED, true, false, false>(sl, a, 7);
+                if (swapped_) launch_sweep_as<DYN_EXTERNAL_FUSED, true, true>(sl, a, 7);
+                else launch_sweep_as<DYN_EXTERNAL_FUSED, true, false>(sl, a, 7);
             } else {
+                a.applyPlanes = 0;
                 if (swapped_) launch_sweep_with<DYN_EXTERNAL, true, true, false>(sl, a, 6);
                 else launch_sweep_with<DYN_EXTERNAL, true, false, false>(sl, a, 6);
             }

@@ -264,6 +264,7 @@ struct SweepArgs {
     double* statsOut;         ///< [4] sum rhoBar, sum uSqr, max uSqr, cell count of this launch
     const T* ext;             ///< MAIN == DYN_EXTERNAL: rhoBar [cells] followed by j_x, j_y, j_z [cells] each (extStride apart)
     long long extStride;
+    int extBcFromFields;      ///< DYN_EXTERNAL_FUSED: the moments of cells with boundary dynamics are stored in the fields (else implied)
 };
 
 /// Deterministic block reduction of the BlockStatistics accumulators (core/blockStatistics.cpp:205-229:
@@ -348,6 +349,15 @@ __device__ __noinline__ void complete_pending(int baseType, const Bc<T>* __restr
     complete_by_face<T, Q>(baseType, bcs[bi], f);
 }
 
+/// Dynamics::computeRhoBarJ of a cell with boundary dynamics from its (completed) populations and its record; out of line
+/// like complete_pending, for the same reason
+template <class T, int Q>
+__device__ __noinline__ void boundary_moments(const Dyn<T>* __restrict__ dyns, int k, const Bc<T>* __restrict__ bcs, int bi, const T* f, T* rhoBar_j) {
+    T rb, j[3];
+    LB<T, Q>::cell_rhoBar_j(dyns[k], true, bcs[bi], f, rb, j);
+    rhoBar_j[0] = rb; rhoBar_j[1] = j[0]; rhoBar_j[2] = j[1]; rhoBar_j[3] = j[2];
+}
+
 /// The fused collide-and-stream sweep (BlockLattice3D::collideAndStream, atomicBlock/blockLattice3D.hh:253-312,
 /// with Cell::collide -> Dynamics::collide inlined as a device functor and gatherStatistics,
 /// core/latticeStatistics.h:36-45, reduced per block).
@@ -400,16 +410,28 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
         if constexpr (MAIN == DYN_EXTERNAL || MAIN == DYN_EXTERNAL_FUSED) {
             // ExternalRhoJcollideAndStream3D (basicDynamics/dynamicsProcessor3D.hh:41-76): rhoBar and j come from the fields.
             // DYN_EXTERNAL_FUSED: nobody has touched the fields since BoxRhoBarJfunctional3D filled them at the end of the
-            // previous step, so for a cell without boundary dynamics they hold Dynamics::computeRhoBarJ of the very
-            // populations this thread has just gathered -- recomputed here instead of stored and re-read (the moment
-            // pass and 64 B per cell of traffic go away).  Cells flagged KIND_PLANE (boundary dynamics: their moments follow
-            // the boundary formulas; envelope layer: zero for ever) still read the fields.
+            // previous step, so they hold Dynamics::computeRhoBarJ of the very populations this thread has just gathered
+            // (and, for a plane boundary cell, completed) -- recomputed here instead of stored and re-read: the moment
+            // pass and 64 B per cell of traffic go away.  Cells flagged KIND_PLANE in this mode: boundary dynamics on top
+            // (moments by the boundary formulas, from the record) or envelope layer (no record: zero for ever); when
+            // the boundary records have changed since, their moments were stored under the old values (extBcFromFields).
             static_assert(GENERIC, "the external-moment sweep reads the dynamics table");
             const Dyn<T> d = a.dyns[k];
             T rb, j[3];
-            if (MAIN == DYN_EXTERNAL || (kRaw & KIND_PLANE)) {
+            if (MAIN == DYN_EXTERNAL || ((kRaw & KIND_PLANE) && a.extBcFromFields)) {
                 rb = a.ext[c];
                 j[0] = a.ext[a.extStride + c]; j[1] = a.ext[2 * a.extStride + c]; j[2] = a.ext[3 * a.extStride + c];
+            } else if (kRaw & KIND_PLANE) {
+                const int bi = a.bcIdx[c];
+                if (bi < 0) {
+                    rb = (T)0; j[0] = j[1] = j[2] = (T)0;
+                } else {
+                    T tmp[Q], m[4];
+#pragma unroll
+                    for (int i = 0; i < Q; ++i) tmp[i] = f[i];
+                    boundary_moments<T, Q>(a.dyns, k, a.bcs, bi, tmp, m);
+                    rb = m[0]; j[0] = m[1]; j[1] = m[2]; j[2] = m[3];
+                }
             } else {
                 Bc<T> none;
                 none.kind = -1; none.dir = 0; none.ori = 1; none.u[0] = none.u[1] = none.u[2] = (T)0; none.rhoBar = (T)0;

@@ -32,7 +32,8 @@ void launch_sweep_kernel(int grid, cudaStream_t stream, const SweepArgs<T>& a) {
     template void launch_sweep_kernel<T, Q, DYN_BGK, true, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);     \
     template void launch_sweep_kernel<T, Q, DYN_BGK, true, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);      \
     template void launch_sweep_kernel<T, Q, DYN_EXTERNAL, true, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);     \
-    template void launch_sweep_kernel<T, Q, DYN_EXTERNAL_FUSED, true, ODD, false>(int, cudaStream_t, const SweepArgs<T>&);
+    template void launch_sweep_kernel<T, Q, DYN_EXTERNAL_FUSED, true, ODD, false>(int, cudaStream_t, const SweepArgs<T>&); \
+    template void launch_sweep_kernel<T, Q, DYN_EXTERNAL_FUSED, true, ODD, true>(int, cudaStream_t, const SweepArgs<T>&);
 #endif
 
 }  // namespace plb200

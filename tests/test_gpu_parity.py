@@ -359,6 +359,15 @@ def test_external_sweep_with_stored_fields(name, monkeypatch):
     check_golden(name, run_gpu(CASES[name][0]()))
 
 
+@pytest.mark.parametrize("name", EXT)
+def test_external_sweep_with_eager_plane_completion(name, monkeypatch):
+    """By default the plane boundaries of an enveloped lattice are completed by the next sweep on load (as in the plain
+    path) and the moments of boundary cells are recomputed from the completed populations inside the sweep;
+    PLB_B200_EAGER_PLANES=1 completes them in a pass of their own after the step."""
+    monkeypatch.setenv("PLB_B200_EAGER_PLANES", "1")
+    check_golden(name, run_gpu(CASES[name][0]()))
+
+
 @pytest.mark.parametrize("name", ["ext_cavity_incbgk", "ext_channel_trt", "ext_open_bgk", "ext_channel_smago_q27", "ext_periodic_rlb_f32",
                                   "ext_interleaved"])
 @pytest.mark.parametrize("slabs", [2, 3])
