@@ -23,11 +23,13 @@ int run(plint nx, plint ny, plint nz, plint steps, const char* dump) {
     const T tau = 3. * nu + 0.5;
 
     MultiBlockLattice3D<T, DESCRIPTOR> lattice(nx, ny, nz, new BGKdynamics<T, DESCRIPTOR>(1. / tau));
-    // CAVITY3D_BC=dynlocal | equilibrium: the dynamics-based managers (populations completed inside collide())
+    // CAVITY3D_BC=dynlocal | equilibrium: the dynamics-based managers (populations completed inside collide()); interp: the
+    // finite-difference manager of the reference's cavity3d showcase
     const std::string model = std::getenv("CAVITY3D_BC") ? std::getenv("CAVITY3D_BC") : "local";
     OnLatticeBoundaryCondition3D<T, DESCRIPTOR>* bc =
         model == "dynlocal" ? createDynamicsBasedLocalBoundaryCondition3D<T, DESCRIPTOR>()
-                            : (model == "equilibrium" ? createEquilibriumBoundaryCondition3D<T, DESCRIPTOR>() : createLocalBoundaryCondition3D<T, DESCRIPTOR>());
+                            : (model == "equilibrium" ? createEquilibriumBoundaryCondition3D<T, DESCRIPTOR>()
+                               : (model == "interp" ? createInterpBoundaryCondition3D<T, DESCRIPTOR>() : createLocalBoundaryCondition3D<T, DESCRIPTOR>()));
     bc->setVelocityConditionOnBlockBoundaries(lattice);
     setBoundaryVelocity(lattice, lattice.getBoundingBox(), Array<T, 3>(0., 0., 0.));
     setBoundaryVelocity(lattice, Box3D(1, nx - 2, 1, ny - 2, nz - 1, nz - 1), Array<T, 3>(uMax, 0., 0.));

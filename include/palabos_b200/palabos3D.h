@@ -450,6 +450,9 @@ OnLatticeBoundaryCondition3D<T, Descriptor>* createZouHeBoundaryCondition3D() { 
 /// collide() (regularized dynamics, no data processor); outer edges and corners as createLocalBoundaryCondition3D
 template <typename T, template <typename U> class Descriptor>
 OnLatticeBoundaryCondition3D<T, Descriptor>* createDynamicsBasedLocalBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<T, Descriptor>(PLB_B200_BC_DYNAMICS_LOCAL); }
+/// boundaryCondition3D.hh:1184-1188: Dirichlet dynamics + the finite-difference plane processor (Skordos)
+template <typename T, template <typename U> class Descriptor>
+OnLatticeBoundaryCondition3D<T, Descriptor>* createInterpBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<T, Descriptor>(PLB_B200_BC_INTERP); }
 template <typename T, template <typename U> class Descriptor>
 OnLatticeBoundaryCondition3D<T, Descriptor>* createEquilibriumBoundaryCondition3D() { return new OnLatticeBoundaryCondition3D<T, Descriptor>(PLB_B200_BC_EQUILIBRIUM); }
 

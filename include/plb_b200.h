@@ -41,7 +41,10 @@ enum { PLB_B200_DYN_BGK = 0, PLB_B200_DYN_RLB = 1, PLB_B200_DYN_TRT = 2, PLB_B20
 /* Boundary-condition families: LOCAL = createLocalBoundaryCondition3D (regularized,
  * boundaryCondition/boundaryCondition3D.hh:1162-1167), ZOUHE = createZouHeBoundaryCondition3D
  * (boundaryCondition/zouHeBoundary3D.hh:338-350). */
-enum { PLB_B200_BC_LOCAL = 0, PLB_B200_BC_ZOUHE = 1, PLB_B200_BC_DYNAMICS_LOCAL = 2, PLB_B200_BC_EQUILIBRIUM = 3 };
+enum { PLB_B200_BC_LOCAL = 0, PLB_B200_BC_ZOUHE = 1, PLB_B200_BC_DYNAMICS_LOCAL = 2, PLB_B200_BC_EQUILIBRIUM = 3, PLB_B200_BC_INTERP = 4 };
+/* INTERP = createInterpBoundaryCondition3D (boundaryCondition3D.hh:1049-1085, :1184-1188): Velocity / DensityDirichletBoundaryDynamics
+ * on the plane cells + PlaneFdBoundaryFunctional3D (finiteDifferenceBoundaryProcessor3D.hh:68-117: velocity gradients by finite
+ * differences of the neighbours' velocities, then regularize); outer edges and corners are those of LOCAL. */
 /* DYNAMICS_LOCAL = createDynamicsBasedLocalBoundaryCondition3D, EQUILIBRIUM = createEquilibriumBoundaryCondition3D
  * (boundaryCondition3D.hh:1170-1181).  In this fork both managers (:712-747, :940-974) put the regularized dynamics on the plane
  * cells WITHOUT a data processor: the dynamics completes the populations at the beginning of collide()

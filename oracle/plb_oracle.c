@@ -15,7 +15,7 @@
 
 #define MAX_DYN 128
 enum { BC_VEL_REG = 0, BC_RHO_REG = 1, BC_VEL_ZH = 2, BC_RHO_ZH = 3, BC_STORE_VEL = 4 };
-enum { PROC_PLANE = 0, PROC_EDGE = 1, PROC_CORNER = 2 };
+enum { PROC_PLANE = 0, PROC_EDGE = 1, PROC_CORNER = 2, PROC_PLANE_FD = 3 };
 typedef struct { int cls; int box[6]; int a, b, c; } Proc;
 
 /* latticeBoltzmann/nearestNeighborLattices3D.hh:165-177 (D3Q19 c), :225-239 (D3Q27 c) */
@@ -145,7 +145,9 @@ static void add_proc(plbo_lattice* L, int cls, const int box[6], int a, int b, i
  * managers (createDynamicsBasedLocalBoundaryCondition3D, createEquilibriumBoundaryCondition3D, boundaryCondition3D.hh:1170-1181:
  * in this fork both hand out the regularized dynamics and NO functional, :712-747, :940-974): the dynamics itself at the
  * beginning of collide() (automaticPrepareCollision, core/dynamics.hh:470-475). */
-static void plane_completion(plbo_lattice* L, int model, const int box[6]) {
+static void plane_completion(plbo_lattice* L, int model, int direction, int orientation, const int box[6]) {
+    /* createInterpBoundaryCondition3D (boundaryCondition3D.hh:1049-1085): plain Dirichlet dynamics + PlaneFdBoundaryFunctional3D */
+    if (model == PLBO_BC_INTERP) { add_proc(L, PROC_PLANE_FD, box, direction, orientation, 0); return; }
     if (model >= PLBO_BC_DYNLOCAL) { if (L->prec == 8) mark_auto_f64(L->d, box); else mark_auto_f32(L->s, box); }
     else add_proc(L, PROC_PLANE, box, 0, 0, 0);
 }
@@ -157,17 +159,17 @@ static void plane_completion(plbo_lattice* L, int model, const int box[6]) {
 int plbo_add_velocity_boundary(plbo_lattice* L, int model, int direction, int orientation, const int box[6]) {
     if (!box_ok(L, box)) return fail("box outside the lattice");
     if (direction < 0 || direction > 2 || (orientation != 1 && orientation != -1)) return fail("bad direction/orientation");
-    if (model < 0 || model > PLBO_BC_EQUILIBRIUM) return fail("unknown boundary condition model");
+    if (model < 0 || model > PLBO_BC_INTERP) return fail("unknown boundary condition model");
     if (!add_bc(L, model == PLBO_BC_ZOUHE ? BC_VEL_ZH : BC_VEL_REG, direction, orientation, box)) return 0;
-    plane_completion(L, model, box);
+    plane_completion(L, model, direction, orientation, box);
     return 1;
 }
 int plbo_add_pressure_boundary(plbo_lattice* L, int model, int direction, int orientation, const int box[6]) {
     if (!box_ok(L, box)) return fail("box outside the lattice");
     if (direction < 0 || direction > 2 || (orientation != 1 && orientation != -1)) return fail("bad direction/orientation");
-    if (model < 0 || model > PLBO_BC_EQUILIBRIUM) return fail("unknown boundary condition model");
+    if (model < 0 || model > PLBO_BC_INTERP) return fail("unknown boundary condition model");
     if (!add_bc(L, model == PLBO_BC_ZOUHE ? BC_RHO_ZH : BC_RHO_REG, direction, orientation, box)) return 0;
-    plane_completion(L, model, box);
+    plane_completion(L, model, direction, orientation, box);
     return 1;
 }
 /* addExternalVelocityEdge / Corner: StoreVelocityDynamics + Outer{Edge,Corner}Functional3D

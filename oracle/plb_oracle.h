@@ -24,7 +24,7 @@ extern "C" {
 /* numeric ids shared with include/plb_b200.h */
 enum { PLBO_DYN_BGK = 0, PLBO_DYN_RLB = 1, PLBO_DYN_TRT = 2, PLBO_DYN_SMAGO = 3,
        PLBO_DYN_BOUNCEBACK = 4, PLBO_DYN_NODYNAMICS = 5, PLBO_DYN_INCBGK = 6 };
-enum { PLBO_BC_LOCAL = 0, PLBO_BC_ZOUHE = 1, PLBO_BC_DYNLOCAL = 2, PLBO_BC_EQUILIBRIUM = 3 };
+enum { PLBO_BC_LOCAL = 0, PLBO_BC_ZOUHE = 1, PLBO_BC_DYNLOCAL = 2, PLBO_BC_EQUILIBRIUM = 3, PLBO_BC_INTERP = 4 };
 
 typedef struct plbo_lattice plbo_lattice;
 

@@ -828,6 +828,21 @@ static void SFX(edge_cell)(SFX(Lat)* L, int x, int y, int z, int plane, int n1, 
     SFX(fd_regularize)(L, CELL(L, x, y, z), rho, dA_uB);
 }
 
+/* PlaneFdBoundaryFunctional3D::processCell finiteDifferenceBoundaryProcessor3D.hh:68-117 (createInterpBoundaryCondition3D,
+ * boundaryCondition3D.hh:1049-1085: Velocity/DensityDirichletBoundaryDynamics + this processor): density and velocity of the
+ * cell itself through its Dirichlet dynamics, velocity gradients one-sided along the normal and central along the face,
+ * then regularize */
+static void SFX(plane_fd_cell)(SFX(Lat)* L, int x, int y, int z, int dir, int ori) {
+    REAL rho, dA_uB[3][3];
+    int d;
+    rho = SFX(cell_density)(L, CELL(L, x, y, z));
+    for (d = 0; d < 3; ++d) {
+        if (d == dir) SFX(grad_normal)(L, x, y, z, d, ori, dA_uB[d]);
+        else SFX(grad_tangent)(L, x, y, z, d, dA_uB[d]);
+    }
+    SFX(fd_regularize)(L, CELL(L, x, y, z), rho, dA_uB);
+}
+
 /* OuterVelocityCornerFunctional3D::processCell finiteDifferenceBoundaryProcessor3D.hh:264-318 */
 static void SFX(corner_cell)(SFX(Lat)* L, int x, int y, int z, int xn, int yn, int zn) {
     REAL rho100 = SFX(cell_density)(L, CELL(L, x - xn, y, z));
@@ -861,6 +876,8 @@ static void SFX(execute_processors)(SFX(Lat)* L) {
                 /* WrappedLocalBoundaryFunctional3D::process wrappedLocalBoundaryProcessor3D.hh:42-62 */
                 int bi = L->bcIdx[cell];
                 if (bi >= 0) SFX(complete_populations)(L, SFX(dyn_of)(L, cell), &L->bcs[bi], L->f + cell * L->q);
+            } else if (pr->cls == PROC_PLANE_FD) {
+                if (L->bcIdx[cell] >= 0) SFX(plane_fd_cell)(L, x, y, z, pr->a, pr->b);
             } else if (pr->cls == PROC_EDGE) {
                 SFX(edge_cell)(L, x, y, z, pr->a, pr->b, pr->c);
             } else {

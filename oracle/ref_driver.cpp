@@ -101,6 +101,7 @@ template<template<typename U> class D>
 static OnLatticeBoundaryCondition3D<T,D>* makeBC(std::string const& kind) {
     if (kind == "local") return createLocalBoundaryCondition3D<T,D>();
     if (kind == "zouhe") return createZouHeBoundaryCondition3D<T,D>();
+    if (kind == "interp") return createInterpBoundaryCondition3D<T,D>();
     if (kind == "dynlocal") return createDynamicsBasedLocalBoundaryCondition3D<T,D>();
     if (kind == "equilibrium") return createEquilibriumBoundaryCondition3D<T,D>();
     fail("unknown boundary condition " + kind);

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(ROOT, "libplb_b200.so")
 CSRC = os.path.join(ROOT, "csrc")
 
 DYN = {"BGK": 0, "RLB": 1, "TRT": 2, "SMAGO": 3, "BB": 4, "NODYN": 5, "INCBGK": 6}
-BC = {"local": 0, "zouhe": 1, "dynlocal": 2, "equilibrium": 3}
+BC = {"local": 0, "zouhe": 1, "dynlocal": 2, "equilibrium": 3, "interp": 4}
 
 #: every symbol include/plb_b200.h declares (tests check the library exports them all)
 SYMBOLS = [

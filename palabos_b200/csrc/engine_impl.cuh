@@ -262,14 +262,16 @@ public:
         check_dir_ori(dir, ori);
         const int autoPrep = auto_model(model);
         add_bc(model == 1 ? BC_VEL_ZH : BC_VEL_REG, dir, ori, box);
-        add_proc(PROC_PLANE, box, autoPrep, 0, 0);
+        if (model == 4) add_proc(PROC_PLANE_FD, box, dir, ori, 0);
+        else add_proc(PROC_PLANE, box, autoPrep, 0, 0);
     }
     void add_pressure_boundary(int model, int dir, int ori, const int box[6]) override {
         check_box(box);
         check_dir_ori(dir, ori);
         const int autoPrep = auto_model(model);
         add_bc(model == 1 ? BC_RHO_ZH : BC_RHO_REG, dir, ori, box);
-        add_proc(PROC_PLANE, box, autoPrep, 0, 0);
+        if (model == 4) add_proc(PROC_PLANE_FD, box, dir, ori, 0);
+        else add_proc(PROC_PLANE, box, autoPrep, 0, 0);
     }
     /// addExternalVelocityEdge / Corner: StoreVelocityDynamics + Outer{Edge,Corner}Functional3D
     /// (boundaryCondition3D.hh:861-877, :899-915; the Zou-He manager does the same)
@@ -786,7 +788,11 @@ private:
     /// populations between two steps.  Here: a plane "processor" entry with a = 1, never executed; the sweep completes such
     /// cells on load (the machinery of the lazy completion, permanently on, without the on-the-fly completion for readers).
     int auto_model(int model) {
-        if (model < 0 || model > 3) throw PlbError("unknown boundary condition model");
+        if (model < 0 || model > 4) throw PlbError("unknown boundary condition model");
+        // model 4 = createInterpBoundaryCondition3D (boundaryCondition3D.hh:1049-1085): plain Velocity / DensityDirichletBoundaryDynamics
+        // (the records of the regularized model: same computeDensity / computeVelocity / computeRhoBarJ, empty completePopulations
+        // is never asked for) + PlaneFdBoundaryFunctional3D, a finite-difference item like the edges and corners
+        if (model == 4) return 0;
         if (model >= 2 && ext_) throw PlbError("dynamics-based boundary conditions are not available with the external-moment sweep");
         if (model >= 2) autoPlanes_ = true;
         return model >= 2 ? 1 : 0;
@@ -874,6 +880,17 @@ private:
                         items.push_back(it);
                         stageOf.push_back(-1);
                         continue;
+                    }
+                } else if (p.cls == PROC_PLANE_FD) {
+                    if (!sl.cellToRec.count(cell)) continue;
+                    // PlaneFdBoundaryFunctional3D: own density and velocity, velocity of the neighbour behind the face and of
+                    // the four neighbours in the face
+                    need_pops(cell, true, true);
+                    need_pops(neighbour(p.a, -p.b), false, true);
+                    for (int d = 0; d < 3; ++d) {
+                        if (d == p.a) continue;
+                        need_pops(neighbour(d, +1), false, true);
+                        need_pops(neighbour(d, -1), false, true);
                     }
                 } else if (p.cls == PROC_EDGE) {
                     const int d1 = (p.a + 1) % 3, d2 = (p.a + 2) % 3;

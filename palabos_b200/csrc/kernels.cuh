@@ -723,7 +723,20 @@ __global__ void __launch_bounds__(64) fd_stage_kernel(CellCtx<T> cx, T* F, const
     if (t >= nItems) return;
     const Item it = items[t];
     const int c = it.cell;
-    if (it.cls == PROC_EDGE) {
+    if (it.cls == PROC_PLANE_FD) {
+        // PlaneFdBoundaryFunctional3D::processCell finiteDifferenceBoundaryProcessor3D.hh:68-117 (createInterpBoundaryCondition3D):
+        // density and velocity of the cell through its Dirichlet dynamics, velocity gradients one-sided along the normal
+        // and central along the face, then regularize
+        const int dir = it.a, ori = it.b;
+        const T rho = density_at<T, Q>(cx, c);
+        T dA_uB[3][3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (d == dir) grad_normal<T, Q>(cx, c, d, ori, dA_uB[d]);
+            else grad_tangent<T, Q>(cx, c, d, dA_uB[d]);
+        }
+        fd_regularize<T, Q>(cx, F, c, rho, dA_uB);
+    } else if (it.cls == PROC_EDGE) {
         // OuterVelocityEdgeFunctional3D::processCell finiteDifferenceBoundaryProcessor3D.hh:164-226
         const int plane = it.a, n1 = it.b, n2 = it.c;
         const int d1 = (plane + 1) % 3, d2 = (plane + 2) % 3;

@@ -19,7 +19,7 @@ constexpr int DYN_EXTERNAL = 100;
 /// ... and the form that takes them from the fields only where they are not a function of the cell's own populations
 constexpr int DYN_EXTERNAL_FUSED = 101;
 enum BcKind : int { BC_VEL_REG = 0, BC_RHO_REG = 1, BC_VEL_ZH = 2, BC_RHO_ZH = 3, BC_STORE_VEL = 4 };
-enum ProcClass : int { PROC_PLANE = 0, PROC_EDGE = 1, PROC_CORNER = 2 };
+enum ProcClass : int { PROC_PLANE = 0, PROC_EDGE = 1, PROC_CORNER = 2, PROC_PLANE_FD = 3 };
 
 /// One entry of the per-lattice dynamics table (a cell stores the 1-byte index of its entry).
 template <class T>

@@ -369,6 +369,11 @@ CASES = {
     "cavity_dynlocal_incbgk":   (lambda: cavity(8, 9, 10, 30, dyn="INCBGK", model="dynlocal"), "full"),
     "obstacle_dynlocal":        (lambda: obstacle(20, 10, 9, 40, omega=1.4, model="dynlocal"), "full"),
     "inlet_outlet_mixed_models": (lambda: inlet_outlet_mixed(12, 9, 8, 40), "full"),
+    # createInterpBoundaryCondition3D: plain Dirichlet dynamics on the planes + the finite-difference plane processor
+    "cavity_interp_10x9x8":     (lambda: cavity(10, 9, 8, 40, model="interp", every=20), "full"),
+    "cavity_interp_rlb_q27":    (lambda: cavity(8, 8, 9, 30, dyn="RLB", q=27, model="interp"), "full"),
+    "cavity_interp_incbgk_f32": (lambda: cavity(9, 8, 10, 30, dyn="INCBGK", prec="f32", model="interp"), "full"),
+    "obstacle_interp":          (lambda: obstacle(20, 10, 9, 40, omega=1.4, model="interp"), "full"),
     # edge cases
     "mixed_omega_11x8x9":       (lambda: mixed_omega(11, 8, 9, 40), "full"),
     "inlet_outlet_local":       (lambda: inlet_outlet_local(12, 9, 8, 40), "full"),

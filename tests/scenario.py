@@ -29,7 +29,7 @@ REF_DRIVER = os.path.join(ORACLE_DIR, "_ref", "ref_driver")
 REF_DRIVER_F32 = os.path.join(ORACLE_DIR, "_ref", "ref_driver_f32")
 
 DYN = {"BGK": 0, "RLB": 1, "TRT": 2, "SMAGO": 3, "BB": 4, "NODYN": 5, "INCBGK": 6}
-BC = {"local": 0, "zouhe": 1, "dynlocal": 2, "equilibrium": 3}
+BC = {"local": 0, "zouhe": 1, "dynlocal": 2, "equilibrium": 3, "interp": 4}
 
 
 def full_box(nx, ny, nz):

@@ -148,12 +148,12 @@ def test_external_rhoj3d_cpp_matches_the_unmodified_reference():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("model", ["dynlocal", "equilibrium"])
+@pytest.mark.parametrize("model", ["dynlocal", "equilibrium", "interp"])
 def test_cavity3d_cpp_dynamics_based_boundary_managers(model):
     """createDynamicsBasedLocalBoundaryCondition3D / createEquilibriumBoundaryCondition3D of the C++ mirror against the dump of
     the unmodified reference (in this fork the two managers are the same for planes, outer edges and corners)"""
     nx, ny, nz = 10, 9, 8
-    gold = np.load(os.path.join(ROOT, "tests", "golden", "cavity_dynlocal_10x9x8.npz"))
+    gold = np.load(os.path.join(ROOT, "tests", "golden", ("cavity_interp_10x9x8" if model == "interp" else "cavity_dynlocal_10x9x8") + ".npz"))
     with tempfile.TemporaryDirectory() as tmp:
         dump = os.path.join(tmp, "f.bin")
         subprocess.run([_exe("cavity3d"), str(nx), str(ny), str(nz), "40", dump], check=True, capture_output=True, text=True,

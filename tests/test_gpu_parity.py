@@ -106,6 +106,7 @@ SLAB_CASES = {
     "cavity_dynlocal_10x9x8": 3,
     "obstacle_dynlocal": 4,
     "inlet_outlet_mixed_models": 2,
+    "cavity_interp_10x9x8": 3,
 }
 
 
