@@ -20,6 +20,9 @@ One JSON line on rank 0:
   cpu_baseline  the reference's own CPU code (oracle/_ref/ref_driver, or the C port when that binary
             is absent) on a bounded sample of the same workload, rank 0, N=1 only
 --impl reference times that CPU implementation with as many host processes as there are cores.
+
+--workload runs another BASELINE.json config (channel_trt, obstacle, les_q27_f64, les_q27_f32) or ext_cavity, the time loop
+of the fork's own application (external-moment sweep), and prints the same line for it.
 """
 import argparse
 import json
