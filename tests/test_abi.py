@@ -28,6 +28,8 @@ def test_no_cpu_fallback():
     import palabos_b200 as pb
     with pytest.raises(pb.PlbError, match="no CUDA device"):
         pb.Lattice(19, "f64", 8, 8, 8, "BGK", 1.0)
+    with pytest.raises(pb.PlbError, match="no CUDA device"):
+        pb.Lattice(19, "f64", 8, 8, 8, "INCBGK", 1.0, enveloped_periodic=(0, 1, 0))
     h = ctypes.c_int(-1)
     assert pb.lib().plb_b200_coproc_add_domain(8, 4, 4, 4, 1.0, ctypes.byref(h)) == 0
 
