@@ -28,7 +28,7 @@ int main(int argc, char** argv) {
         MultiBlockLattice3D<T, DESCRIPTOR> lattice(nx, ny, nz, new IncBGKdynamics<T, DESCRIPTOR>(omega), WithEnvelope());
         lattice.toggleInternalStatistics(false);
 
-        std::unique_ptr<MultiScalarField3D<T> > rhoBar = generateMultiScalarField<T>(lattice, 1);
+        std::unique_ptr<MultiScalarField3D<T> > rhoBar = generateMultiScalarField<T>((MultiBlock3D&)lattice, 1);   // as src/variables.hh:475
         std::unique_ptr<MultiTensorField3D<T, 3> > j = generateMultiTensorField<T, 3>(lattice, 1);
         std::vector<MultiBlock3D*> rhoBarJarg;
         rhoBarJarg.push_back(&lattice);

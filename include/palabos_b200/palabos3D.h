@@ -165,6 +165,9 @@ template <typename T, template <typename U> class Descriptor> class MultiBlockLa
 class MultiBlock3D {
 public:
     virtual ~MultiBlock3D() {}
+    virtual plint getNx() const = 0;
+    virtual plint getNy() const = 0;
+    virtual plint getNz() const = 0;
 };
 
 /// Tag of the lattice constructor for the time loop of the fork's own application (src/variables.hh:461-486): the lattice
@@ -654,6 +657,16 @@ std::unique_ptr<MultiScalarField3D<T> > generateMultiScalarField(MultiBlockLatti
 template <typename T, int nDim, template <typename U> class Descriptor>
 std::unique_ptr<MultiTensorField3D<T, nDim> > generateMultiTensorField(MultiBlockLattice3D<T, Descriptor>& lattice, plint /*envelopeWidth*/ = 1) {
     return std::unique_ptr<MultiTensorField3D<T, nDim> >(new MultiTensorField3D<T, nDim>(lattice.getNx(), lattice.getNy(), lattice.getNz()));
+}
+
+/// the fork writes generateMultiScalarField<T>((MultiBlock3D&) *lattice, envelopeWidth) (src/variables.hh:475-479): same through the base class
+template <typename T>
+std::unique_ptr<MultiScalarField3D<T> > generateMultiScalarField(MultiBlock3D& block, plint /*envelopeWidth*/ = 1) {
+    return std::unique_ptr<MultiScalarField3D<T> >(new MultiScalarField3D<T>(block.getNx(), block.getNy(), block.getNz()));
+}
+template <typename T, int nDim>
+std::unique_ptr<MultiTensorField3D<T, nDim> > generateMultiTensorField(MultiBlock3D& block, plint /*envelopeWidth*/ = 1) {
+    return std::unique_ptr<MultiTensorField3D<T, nDim> >(new MultiTensorField3D<T, nDim>(block.getNx(), block.getNy(), block.getNz()));
 }
 
 namespace detail {
