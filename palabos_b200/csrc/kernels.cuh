@@ -524,6 +524,14 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
                 z += (int)(threadIdx.x & 31u);
                 if (z >= g.nz) decode_cell(g, c, X, y, z);
             }
+            // cells of the sparse list are left to the list blocks: skip them before their populations are gathered (measured at
+            // 512^3, profiles/r01_fused_planes_variants.log: 7.14 -> 7.05 ms per step against checking after the gather);
+            // without fused planes the kind byte is read after the gather has been issued, as before
+            int k = 0;
+            if (PLANES) {
+                k = a.kind[c];
+                if (planes && (k & KIND_SPARSE)) continue;
+            }
             T f[Q];
             Nbr n;
             gather(c, interior, X, y, z, n, f);
@@ -534,9 +542,8 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
                     else CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
                 }
             }
-            const int k = a.kind[c];
+            if (!PLANES) k = a.kind[c];
             if (PLANES && planes) {
-                if (k & KIND_SPARSE) continue;
                 if (k & KIND_PLANE) complete(c, k, f);
             }
             collide_scatter(c, k, interior, n, f);
