@@ -176,6 +176,56 @@ class ClockSampler:
         return out
 
 
+def nccl_parity_check(pb, dist, torch, rank, world):
+    """Untimed prologue of the N > 1 runs (the driver's test box has one GPU, its bench boxes have N): a small lid-driven cavity
+    stepped over the N-rank lattice -- the very exchange path the timed steps use -- must give, bit for bit, the populations of
+    the same engine run on ONE slab on rank 0 (which tests/test_gpu_parity.py pins against the oracle and the reference's dumps)."""
+    import numpy as np
+    nx, ny, nz, steps = max(24, 5 * world + 3), 20, 18, 25          # odd step count: the download reads across the slab faces
+    out = {}
+    for name, q, prec, dyn, omega in (("cavity D3Q19 BGK f64", 19, "f64", "BGK", cavity_omega(ny)),
+                                      ("periodic D3Q27 SMAGO f32 + BB walls", 27, "f32", "SMAGO", 1.9)):
+        def run(lat):
+            box = lat.box
+            if dyn == "BGK":
+                lat.set_velocity_condition_on_block_boundaries("local", box, box)
+                lat.set_boundary_velocity(box, (0, 0, 0))
+                lat.set_boundary_velocity((1, nx - 2, 1, ny - 2, nz - 1, nz - 1), (U_MAX, 0, 0))
+                lat.initialize_at_equilibrium(box, 1.0, (0, 0, 0))
+            else:
+                lat.set_periodicity(True, False, True)
+                lat.define_dynamics((0, nx - 1, 0, 0, 0, nz - 1), "BB", 1.0)
+                lat.define_dynamics((0, nx - 1, ny - 1, ny - 1, 0, nz - 1), "BB", 1.0)
+                lat.initialize_at_equilibrium(box, 1.0, (0.05, 0, 0))
+                lat.initialize_at_equilibrium((1, 3, 2, 5, 0, nz - 1), 1.02, (0.02, 0.01, -0.01))
+                lat.initialize_at_equilibrium((nx - 2, nx - 1, 2, 9, 4, 9), 0.99, (0.04, -0.01, 0.02))
+            lat.initialize()
+            lat.collide_and_stream(steps)
+            return lat.download()
+        lat = pb.Lattice(q, prec, nx, ny, nz, dyn, omega, 0.14 if dyn == "SMAGO" else 0.0, rank=rank, n_ranks=world)
+        uid = [pb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        lat.comm_init(uid[0])
+        mine = run(lat)
+        halo = lat.halo_transport() if hasattr(lat, "halo_transport") else "nccl"
+        lat.close()
+        parts = [None] * world
+        dist.all_gather_object(parts, mine.reshape(-1, q))
+        if rank == 0:
+            single = pb.Lattice(q, prec, nx, ny, nz, dyn, omega, 0.14 if dyn == "SMAGO" else 0.0)
+            want = run(single).reshape(-1, q)
+            single.close()
+            got = np.concatenate(parts, axis=0)
+            same = got.shape == want.shape and got.tobytes() == want.tobytes() and bool(np.isfinite(want).all()) and float(np.abs(want).max()) > 0
+            out[name] = "identical" if same else "DIFFERENT"
+            out["transport"] = halo
+    if rank == 0:
+        res = {"nccl_vs_single": "identical" if all(v == "identical" for k, v in out.items() if k != "transport") else "DIFFERENT",
+               "ranks": world, "lattice": "%dx%dx%d, %d steps" % (nx, ny, nz, steps), "cases": out}
+        return res
+    return None
+
+
 def our_arm(args):
     import numpy as np
     import torch
@@ -192,6 +242,10 @@ def our_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    parity = nccl_parity_check(pb, dist, torch, rank, world) if world > 1 else None
+    if parity and parity["nccl_vs_single"] != "identical":
+        raise SystemExit("multi-rank parity check failed: %s" % json.dumps(parity))
 
     n = args.n
     wl = WORKLOADS[args.workload]
@@ -282,12 +336,15 @@ def our_arm(args):
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lat.launch_count()
     lat.profile_sweeps(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    step(args.steps)
-    e1.record()
+    # one event per step: the whole region is timed e[0] -> e[K] as before, the per-step distribution comes for free
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for k in range(args.steps):
+        step(1)
+        ev[k + 1].record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = ev[0].elapsed_time(ev[-1])
+    per_step = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
     sweep_ms, sweep_n = lat.profile_read()
     lat.profile_sweeps(False)
     launches = lat.launch_count() - launches0
@@ -369,14 +426,16 @@ def our_arm(args):
 
     if rank == 0:
         line = {"metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+                "ms_per_step": ms / args.steps,
+                "ms_per_step_p50": per_step[len(per_step) // 2], "ms_per_step_p95": per_step[min(len(per_step) - 1, int(0.95 * len(per_step)))],
+                "ms_per_step_min": per_step[0], "ms_per_step_max": per_step[-1], "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
                 "dtype": PREC, "data": "synthetic",
                 "config": {"workload": what,
                            "parallelism": "x-slabs, %d rank(s)" % world, "streaming": "in-place AA pattern",
                            "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed" % (cells_local * BYTES_PER_LU / 2 / 1e9),
                            "omega": omega, "stored_avg_energy": 0.5 * stats[1], "stored_avg_density": stats[0] + 1.0},
                 "mlups_per_gpu": value / world,
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+                "parity_check": parity, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     lat.close()
     if world > 1:

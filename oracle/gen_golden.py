@@ -11,7 +11,7 @@ code, compiled by `make -C oracle ref` from /root/reference/src) and stores, per
   <dump>_full            the whole dump, only for the cases marked "full" that are tiny
 
 This can only run where /root/reference exists (this container); the fixtures travel.
-Usage: python oracle/gen_golden.py [case ...]
+Usage: python oracle/gen_golden.py [case ...]      (no argument: every case of CASES; the LARGE_CASES only by name)
 """
 import os
 import sys
@@ -20,7 +20,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from cases import CASES, probe_index  # noqa: E402
+from cases import CASES, LARGE_CASES, probe_index  # noqa: E402
 from scenario import digest, run_reference  # noqa: E402
 
 FULL_LIMIT = 800  # cells: dumps of lattices up to this size are stored whole
@@ -31,7 +31,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     names = sys.argv[1:] or list(CASES)
     for name in names:
-        build, how = CASES[name]
+        build, how = CASES[name] if name in CASES else LARGE_CASES[name]
         sc = build()
         ref = run_reference(sc)
         rec = {"stats": ref["stats"]}

@@ -877,7 +877,9 @@ static void SFX(execute_processors)(SFX(Lat)* L) {
                 int bi = L->bcIdx[cell];
                 if (bi >= 0) SFX(complete_populations)(L, SFX(dyn_of)(L, cell), &L->bcs[bi], L->f + cell * L->q);
             } else if (pr->cls == PROC_PLANE_FD) {
-                if (L->bcIdx[cell] >= 0) SFX(plane_fd_cell)(L, x, y, z, pr->a, pr->b);
+                /* PlaneFdBoundaryFunctional3D::processCell finiteDifferenceBoundaryProcessor3D.hh:68-117 has no isComposite() test:
+                 * it runs on every cell of its box, also where defineDynamics has replaced the Dirichlet dynamics */
+                SFX(plane_fd_cell)(L, x, y, z, pr->a, pr->b);
             } else if (pr->cls == PROC_EDGE) {
                 SFX(edge_cell)(L, x, y, z, pr->a, pr->b, pr->c);
             } else {

@@ -101,6 +101,7 @@ void plb_b200_destroy(plb_b200_lattice* L) {
 
 int plb_b200_comm_unique_id(char id128[128]) {
     try {
+        if (!id128) throw PlbError("null id buffer");
         NcclApi& n = NcclApi::get();
         ncclUniqueId uid;
         n.check(n.GetUniqueId(&uid), "ncclGetUniqueId");
@@ -108,7 +109,9 @@ int plb_b200_comm_unique_id(char id128[128]) {
         return 1;
     } catch (const std::exception& e) { return fail(e.what()); }
 }
-int plb_b200_comm_init(plb_b200_lattice* L, const char id128[128]) { PLB_TRY(L, L->impl->comm_init(id128)) }
+int plb_b200_comm_init(plb_b200_lattice* L, const char id128[128]) {
+    PLB_TRY(L, { if (!id128) throw PlbError("null id buffer"); L->impl->comm_init(id128); })
+}
 
 int plb_b200_slab_range(int nx, int nSlabs, int slab, int* x0, int* x1) {
     if (nx < 1 || nSlabs < 1 || nSlabs > nx || slab < 0 || slab >= nSlabs || !x0 || !x1) return fail("bad slab query");
@@ -332,13 +335,13 @@ int plb_b200_download_rhobar_j(plb_b200_lattice* L, const int box[6], void* data
 int plb_b200_synchronize(plb_b200_lattice* L) { PLB_TRY(L, L->impl->synchronize()) }
 
 int plb_b200_get_stored_statistics(plb_b200_lattice* L, double out3[3], uint64_t* n) {
-    PLB_TRY(L, L->impl->stored_statistics(out3, n))
+    PLB_TRY(L, { if (!out3) throw PlbError("null output pointer"); L->impl->stored_statistics(out3, n); })
 }
 int plb_b200_compute_average_energy(plb_b200_lattice* L, const int box[6], double* out) {
-    PLB_TRY(L, *out = L->impl->average_energy(SBox(L, box)))
+    PLB_TRY(L, { if (!out) throw PlbError("null output pointer"); *out = L->impl->average_energy(SBox(L, box)); })
 }
 int plb_b200_compute_average_density(plb_b200_lattice* L, const int box[6], double* out) {
-    PLB_TRY(L, *out = L->impl->average_density(SBox(L, box)))
+    PLB_TRY(L, { if (!out) throw PlbError("null output pointer"); *out = L->impl->average_density(SBox(L, box)); })
 }
 int plb_b200_compute_density_velocity(plb_b200_lattice* L, const int box[6], void* out, size_t bytes) {
     PLB_TRY(L, L->impl->density_velocity(SBox(L, box), out, bytes))

@@ -89,6 +89,7 @@ class LatticeImpl : public LatticeBase {
     bool extFuse_ = true;                    ///< PLB_B200_EXT_EXPLICIT=1 in the environment: always store and re-read the fields (A/B tests)
     bool anySetup_ = false;
     bool stepped_ = false;
+    bool failed_ = false;                    ///< a step died half-way (exchange or launch error): the populations are in no defined layout
     cudaStream_t stream_ = 0;
     uint64_t launches_ = 0;
     size_t devBytes_ = 0;
@@ -543,7 +544,12 @@ public:
     void advance(int n, bool ext) {
         if (n < 0) throw PlbError("negative step count");
         if (desc_.nRanks > 1 && !comm_) throw PlbError("plb_b200_comm_init must be called before stepping a multi-rank lattice");
+        if (failed_) throw PlbError("an earlier step of this lattice failed half-way: its state is undefined, create a new lattice");
         sync_setup();
+        try { advance_steps(n, ext); }
+        catch (...) { failed_ = true; throw; }   // launches of a step were issued and the layout flags toggled only in part
+    }
+    void advance_steps(int n, bool ext) {
         for (int s = 0; s < n; ++s) {
             if (ext && !(extImplied_ && extFuse_)) materialize();   // the stored-fields sweep has no completion on load
             // measured at 512^3 per GPU on 2 B200s: 7.18 ms per step overlapped against 7.26 (the split costs 0.03 ms of sweep time)
@@ -882,7 +888,8 @@ private:
                         continue;
                     }
                 } else if (p.cls == PROC_PLANE_FD) {
-                    if (!sl.cellToRec.count(cell)) continue;
+                    // (no isComposite() test in the reference: the processor also runs where defineDynamics has replaced
+                    // the Dirichlet dynamics, finiteDifferenceBoundaryProcessor3D.hh:68-117)
                     // PlaneFdBoundaryFunctional3D: own density and velocity, velocity of the neighbour behind the face and of
                     // the four neighbours in the face
                     need_pops(cell, true, true);
@@ -1234,36 +1241,43 @@ private:
         const bool remote = desc_.nRanks > 1;
         NcclApi* n = remote ? &NcclApi::get() : nullptr;
         if (remote) n->check(n->GroupStart(), "ncclGroupStart");
-        for (int face = 0; face < nFaces; ++face) {
-            const int gLo = face, gHi = (face + 1) % G_;
-            for (int part = 0; part < 2; ++part) {
-                // part 0 carries the slots with c_x = -1, part 1 those with c_x = +1
-                const int cxSel = part == 0 ? -1 : +1;
-                int srcG, dstG, srcPlane, dstPlane;     // plane: 0 low ghost, 1 first, 2 last, 3 high ghost
-                if (swapped_) {
-                    if (part == 0) { srcG = gLo; srcPlane = 2; dstG = gHi; dstPlane = 0; }
-                    else           { srcG = gHi; srcPlane = 1; dstG = gLo; dstPlane = 3; }
-                } else {
-                    // ghost -> ghost; unpack_halo_kernel then moves the valid entries onto the boundary plane
-                    if (part == 1) { srcG = gLo; srcPlane = 3; dstG = gHi; dstPlane = 0; }
-                    else           { srcG = gHi; srcPlane = 0; dstG = gLo; dstPlane = 3; }
-                }
-                Slab* src = find_slab(srcG);
-                Slab* dst = find_slab(dstG);
-                if (!src && !dst) continue;
-                for (int i = 1; i < Q; ++i) {
-                    if (c_of(i, 0) != cxSel) continue;
-                    T* sp = src ? plane_ptr(*src, i, srcPlane) : nullptr;
-                    T* dp = dst ? plane_ptr(*dst, i, dstPlane) : nullptr;
-                    if (src && dst) {
-                        PLB_CUDA(cudaMemcpyAsync(dp, sp, planeBytes, cudaMemcpyDeviceToDevice, stream));
-                    } else if (src) {
-                        n->check(n->Send(sp, planeBytes, ncclInt8, dstG / desc_.slabsPerRank, comm_, stream), "ncclSend");
+        try {
+            for (int face = 0; face < nFaces; ++face) {
+                const int gLo = face, gHi = (face + 1) % G_;
+                for (int part = 0; part < 2; ++part) {
+                    // part 0 carries the slots with c_x = -1, part 1 those with c_x = +1
+                    const int cxSel = part == 0 ? -1 : +1;
+                    int srcG, dstG, srcPlane, dstPlane;     // plane: 0 low ghost, 1 first, 2 last, 3 high ghost
+                    if (swapped_) {
+                        if (part == 0) { srcG = gLo; srcPlane = 2; dstG = gHi; dstPlane = 0; }
+                        else           { srcG = gHi; srcPlane = 1; dstG = gLo; dstPlane = 3; }
                     } else {
-                        n->check(n->Recv(dp, planeBytes, ncclInt8, srcG / desc_.slabsPerRank, comm_, stream), "ncclRecv");
+                        // ghost -> ghost; unpack_halo_kernel then moves the valid entries onto the boundary plane
+                        if (part == 1) { srcG = gLo; srcPlane = 3; dstG = gHi; dstPlane = 0; }
+                        else           { srcG = gHi; srcPlane = 0; dstG = gLo; dstPlane = 3; }
+                    }
+                    Slab* src = find_slab(srcG);
+                    Slab* dst = find_slab(dstG);
+                    if (!src && !dst) continue;
+                    for (int i = 1; i < Q; ++i) {
+                        if (c_of(i, 0) != cxSel) continue;
+                        T* sp = src ? plane_ptr(*src, i, srcPlane) : nullptr;
+                        T* dp = dst ? plane_ptr(*dst, i, dstPlane) : nullptr;
+                        if (src && dst) {
+                            PLB_CUDA(cudaMemcpyAsync(dp, sp, planeBytes, cudaMemcpyDeviceToDevice, stream));
+                        } else if (src) {
+                            n->check(n->Send(sp, planeBytes, ncclInt8, dstG / desc_.slabsPerRank, comm_, stream), "ncclSend");
+                        } else {
+                            n->check(n->Recv(dp, planeBytes, ncclInt8, srcG / desc_.slabsPerRank, comm_, stream), "ncclRecv");
+                        }
                     }
                 }
             }
+        } catch (...) {
+            // never leave the NCCL group open: every later call on this thread would be swallowed by it
+            if (remote) n->GroupEnd();
+            failed_ = true;
+            throw;
         }
         if (remote) n->check(n->GroupEnd(), "ncclGroupEnd");
     }

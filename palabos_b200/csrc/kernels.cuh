@@ -972,7 +972,9 @@ static __global__ void flag_sparse_cells_kernel(const int* cells, int n, uint8_t
 /// Scatter the sparse (cell -> boundary record) map into the dense per-cell index.
 static __global__ void scatter_bc_index_kernel(const int* cells, int n, int* bcIdx) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) bcIdx[cells[t]] = t;
+    if (t >= n) return;
+    const int c = cells[t];
+    if (c >= 0) bcIdx[c] = t;          // dead records (cell -1: defineDynamics replaced the composite) are not indexed
 }
 
 }  // namespace plb200

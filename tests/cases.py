@@ -306,6 +306,37 @@ def inlet_outlet_mixed(nx, ny, nz, steps):
     return sc
 
 
+def cavity_eraser(nx, ny, nz, steps, model="local", q=19, prec="f64"):
+    """defineDynamics used as an "eraser tool" AFTER the boundary set-up (wrappedLocalBoundaryProcessor3D.hh:51-58): BounceBack,
+    NoDynamics and plain bulk dynamics replace the boundary composites on parts of planes, edges and corners, by box and by
+    mask; the data processors stay and meet cells without a composite.  (Engine: boundary records die, ADVICE r1 high.)"""
+    u_max, re = 0.02, 100.0
+    omega = 1.0 / (3 * u_max * ny / re + 0.5)
+    sc = Scenario(q, prec, nx, ny, nz, "BGK", omega, 0.0)
+    sc.bc_box(model)
+    sc.set_velocity(sc.box, (0, 0, 0))
+    sc.set_velocity((1, nx - 2, 1, ny - 2, nz - 1, nz - 1), (u_max, 0, 0))
+    sc.dynamics((0, 0, 2, ny - 3, 1, nz // 2), "BB", 1.0)                  # part of the x = 0 plane
+    sc.dynamics((2, 4, 3, 4, nz - 1, nz - 1), "BB", 1.0)                   # a patch of the lid
+    sc.dynamics((1, nx // 2, 0, 0, 0, 0), "BB", 1.0)                       # half an edge
+    sc.dynamics((nx - 1, nx - 1, ny - 1, ny - 1, nz - 1, nz - 1), "BB", 1.0)   # a corner
+    sc.dynamics((0, 0, 0, 0, 0, 0), "NODYN", 1.0)                          # another corner
+    sc.dynamics((nx - 1, nx - 1, 1, 3, 2, 4), "BGK", 1.3)                  # bulk dynamics on plane cells: the composite goes
+    sc.dynamics((nx - 1, nx - 1, 0, 0, 2, 3), "RLB", 1.2)                  # ... and on edge cells
+    mask = np.zeros((nx, ny, nz), dtype=np.int32)
+    mask[3:6, ny - 1, 2:5] = 7                                             # patch of the y = ny-1 plane
+    mask[nx - 2, ny - 1, 0] = 7                                            # an edge cell
+    mask[5, 5, 3] = 7                                                      # and a bulk cell
+    sc.dynamics_mask(mask, 7, "BB", 1.0)
+    sc.init_eq(sc.box, 1.0, (0, 0, 0))
+    sc.initialize()
+    sc.dump("f_init")
+    sc.run(steps // 2).stats()
+    sc.set_velocity((1, nx - 2, 1, ny - 2, nz - 1, nz - 1), (u_max, 0.001, 0))
+    sc.run(steps - steps // 2).stats().dump("f_end").dump_rho_u("rho_u_end")
+    return sc
+
+
 # name -> (builder, how to store the reference outcome: "full" dumps, or "probe" = sha256 + sampled cells)
 CASES = {
     # configs[0]-style cavity, all dynamics on the path
@@ -378,6 +409,19 @@ CASES = {
     "mixed_omega_11x8x9":       (lambda: mixed_omega(11, 8, 9, 40), "full"),
     "inlet_outlet_local":       (lambda: inlet_outlet_local(12, 9, 8, 40), "full"),
     "thin_4x5x3":               (lambda: cavity(4, 5, 3, 10), "full"),
+    # defineDynamics over boundary cells after the boundary set-up (the "eraser tool")
+    "cavity_eraser_10x9x8":     (lambda: cavity_eraser(10, 9, 8, 40), "full"),
+    "cavity_eraser_zouhe_q27":  (lambda: cavity_eraser(9, 8, 8, 30, model="zouhe", q=27), "full"),
+    "cavity_eraser_interp_f32": (lambda: cavity_eraser(9, 8, 10, 30, model="interp", prec="f32"), "full"),
+}
+
+# Bench-scale cases: large enough that both halves of the sweep run several tiles per block in their
+# grid-stride loop and the L2-prefetch branch sees a real stride (> 148 SMs x 128 blocks x 512 cells = 9.7 M cells).  Goldens
+# (sha256 + probe cells) come from the unmodified reference like all others; the C oracle replays them in ~30 s each.
+LARGE_CASES = {
+    "cavity_bgk_256_10":              (lambda: cavity(256, 256, 256, 10, dumps=False).dump("f_end").dump_rho_u("rho_u_end"), "probe"),
+    "channel_smago_q27_f32_224x160x320": (lambda: channel(224, 160, 320, 6, dyn="SMAGO", omega=1.99, q=27, cs=0.14, perturb=0.01,
+                                                            prec="f32"), "probe"),
 }
 
 PROBE_CELLS = 97  # cells sampled (deterministically) from large dumps

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import CASES, cavity, channel, obstacle, periodic_box
+from cases import CASES, LARGE_CASES, cavity, channel, obstacle, periodic_box
 from scenario import digest, max_rel_diff, replay, run_oracle
 
 pytestmark = pytest.mark.gpu
@@ -107,6 +107,8 @@ SLAB_CASES = {
     "obstacle_dynlocal": 4,
     "inlet_outlet_mixed_models": 2,
     "cavity_interp_10x9x8": 3,
+    "cavity_eraser_10x9x8": 3,
+    "cavity_eraser_zouhe_q27": 2,
 }
 
 
@@ -479,3 +481,132 @@ def test_checkpoint_of_an_enveloped_lattice_round_trips(tmp_path):
     b.apply_rhobar_j()                       # the application's restart: fields from the restored populations
     assert np.array_equal(b.download_rhobar_j(), fld)
     a.close(); b.close()
+
+
+# ---- bench scale: the configuration the bench line is quoted on runs code no small lattice reaches --
+# ---- several tiles per block in the grid-stride loop, the L2 prefetch with a real stride, element offsets beyond 2^31
+
+
+@pytest.mark.parametrize("name", sorted(LARGE_CASES))
+def test_bench_scale_matches_oracle_and_reference_dump(name):
+    """16.8 M cells (D3Q19 fp64 cavity, 10 steps) and 11.5 M cells (D3Q27 fp32 Smagorinsky channel, 6 steps): engine == C oracle on
+    every population and on rho / u, and == the unmodified reference's sha256 + probe cells."""
+    sc = LARGE_CASES[name][0]()
+    got = run_gpu(sc)
+    want = run_oracle(sc)
+    for key, w in want.items():
+        if key in ("stats", "time"):
+            continue
+        assert np.array_equal(got[key], w), "%s: %s differs, max rel diff %.3e" % (name, key, max_rel_diff(got[key], w))
+    # statistics: sums of > 1e7 terms in three different orders (reference block-wise, oracle linear, device tree)
+    rel = 1e-10 if sc.prec == "f64" else 1e-5
+    assert np.allclose(got["stats"], want["stats"], rtol=rel, atol=1e-300)
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    for key in [k[:-7] for k in gold.files if k.endswith("_sha256")]:
+        arr = got[key]
+        assert np.array_equal(arr.reshape(-1, arr.shape[-1])[gold[key + "_probe_idx"]], gold[key + "_probe"])
+        assert digest(arr) == str(gold[key + "_sha256"]), "%s: sha256 of %s differs from the reference's" % (name, key)
+    assert np.allclose(got["stats"], gold["stats"], rtol=rel, atol=1e-300)
+
+
+def _plane_checksums(eng, nx, planes_per_chunk=8):
+    """Download the lattice in x-chunks; per x-plane (sum, xor) of the raw 64-bit words + sha256 of the whole stream."""
+    import hashlib
+    sums, sha = [], hashlib.sha256()
+    for x0 in range(0, nx, planes_per_chunk):
+        x1 = min(nx, x0 + planes_per_chunk) - 1
+        a = eng.download((x0, x1, 0, eng.ny - 1, 0, eng.nz - 1))
+        w = a.view(np.uint64).reshape(x1 - x0 + 1, -1)
+        sums.append(np.stack([np.add.reduce(w, axis=1), np.bitwise_xor.reduce(w, axis=1)], axis=1))
+        if x0 % (8 * planes_per_chunk) == 0:        # sha256 is the slow part (20 GB per run): one chunk in eight
+            sha.update(a.tobytes())
+    return np.concatenate(sums), sha.hexdigest()
+
+
+def test_full_size_cavity_is_decomposition_invariant():
+    """BASELINE configs[1] itself: 512^3 D3Q19 BGK fp64 cavity (20.4 GB of populations, slot stride 1.35e8 elements, offsets up to
+    2.6e9), 6 steps on 1, 2 and 3 x-slabs: every x-plane of populations has the same 64-bit sum and xor, sampled chunks the same
+    sha256, and computeAverageDensity / computeAverageEnergy / the stored statistics agree to rounding.  (The reference guarantees
+    decomposition invariance, jlabos/src/testing/testsuite:3-7.)"""
+    import palabos_b200 as pb
+    n, steps = 512, 6
+    res = []
+    for slabs in (1, 2, 3):
+        sc = cavity(n, n, n, 0, dumps=False)
+        eng = pb.Lattice(19, "f64", n, n, n, "BGK", sc.p1, 0.0, slabs_per_rank=slabs)
+        try:
+            eng.set_velocity_condition_on_block_boundaries("local")
+            eng.set_boundary_velocity(eng.box, (0, 0, 0))
+            eng.set_boundary_velocity((1, n - 2, 1, n - 2, n - 1, n - 1), (0.02, 0, 0))
+            eng.initialize_at_equilibrium(eng.box, 1.0, (0, 0, 0))
+            eng.initialize()
+            eng.collide_and_stream(steps)
+            st = eng.stored_statistics()
+            rho, en = eng.compute_average_density(), eng.compute_average_energy()
+            sums, sha = _plane_checksums(eng, n)
+            res.append((sums, sha, st, rho, en))
+        finally:
+            eng.close()
+    for k in (1, 2):
+        assert np.array_equal(res[k][0], res[0][0]), "x-planes %s differ between 1 and %d slabs" % (
+            np.nonzero((res[k][0] != res[0][0]).any(axis=1))[0][:8], k + 1)
+        assert res[k][1] == res[0][1]
+        assert np.allclose(res[k][2][:3], res[0][2][:3], rtol=1e-10, atol=0) and res[k][2][3] == res[0][2][3]
+        assert abs(res[k][3] - res[0][3]) <= 1e-13 and abs(res[k][4] - res[0][4]) <= 1e-12 * abs(res[0][4])
+    # the lid has been moving for 6 steps: a developed, non-trivial state
+    assert res[0][4] > 0 and 0.99999 < res[0][3] < 1.00001 and res[0][2][3] >= (n - 2) ** 3
+
+
+def test_full_size_channel_conserves_mass_and_is_decomposition_invariant():
+    """BASELINE configs[2] on one GPU: 2048x512x512 D3Q19 TRT (81.6 GB of populations in ONE slab: element offsets up to 1.0e10).
+    (a) without walls (periodic in x, y, z) nothing enters or leaves: computeAverageDensity, i.e. the sum over all populations, is
+    conserved to rounding over 5 steps (3 even + 2 odd halves of the AA pattern, wrap-around inside the kernel);
+    (b) the config itself (periodic x, z, BounceBack walls) on 1 and on 3 x-slabs: the planes next to the slab faces and to the
+    periodic seam are bit-identical after an odd number of steps (swapped layout: the download reads across the faces), and
+    density / energy over the fluid agree to rounding."""
+    import hashlib
+    import torch
+    import palabos_b200 as pb
+    nx, ny, nz = 2048, 512, 512
+    if torch.cuda.mem_get_info()[0] < 100e9:
+        pytest.skip("needs 100 GB of free device memory")
+
+    def build(slabs, walls):
+        eng = pb.Lattice(19, "f64", nx, ny, nz, "TRT", 1.2, 0.0, slabs_per_rank=slabs)
+        eng.set_periodicity(True, not walls, True)
+        if walls:
+            eng.define_dynamics((0, nx - 1, 0, 0, 0, nz - 1), "BB", 1.0)
+            eng.define_dynamics((0, nx - 1, ny - 1, ny - 1, 0, nz - 1), "BB", 1.0)
+        eng.initialize_at_equilibrium(eng.box, 1.0, (0.05, 0, 0))
+        # something to transport, across the periodic seam and across the faces of the 3-slab decomposition (x = 682|683, 1364|1365)
+        eng.initialize_at_equilibrium((2040, 2047, 1, ny - 2, 0, nz - 1), 1.02, (0.03, 0.01, -0.01))
+        eng.initialize_at_equilibrium((0, 7, 1, ny - 2, 3, nz - 5), 0.99, (0.04, -0.01, 0.01))
+        eng.initialize_at_equilibrium((676, 690, 1, ny - 2, 0, nz - 1), 1.01, (0.02, 0.01, 0.02))
+        eng.initialize_at_equilibrium((1360, 1370, 1, ny - 2, 0, nz - 1), 0.98, (0.06, 0.0, -0.02))
+        eng.initialize()
+        return eng
+
+    eng = build(1, walls=False)
+    try:
+        rho0 = eng.compute_average_density()
+        eng.collide_and_stream(5)
+        rho5 = eng.compute_average_density()
+        assert abs(rho0 - 1.0) > 1e-6                       # the lattice is not uniform
+        assert abs(rho5 - rho0) <= 1e-12, (rho0, rho5)
+    finally:
+        eng.close()
+
+    fluid = (0, nx - 1, 1, ny - 2, 0, nz - 1)
+    planes = (0, 1, 2, 681, 682, 683, 684, 1363, 1364, 1365, 1366, 2045, 2046, 2047)
+    res = []
+    for slabs in (1, 3):
+        eng = build(slabs, walls=True)
+        try:
+            eng.collide_and_stream(5)
+            sha = [hashlib.sha256(eng.download((x, x, 0, ny - 1, 0, nz - 1)).tobytes()).hexdigest() for x in planes]
+            res.append((sha, eng.compute_average_density(fluid), eng.compute_average_energy(fluid), eng.stored_statistics()))
+        finally:
+            eng.close()
+    assert res[0][0] == res[1][0], [x for x, a, b in zip(planes, res[0][0], res[1][0]) if a != b]
+    assert abs(res[0][1] - res[1][1]) <= 1e-13 and abs(res[0][2] - res[1][2]) <= 1e-12 * res[0][2]
+    assert res[0][3][3] == res[1][3][3] == nx * (ny - 2) * nz and np.allclose(res[0][3][:3], res[1][3][:3], rtol=1e-10, atol=0)
