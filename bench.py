@@ -53,6 +53,15 @@ WORKLOADS = {
 }
 
 
+def kernel_sources_hash():
+    """sha256 over the sources of the sweep kernel -- the key profiles/traffic.json is valid for"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("lb_core.cuh", "kernels.cuh", "sweep_launch.cuh", "Makefile"):
+        h.update(open(os.path.join(ROOT, "palabos_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
 def cavity_omega(ny):
     nu = U_MAX * ny / RE
     return 1.0 / (3 * nu + 0.5)
@@ -370,18 +379,24 @@ def our_arm(args):
     # is overlapped: the roofline is taken over the sweep launches of one step
     sweep_ms_step = sweep_ms / args.steps
     achieved = cells_local * BYTES_PER_LU / (sweep_ms_step * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes per launch from the ncu --set full capture of this very kernel (tools/ncu_traffic.py writes profiles/traffic.json
+    # together with a hash of the kernel sources): a capture of other sources, size or workload is not this kernel's traffic
+    traffic, traffic_note = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch_512")
-        if n != 512 or args.workload != "cavity":
-            traffic = None                  # measured for the bench line's kernel only
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if n == 512 and args.workload == "cavity":
+            if tj.get("kernel_sources_sha256") == kernel_sources_hash():
+                traffic = tj.get("dram_bytes_per_launch_512")
+            else:
+                traffic_note = "profiles/traffic.json was captured for other kernel sources (%s...): not reported" % str(tj.get("kernel_sources_sha256"))[:12]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "sweep_kernel<%s,%d,%s> (even/odd AA halves averaged)" % ("double" if PREC == "f64" else "float", Q, wl["dyn"]),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": BYTES_PER_LU, "cells_per_launch": cells_local,
-                "launches_per_step": sweep_n / args.steps, "kernel_ms": sweep_ms_step, "kernel_share_of_step": sweep_ms / ms}
+                "launches_per_step": sweep_n / args.steps, "kernel_ms": sweep_ms_step, "kernel_share_of_step": sweep_ms / ms,
+                "traffic_note": traffic_note, "peak_nominal_gbs": 8000.0, "frac_of_nominal": achieved / 8000.0}
 
     # ---- e2e: the same job from host buffers through the C-ABI ----------------------------------
     e2e = None
@@ -399,22 +414,28 @@ def our_arm(args):
         launches_e0 = lat.launch_count()
         t0 = time.perf_counter()
         lat.upload_ptr(host.data_ptr(), nbytes)
+        t1 = time.perf_counter()
         for it in range(k2):
             lat.set_boundary_velocity(lid, (U_MAX * min(1.0, (it + 1) / 50.0), 0, 0))
             lat.collide_and_stream(1)
             lat.stored_statistics()
+        t2 = time.perf_counter()
         lat.download_ptr(host.data_ptr(), nbytes)
         barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        t3 = time.perf_counter()
+        dt = t3 - t0
+        tt = torch.tensor([dt, t1 - t0, t2 - t1, t3 - t2], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        lid_records = (nx - 2) * (ny - 2) if world == 1 else None
+        dt, h2d_s, loop_s, d2h_s = [float(v) for v in tt.tolist()]
         e2e = {"value": cells_global * k2 / dt / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": (nbytes * world) / k2 + (48 * (nx - 2) * (ny - 2)),
+               "h2d_bytes_per_step": (nbytes * world) / k2 + 48 * world,
                "d2h_bytes_per_step": (nbytes * world) / k2 + 32 * world,
                "steps": k2, "seconds": dt, "pinned_host": pinned,
+               # where the time goes (max over ranks each): the two PCIe transfers of the whole lattice, and the time loop whose
+               # every step changes the lid velocity on the device (set_bc_values_kernel), sweeps, and reads the statistics back
+               "h2d_s": h2d_s, "d2h_s": d2h_s, "loop_s": loop_s, "step_ms": loop_s / k2 * 1e3,
+               "h2d_gbs_per_gpu": nbytes / h2d_s / 1e9, "d2h_gbs_per_gpu": nbytes / d2h_s / 1e9,
                "what": "upload initial populations + K x {setBoundaryVelocity(lid), collideAndStream, getStored statistics} + download final populations",
                "launches": lat.launch_count() - launches_e0}
         del host

@@ -472,25 +472,12 @@ public:
     virtual int collideAndStream(int domainHandle) = 0;
 };
 
-/// What global::defaultCoProcessor3D<T>() (coProcessor3D.h:179-186) should return instead of the
-/// commented-out D3Q19CudaCoProcessor3D (coProcessor3D.hh:82-434): see INTEGRATION.md.
-template <typename T>
-class B200CoProcessor3D : public CoProcessor3D<T> {
-public:
-    virtual int addDomain(plint nx, plint ny, plint nz, T omega, int& domainHandle) {
-        return plb_b200_coproc_add_domain((int)sizeof(T), (int)nx, (int)ny, (int)nz, (double)omega, &domainHandle);
-    }
-    virtual int send(int domainHandle, Box3D const& subDomain, std::vector<char> const& data) {
-        detail::CBox b(subDomain);
-        return plb_b200_coproc_send(domainHandle, b.v, data.data(), data.size());
-    }
-    virtual int receive(int domainHandle, Box3D const& subDomain, std::vector<char>& data) const {
-        detail::CBox b(subDomain);
-        data.resize((std::size_t)subDomain.nCells() * 19 * sizeof(T));      // "it is the responsibility of the receive method to resize"
-        return plb_b200_coproc_receive(domainHandle, b.v, data.data(), data.size());
-    }
-    virtual int collideAndStream(int domainHandle) { return plb_b200_coproc_collide_and_stream(domainHandle); }
-};
+}  // namespace plb
+// B200CoProcessor3D<T>: the adapter itself lives in a header of its own, because it is what a maintainer of the REFERENCE includes
+// (it needs nothing but the reference's CoProcessor3D<T>, Box3D and plint; examples/ref_coprocessor.cpp builds it against the
+// unmodified Palabos sources)
+#include "coprocessor_adapter.h"
+namespace plb {
 
 // ------------------------------------------- STL -> voxel flags (offLattice/)
 

@@ -195,6 +195,11 @@ int plb_b200_boundary_stages(plb_b200_lattice* L, int* n_stages, int64_t* n_item
  * atomicBlock/blockLattice3D.hh:257-258,311): switch on, step, read total milliseconds and launches. */
 int plb_b200_profile_sweeps(plb_b200_lattice* L, int on);
 int plb_b200_profile_read(plb_b200_lattice* L, double* total_ms, int* n_launches);
+/* how the envelopes between x-slabs are refreshed in this lattice (a static string; replaces the choice of
+ * BlockCommunicator3D, multiBlock/serialBlockCommunicator3D.cpp / parallelism/parallelBlockCommunicator3D.cpp):
+ * direct stores of the sweep's rim cells into the neighbouring slab (CUDA IPC over NVLink between ranks), or -- with
+ * PLB_B200_HALO=nccl in the environment, or where peer mapping is impossible -- ghost planes + ncclSend/ncclRecv. */
+const char* plb_b200_halo_transport(plb_b200_lattice* L);
 
 /* ---- geometry side of the path: STL -> voxel flags --------------------------------- */
 

@@ -37,7 +37,7 @@ SYMBOLS = [
     "plb_b200_local_bytes", "plb_b200_collide_and_stream", "plb_b200_synchronize",
     "plb_b200_get_stored_statistics", "plb_b200_compute_average_energy", "plb_b200_compute_average_density",
     "plb_b200_compute_density_velocity", "plb_b200_launch_count", "plb_b200_device_bytes",
-    "plb_b200_boundary_stages", "plb_b200_profile_sweeps", "plb_b200_profile_read", "plb_b200_coproc_add_domain", "plb_b200_coproc_send",
+    "plb_b200_boundary_stages", "plb_b200_profile_sweeps", "plb_b200_profile_read", "plb_b200_halo_transport", "plb_b200_coproc_add_domain", "plb_b200_coproc_send",
     "plb_b200_coproc_receive", "plb_b200_coproc_collide_and_stream", "plb_b200_coproc_remove_domain",
     "plb_b200_save_binary_block", "plb_b200_load_binary_block",
     "plb_b200_create_enveloped", "plb_b200_execute_internal_processors", "plb_b200_apply_rhobar_j",
@@ -113,6 +113,8 @@ def lib():
         L.plb_b200_boundary_stages.argtypes = [vp, vp, vp]
         L.plb_b200_profile_sweeps.argtypes = [vp, ci]
         L.plb_b200_profile_read.argtypes = [vp, vp, vp]
+        L.plb_b200_halo_transport.restype = ctypes.c_char_p
+        L.plb_b200_halo_transport.argtypes = [vp]
         L.plb_b200_slab_range.argtypes = [ci, ci, ci, vp, vp]
         L.plb_b200_coproc_add_domain.argtypes = [ci, ci, ci, ci, cd, vp]
         L.plb_b200_coproc_send.argtypes = [ci, vp, vp, ctypes.c_size_t]
@@ -373,6 +375,9 @@ class Lattice:
         ms, n = ctypes.c_double(), ctypes.c_int()
         self._ck(self.lib.plb_b200_profile_read(self.h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def halo_transport(self):
+        return self.lib.plb_b200_halo_transport(self.h).decode()
 
     def save_binary_block(self, path):
         """saveBinaryBlock(lattice, fName): checkpoint file in the reference's format"""

@@ -355,6 +355,7 @@ int plb_b200_boundary_stages(plb_b200_lattice* L, int* nStages, int64_t* nItems)
 
 int plb_b200_profile_sweeps(plb_b200_lattice* L, int on) { PLB_TRY(L, L->impl->profile_sweeps(on != 0)) }
 int plb_b200_profile_read(plb_b200_lattice* L, double* totalMs, int* nLaunches) { PLB_TRY(L, L->impl->profile_read(totalMs, nLaunches)) }
+const char* plb_b200_halo_transport(plb_b200_lattice* L) { return (L && L->impl) ? L->impl->halo_transport() : ""; }
 
 // ---- plb::CoProcessor3D<T> surface (coProcessors/coProcessor3D.h:59-116) -------------------------
 

@@ -65,6 +65,7 @@ public:
     virtual void boundary_stages(int* nStages, int64_t* nItems) = 0;
     virtual void profile_sweeps(bool on) = 0;
     virtual void profile_read(double* totalMs, int* nLaunches) = 0;
+    virtual const char* halo_transport() const = 0;
 };
 
 LatticeBase* make_lattice_f64_q19(const CreateDesc&);

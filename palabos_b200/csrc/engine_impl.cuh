@@ -11,8 +11,11 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <unordered_map>
 #include <vector>
+#include <cuda.h>
 #include "engine.h"
 #include "kernels.cuh"
 #include "sweep_launch.cuh"
@@ -46,8 +49,8 @@ class LatticeImpl : public LatticeBase {
         T* dExt = nullptr;                 ///< external-moment sweep: rhoBar [cellsStore] | j_x | j_y | j_z, zero where nothing writes
         int* dBcCells = nullptr; size_t dBcCellsCap = 0;   ///< ... cells that carry a boundary record (-1: dead record)
         int nBcCells = 0;
-        double* dStats = nullptr;          ///< [3 launches][4]: a step sweeps a slab in up to three launches (5.)
-        int statSlots = 0;                 ///< launches of the last step
+        double* dStats = nullptr;          ///< [4] sum rhoBar, sum uSqr, max uSqr, cell count of the last sweep
+        int statSlots = 0;                 ///< 1 once a sweep has reported
         unsigned int* dTicket = nullptr;
         int nAuto = 0;                     ///< items [0, nAuto): plane cells that complete at collision time (never executed as a stage)
         std::vector<uint8_t> hKind;
@@ -57,9 +60,8 @@ class LatticeImpl : public LatticeBase {
         std::vector<int> stageOffsets;     ///< items of stage s are [stageOffsets[s], stageOffsets[s+1]) ...
         std::vector<int> stageSplit;       ///< ... plane items first, finite-difference items from stageSplit[s]
         size_t nItems = 0;
-        int* dSparse = nullptr; size_t dSparseCap = 0;
-        int nSparse = 0;                   ///< cells listed for the sweep's list blocks (z-face plane cells and their sector mates)
-        std::vector<int> hSparse;          ///< host copy (ascending): a launch over part of the slab takes its sub-range
+        unsigned int* dRimTicket = nullptr; ///< counts the rim tiles of a launch that signals a neighbouring rank
+        bool valuesOnDevice = false;       ///< the records on the device hold newer u / rhoBar than `recs` (set_values_on_device)
         bool dirtyKind = true, dirtyBcIndex = true, dirtySched = true;
         bool kindUnflagged = true;         ///< dKind was uploaded from hKind and carries no KIND_PLANE flags
         int bcDirtyLo = 0, bcDirtyHi = 0;  ///< record range whose values must be re-uploaded
@@ -103,10 +105,16 @@ class LatticeImpl : public LatticeBase {
 
     static constexpr size_t STAGE_BYTES = size_t(256) << 20;
     static constexpr size_t XFER_CHUNK_BYTES = size_t(64) << 20;   ///< one of the two upload/download staging halves
-    cudaStream_t commStream_ = nullptr;      ///< envelope exchange, overlapped with the sweep of the interior planes
-    cudaEvent_t rimDone_ = nullptr, commDone_ = nullptr;
-    int overlap_ = -1;                       ///< overlap the exchange with the interior sweep (default); PLB_B200_OVERLAP=0 in the
-                                             ///< environment: one launch per slab, exchange afterwards (A/B tests)
+    // envelope exchange (section 5 of DESIGN.md).  direct_: the rim cells of the sweep store the face-crossing populations straight
+    // into the neighbouring slab -- a slab of this process, or (remote*_) the slab of the neighbouring rank mapped through
+    // CUDA IPC, with one step counter per face direction written by the last rim tile and awaited by a stream memory
+    // operation.  !direct_ (PLB_B200_HALO=nccl, or peer mapping impossible): ghost planes, cudaMemcpy / NCCL send/recv, unpack.
+    bool direct_ = true;
+    struct Remote { T* F = nullptr; long long S = 0; int nxl = 0; unsigned int* flag = nullptr; };
+    Remote remoteLo_, remoteHi_;             ///< last slab of rank-1 / first slab of rank+1 (ring), and the flag of theirs this rank writes
+    unsigned int* dFlags_ = nullptr;         ///< [0]: step count of the neighbour below, [32]: of the neighbour above (128 bytes apart)
+    unsigned int stepCount_ = 0;
+    std::map<std::string, void*> ipcOpened_; ///< CUDA IPC mappings by handle (an allocation can be opened once per process)
     cudaStream_t copyStream_ = nullptr;
     cudaEvent_t copied_[2] = {nullptr, nullptr}, transposed_[2] = {nullptr, nullptr};
 
@@ -122,7 +130,7 @@ public:
         if (G_ > nx_) throw PlbError("more slabs than x-planes");
         if ((long long)ny_ * nz_ >= (1ll << 30)) throw PlbError("y-z plane too large");
         if (const char* e = std::getenv("PLB_B200_EAGER_PLANES")) allowFuse_ = !(e[0] == '1');
-        if (const char* e = std::getenv("PLB_B200_OVERLAP")) overlap_ = e[0] == '1' ? 1 : (e[0] == '0' ? 0 : -1);
+        if (const char* e = std::getenv("PLB_B200_HALO")) direct_ = !(std::strcmp(e, "nccl") == 0 || std::strcmp(e, "copy") == 0);
         if (const char* e = std::getenv("PLB_B200_EXT_EXPLICIT")) extFuse_ = !(e[0] == '1');
         add_dyn(d.dynamics, d.p1, d.p2);     // entry 0: the background dynamics
         for (int s = 0; s < d.slabsPerRank; ++s) {
@@ -141,7 +149,9 @@ public:
             PLB_CUDA(cudaMemsetAsync(sl.F, 0, nF * sizeof(T), stream_));
             sl.dKind = (uint8_t*)dev_alloc(sl.cellsStore);
             sl.dBcIdx = (int*)dev_alloc(sl.cellsStore * sizeof(int));
-            sl.dStats = (double*)dev_alloc(3 * 4 * sizeof(double));
+            sl.dStats = (double*)dev_alloc(4 * sizeof(double));
+            sl.dRimTicket = (unsigned int*)dev_alloc(sizeof(unsigned int));
+            PLB_CUDA(cudaMemsetAsync(sl.dRimTicket, 0, sizeof(unsigned int), stream_));
             sl.dTicket = (unsigned int*)dev_alloc(sizeof(unsigned int));
             PLB_CUDA(cudaMemsetAsync(sl.dTicket, 0, sizeof(unsigned int), stream_));
             sl.hKind.assign((size_t)sl.cellsStore, 0);
@@ -152,14 +162,19 @@ public:
 
     ~LatticeImpl() override {
         cudaStreamSynchronize(stream_);
+        if (!ipcOpened_.empty()) {
+            // nobody frees storage a neighbour still has mapped: unmap, meet, free
+            for (auto& kv : ipcOpened_) cudaIpcCloseMemHandle(kv.second);
+            try { double one = 1.; all_reduce(&one, 1, false); } catch (...) {}
+        }
+        cudaFree(dFlags_);
         for (Slab& sl : slabs_) {
-            cudaFree(sl.F); cudaFree(sl.dExt); cudaFree(sl.dBcCells); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems); cudaFree(sl.dSparse);
-            cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket);
+            cudaFree(sl.F); cudaFree(sl.dExt); cudaFree(sl.dBcCells); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems);
+            cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket); cudaFree(sl.dRimTicket);
         }
         cudaFree(dDyns_); cudaFree(dStage_); cudaFree(dReduce_);
         if (comm_) NcclApi::get().CommDestroy(comm_);
         for (cudaEvent_t e : profEvents_) cudaEventDestroy(e);
-        if (commStream_) { cudaStreamDestroy(commStream_); cudaEventDestroy(rimDone_); cudaEventDestroy(commDone_); }
         if (copyStream_) {
             cudaStreamDestroy(copyStream_);
             for (int k = 0; k < 2; ++k) { cudaEventDestroy(copied_[k]); cudaEventDestroy(transposed_[k]); }
@@ -175,6 +190,13 @@ public:
         static_assert(sizeof(uid) == 128, "ncclUniqueId is 128 bytes");
         std::memcpy(&uid, id, 128);
         n.check(n.CommInitRank(&comm_, desc_.nRanks, uid, desc_.rank), "ncclCommInitRank");
+        map_neighbours();
+    }
+    const char* halo_transport() const override {
+        if (G_ == 1) return "none (one slab)";
+        if (!direct_) return desc_.nRanks > 1 ? "ghost planes: ncclSend/ncclRecv + unpack" : "ghost planes: cudaMemcpy + unpack";
+        return desc_.nRanks > 1 ? "direct stores of the rim cells into the neighbour's slab (CUDA IPC over NVLink), one flag per face"
+                                : "direct stores of the rim cells into the neighbouring slab";
     }
     void set_stream(cudaStream_t s) override { PLB_CUDA(cudaStreamSynchronize(stream_)); stream_ = s; }
     void synchronize() override { PLB_CUDA(cudaStreamSynchronize(stream_)); }
@@ -324,6 +346,7 @@ public:
     void set_boundary_velocity(const int box[6], const double u[3]) override {
         check_box(box);
         const T v[3] = {(T)u[0], (T)u[1], (T)u[2]};
+        if (set_values_on_device(box, 0, v, (T)0)) return;
         for_records_in(box, [&](Bc<T>& b) {
             if (L::is_rho_plane(b.kind)) return false;
             if (std::memcmp(b.u, v, sizeof v) == 0) return false;      // unchanged: nothing to re-upload
@@ -335,6 +358,8 @@ public:
     void set_boundary_density(const int box[6], double rho) override {
         check_box(box);
         const T rb = (T)rho - (T)1;
+        const T none[3] = {(T)0, (T)0, (T)0};
+        if (set_values_on_device(box, 1, none, rb)) return;
         for_records_in(box, [&](Bc<T>& b) {
             if (!L::is_rho_plane(b.kind)) return false;
             if (std::memcmp(&b.rhoBar, &rb, sizeof rb) == 0) return false;
@@ -552,43 +577,15 @@ public:
     void advance_steps(int n, bool ext) {
         for (int s = 0; s < n; ++s) {
             if (ext && !(extImplied_ && extFuse_)) materialize();   // the stored-fields sweep has no completion on load
-            // measured at 512^3 per GPU on 2 B200s: 7.18 ms per step overlapped against 7.26 (the split costs 0.03 ms of sweep time)
-            const bool overlap = G_ > 1 && overlap_ != 0;
-            if (!overlap) {
-                for (Slab& sl : slabs_) { launch_sweep(sl, 1, sl.nxl, 0); sl.statSlots = 1; }
-                swapped_ = !swapped_;
-                pending_ = false;              // the sweep has applied the outstanding completion
-                exchange_copies(stream_);
-            } else {
-                // the two planes next to the slab faces first; their face-crossing populations travel on the
-                // communication stream while the interior planes are swept
-                if (!commStream_) {
-                    // highest priority: the copy kernels must get SMs while the interior sweep still has blocks to place
-                    int prLow = 0, prHigh = 0;
-                    PLB_CUDA(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
-                    PLB_CUDA(cudaStreamCreateWithPriority(&commStream_, cudaStreamNonBlocking, prHigh));
-                    PLB_CUDA(cudaEventCreateWithFlags(&rimDone_, cudaEventDisableTiming));
-                    PLB_CUDA(cudaEventCreateWithFlags(&commDone_, cudaEventDisableTiming));
-                }
-                for (Slab& sl : slabs_) {
-                    sl.statSlots = 0;
-                    launch_sweep(sl, 1, 1, sl.statSlots++);
-                    if (sl.nxl > 1) launch_sweep(sl, sl.nxl, sl.nxl, sl.statSlots++);
-                }
-                PLB_CUDA(cudaEventRecord(rimDone_, stream_));
-                PLB_CUDA(cudaStreamWaitEvent(commStream_, rimDone_, 0));
-                const bool wasPending = pending_;
-                swapped_ = !swapped_;
-                exchange_copies(commStream_);
-                PLB_CUDA(cudaEventRecord(commDone_, commStream_));
-                swapped_ = !swapped_;          // the interior launches still belong to the old layout
-                pending_ = wasPending;
-                for (Slab& sl : slabs_)
-                    if (sl.nxl > 2) launch_sweep(sl, 2, sl.nxl - 1, sl.statSlots++);
-                swapped_ = !swapped_;
-                pending_ = false;
-                PLB_CUDA(cudaStreamWaitEvent(stream_, commDone_, 0));
-            }
+            // One launch per slab: rim planes first (their stores go to the neighbouring slab), then the interior.  With the
+            // direct transport nothing else is needed -- the neighbour reads what was stored into it one step later; the wait
+            // below only orders this rank's NEXT accesses to its rim / ghost planes after the neighbours' stores of THIS step.
+            ++stepCount_;
+            for (Slab& sl : slabs_) { launch_sweep(sl); sl.statSlots = 1; }
+            swapped_ = !swapped_;
+            pending_ = false;                  // the sweep has applied the outstanding completion
+            if (direct_) wait_neighbours();
+            else exchange_copies(stream_);
             exchange_unpack();
             run_processors();
             if (ext) {
@@ -615,11 +612,11 @@ public:
         if (stepped_ && statsOn_) {
             PLB_CUDA(cudaStreamSynchronize(stream_));
             for (Slab& sl : slabs_) {
-                double h[12];
+                double h[4];
                 PLB_CUDA(cudaMemcpy(h, sl.dStats, sizeof h, cudaMemcpyDeviceToHost));
-                for (int k = 0; k < sl.statSlots; ++k) {
-                    sum[0] += h[4 * k]; sum[1] += h[4 * k + 1]; sum[2] += h[4 * k + 3];
-                    mx = std::max(mx, h[4 * k + 2]);
+                if (sl.statSlots > 0) {
+                    sum[0] += h[0]; sum[1] += h[1]; sum[2] += h[3];
+                    mx = std::max(mx, h[2]);
                 }
             }
         }
@@ -738,6 +735,7 @@ private:
         CellCtx<T> c;
         c.F = sl.F; c.kind = sl.dKind; c.bcIdx = sl.dBcIdx; c.dyns = dDyns_; c.bcs = sl.dBcs;
         c.g = geo(sl); c.swapped = swapped_; c.pending = pending_;
+        c.pendingStamp = (int)(stepCount_ + 1);     // the next sweep applies what is pending now
         return c;
     }
 
@@ -811,8 +809,69 @@ private:
         for (Slab& sl : slabs_) sl.dirtySched = true;
     }
 
+    /// The time loop's form of setBoundaryVelocity / setBoundaryDensity: when the set-up on the device is current (no dynamics,
+    /// boundary or schedule change outstanding) the values are changed THERE, by one small kernel over the box -- no walk over
+    /// the host records, no upload, and the pending plane completion stays pending (it answers with the previous values,
+    /// Bc::stamp).  The host records are refreshed from the device before they are needed again (pull_record_values).
+    bool set_values_on_device(const int box[6], int what, const T u[3], T rhoBar) {
+        if (!stepped_ && !ext_) return false;                 // set-up phase: the host path batches everything into one upload
+        if (dirtyDyns_) return false;
+        for (Slab& sl : slabs_)
+            if (sl.dirtyKind || sl.dirtyBcIndex || sl.dirtySched || sl.bcDirtyHi > sl.bcDirtyLo || sl.kindUnflagged) return false;
+        if (ext_ && !extComplete_ && !extBcStored_) {
+            // the implied moments of the boundary cells are functions of the records about to change: store them first
+            for (Slab& sl : slabs_) {
+                if (sl.nBcCells == 0) continue;
+                rhobar_j_list_kernel<T, Q><<<(sl.nBcCells + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.dBcCells, sl.nBcCells, sl.dExt, sl.cellsStore);
+                launched();
+            }
+            extBcStored_ = true;
+        }
+        for (Slab& sl : slabs_) {
+            if (sl.nBcCells == 0) continue;
+            // owned planes, and the ghost planes (their records answer the neighbour reads of the edge / corner processors)
+            BoxL parts[3];
+            int nParts = 0;
+            if (local_box(sl, box, parts[nParts])) ++nParts;
+            for (int X : {0, sl.nxl + 1}) {
+                const int gx = global_x(sl, X);
+                if (gx < box[0] || gx > box[1]) continue;
+                BoxL& b = parts[nParts++];
+                b.X0 = b.X1 = X; b.y0 = box[2]; b.y1 = box[3]; b.z0 = box[4]; b.z1 = box[5];
+            }
+            for (int k = 0; k < nParts; ++k) {
+                const long long n = parts[k].cells();
+                set_bc_values_kernel<T, Q><<<(unsigned)((n + 127) / 128), 128, 0, stream_>>>(
+                    sl.dBcIdx, sl.dBcs, geo(sl), parts[k], what, u[0], u[1], u[2], rhoBar, (int)(stepCount_ + 1));
+                launched();
+            }
+            sl.valuesOnDevice = true;
+        }
+        return true;
+    }
+
+    /// the device holds newer record values than the host (set_values_on_device): fetch them before the host records are changed
+    /// or uploaded again
+    void pull_record_values() {
+        for (Slab& sl : slabs_) {
+            if (!sl.valuesOnDevice) continue;
+            const size_t n = std::min<size_t>(sl.recs.size(), (size_t)sl.nBcCells);
+            std::vector<Bc<T>> vals(n);
+            if (n) {
+                PLB_CUDA(cudaMemcpyAsync(vals.data(), sl.dBcs, n * sizeof(Bc<T>), cudaMemcpyDeviceToHost, stream_));
+                PLB_CUDA(cudaStreamSynchronize(stream_));
+            }
+            for (size_t r = 0; r < n; ++r) {
+                Bc<T>& b = sl.recs[r].b;
+                b.u[0] = vals[r].u[0]; b.u[1] = vals[r].u[1]; b.u[2] = vals[r].u[2]; b.rhoBar = vals[r].rhoBar;
+            }
+            sl.valuesOnDevice = false;
+        }
+    }
+
     template <class Fn>
     void for_records_in(const int box[6], Fn fn) {
+        pull_record_values();
         for (Slab& sl : slabs_)
             for (const Group& grp : sl.groups) {
                 int tmp[6];
@@ -938,36 +997,6 @@ private:
         // count[2*stage + (0|1)] as before; the cells the sweep completes on load: the automatic ones if the lattice has
         // any (the wrapped ones then run eagerly), else the wrapped plane items of stage 0
         const int* count = count0.data() + 1;
-        const int flagLo = autoPlanes_ ? 0 : (nStages > 0 ? count[0] : 0), flagHi = autoPlanes_ ? sl.nAuto : (nStages > 0 ? count[1] : 0);
-        // stage-0 plane cells that do not (nearly) fill the 32-cell piece a warp of the sweep covers -- one
-        // per warp on a z-face -- are listed for the sweep's list blocks together with the cells that
-        // share their sector; see sweep_kernel
-        std::vector<int> sparse;
-        if (flagHi > flagLo) {
-            std::unordered_map<int, int> perPiece;
-            for (int k = flagLo; k < flagHi; ++k) ++perPiece[(sorted[k].cell - P_) / 32];
-            const int G = PLB_SPARSE_GROUP;
-            const int lo = P_, hi = (sl.nxl + 1) * P_;
-            for (int k = flagLo; k < flagHi; ++k) {
-                const int cell = sorted[k].cell;
-                if (perPiece[(cell - P_) / 32] >= 16) continue;
-                const int g0 = cell / G * G;
-                for (int c2 = std::max(g0, lo); c2 < std::min(g0 + G, hi); ++c2) sparse.push_back(c2);
-            }
-            std::sort(sparse.begin(), sparse.end());
-            sparse.erase(std::unique(sparse.begin(), sparse.end()), sparse.end());
-        }
-        sl.nSparse = (int)sparse.size();
-        sl.hSparse = sparse;
-        if (sparse.size() > sl.dSparseCap) {
-            if (sl.dSparse) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dSparse); devBytes_ -= sl.dSparseCap * sizeof(int); }
-            sl.dSparse = (int*)dev_alloc(sparse.size() * sizeof(int));
-            sl.dSparseCap = sparse.size();
-        }
-        if (!sparse.empty()) {
-            PLB_CUDA(cudaMemcpyAsync(sl.dSparse, sparse.data(), sparse.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
-            PLB_CUDA(cudaStreamSynchronize(stream_));
-        }
         sl.stageOffsets.assign(nStages + 1, 0);
         sl.stageSplit.assign(nStages, 0);
         for (int st = 0; st < nStages; ++st) { sl.stageOffsets[st] = count[2 * st]; sl.stageSplit[st] = count[2 * st + 1]; }
@@ -1006,6 +1035,7 @@ private:
         for (Slab& sl : slabs_) anyDirty = anyDirty || sl.dirtyKind || sl.dirtyBcIndex || sl.dirtySched || sl.bcDirtyHi > sl.bcDirtyLo;
         if (!anyDirty) return;
         materialize();                         // with the device state the completion was deferred under
+        pull_record_values();
         bool reflag = false;
         bool structural = false;               // (external-moment sweep) which cells read their moments from the fields may have changed
         for (Slab& sl : slabs_) structural = structural || sl.dirtyKind || sl.dirtyBcIndex || sl.dirtySched;
@@ -1105,10 +1135,6 @@ private:
                 if (n > 0) {
                     flag_plane_cells_kernel<<<(n + 255) / 256, 256, 0, stream_>>>(sl.dItems + first, n, sl.dKind);
                     launched();
-                    if (sl.nSparse > 0) {
-                        flag_sparse_cells_kernel<<<(sl.nSparse + 255) / 256, 256, 0, stream_>>>(sl.dSparse, sl.nSparse, sl.dKind);
-                        launched();
-                    }
                 }
             }
         }
@@ -1136,11 +1162,27 @@ private:
     template <int MAIN, bool GEN, bool ODD, bool PLANES>
     void launch_sweep_with(Slab& sl, SweepArgs<T>& a, int mainIdx) {
         constexpr int threads = sweep_threads(ODD);
-        const int nTiles = (a.cellEnd - a.cellBegin + threads - 1) / threads;
-        int grid = std::max(1, std::min(nTiles, numSMs_ * sweep_grid_factor(ODD)));
         (void)mainIdx;
-        a.nListBlocks = PLANES ? (a.nSparse + threads - 1) / threads : 0;
-        grid += a.nListBlocks;
+        // tile sequence: the planes next to a slab that takes direct stores first, then the rest
+        const int lowEnd = a.lo.F ? 2 * P_ : P_, end = (sl.nxl + 1) * P_;
+        const int highBegin = a.hi.F ? std::max(sl.nxl * P_, lowEnd) : end;
+        a.nRanges = 0; a.nTiles = 0;
+        auto add = [&](int b, int e) {
+            if (e <= b) return;
+            a.range[a.nRanges].begin = b; a.range[a.nRanges].end = e; a.range[a.nRanges].tile0 = a.nTiles;
+            a.nTiles += (e - b + threads - 1) / threads;
+            ++a.nRanges;
+        };
+        for (int k = 0; k < 3; ++k) { a.range[k].begin = a.range[k].end = a.range[k].tile0 = 0; }
+        add(P_, lowEnd);
+        add(highBegin, end);
+        a.nRimTiles = (a.sigLo || a.sigHi) ? a.nTiles : 0;
+        add(lowEnd, highBegin);
+        // blocks per SM in the grid: the measured optimum (kernels.cuh), or PLB_B200_GRID_EVEN / PLB_B200_GRID_ODD (tuning runs)
+        static const int gfEnv[2] = {std::getenv("PLB_B200_GRID_EVEN") ? std::atoi(std::getenv("PLB_B200_GRID_EVEN")) : 0,
+                                     std::getenv("PLB_B200_GRID_ODD") ? std::atoi(std::getenv("PLB_B200_GRID_ODD")) : 0};
+        const int gf = gfEnv[ODD ? 1 : 0] > 0 ? gfEnv[ODD ? 1 : 0] : sweep_grid_factor(ODD);
+        const int grid = std::max(1, std::min(a.nTiles, numSMs_ * gf));
         if (grid > sl.partialsCap) {
             if (sl.dPartials) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dPartials); devBytes_ -= (size_t)sl.partialsCap * 4 * sizeof(double); }
             sl.partialsCap = std::max(grid, numSMs_ * 16);
@@ -1157,22 +1199,41 @@ private:
         if (prof) { PLB_CUDA(cudaEventRecord(profEvents_[profUsed_ + 1], stream_)); profUsed_ += 2; }
     }
 
-    /// sweep the planes X0..X1 of a slab; `slot`: which statistics slot of the slab this launch reports to
-    void launch_sweep(Slab& sl, int X0, int X1, int slot) {
+    /// the slab on the other side of a face of `sl`, if the rim cells store into it directly
+    void peers_of(const Slab& sl, const Geo& g, SweepArgs<T>& a) {
+        a.lo.F = a.hi.F = nullptr; a.lo.S = a.hi.S = 0; a.lo.nxl = a.hi.nxl = 0;
+        a.sigLo = a.sigHi = nullptr;
+        if (!direct_ || G_ == 1) return;
+        auto local = [&](int gIdx, PeerSlab<T>& p) {
+            Slab* o = find_slab(gIdx);
+            if (!o) return false;
+            p.F = o->F; p.S = o->cellsStore; p.nxl = o->nxl;
+            return true;
+        };
+        if (g.lowMode == XMODE_GHOST && !local((sl.g - 1 + G_) % G_, a.lo)) {
+            a.lo.F = remoteLo_.F; a.lo.S = remoteLo_.S; a.lo.nxl = remoteLo_.nxl; a.sigLo = remoteLo_.flag;
+        }
+        if (g.highMode == XMODE_GHOST && !local((sl.g + 1) % G_, a.hi)) {
+            a.hi.F = remoteHi_.F; a.hi.S = remoteHi_.S; a.hi.nxl = remoteHi_.nxl; a.sigHi = remoteHi_.flag;
+        }
+        if ((g.lowMode == XMODE_GHOST && !a.lo.F) || (g.highMode == XMODE_GHOST && !a.hi.F))
+            throw PlbError("the neighbouring rank's slab is not mapped (plb_b200_comm_init)");
+    }
+
+    /// sweep a slab
+    void launch_sweep(Slab& sl) {
         SweepArgs<T> a;
         a.F = sl.F; a.kind = sl.dKind; a.dyns = dDyns_; a.g = geo(sl);
         a.bcIdx = sl.dBcIdx; a.bcs = sl.dBcs;
         a.applyPlanes = ((pending_ && sl.stageOffsets.size() >= 2 && sl.stageSplit[0] > sl.stageOffsets[0]) || sl.nAuto > 0) ? 1 : 0;
-        a.cellBegin = X0 * P_; a.cellEnd = (X1 + 1) * P_;
-        a.sparseCells = sl.dSparse; a.nSparse = 0; a.nListBlocks = 0;
-        if (a.applyPlanes && sl.nSparse > 0) {
-            const int lo = (int)(std::lower_bound(sl.hSparse.begin(), sl.hSparse.end(), a.cellBegin) - sl.hSparse.begin());
-            const int hi = (int)(std::lower_bound(sl.hSparse.begin(), sl.hSparse.end(), a.cellEnd) - sl.hSparse.begin());
-            a.sparseCells = sl.dSparse + lo; a.nSparse = hi - lo;
-        }
+        // wrapped planes: the completion applied on load belongs to the step before (values as of then); planes that complete at
+        // collision time (dynamics-based managers) take the current values
+        a.pendingStamp = sl.nAuto > 0 ? -1 : (int)stepCount_;
+        peers_of(sl, a.g, a);
+        a.rimTicket = sl.dRimTicket; a.sigValue = stepCount_; a.nRimTiles = 0;
         a.omega = dyns_[0].omega; a.preFactor = dyns_[0].preFactor;
         a.gatherStats = statsOn_ ? 1 : 0;
-        a.partials = nullptr; a.ticket = sl.dTicket; a.statsOut = sl.dStats + 4 * slot;
+        a.partials = nullptr; a.ticket = sl.dTicket; a.statsOut = sl.dStats;
         a.ext = sl.dExt; a.extStride = sl.cellsStore; a.extBcFromFields = 1;
         if (ext_) {
             // the statistics of this mode are never evaluated by the reference's loop (executeInternalProcessors + incrementTime)
@@ -1225,7 +1286,128 @@ private:
         }
     }
 
-    /// Envelope exchange (replaces BlockCommunicator3D::duplicateOverlaps, multiBlock/serialBlockCommunicator3D.cpp:44-95
+    // ------------------------------------------------------------------ direct envelope exchange
+
+    /// driver entry points resolved through the runtime (no link-time dependency on libcuda)
+    struct DriverApi {
+        CUresult (*MemGetAddressRange)(CUdeviceptr*, size_t*, CUdeviceptr) = nullptr;
+        CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+        static DriverApi& get() {
+            static DriverApi api = load();
+            return api;
+        }
+        static DriverApi load() {
+            DriverApi a;
+            cudaDriverEntryPointQueryResult st;
+            void* fn = nullptr;
+            if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+                a.MemGetAddressRange = reinterpret_cast<decltype(a.MemGetAddressRange)>(fn);
+            fn = nullptr;
+            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+                a.StreamWaitValue32 = reinterpret_cast<decltype(a.StreamWaitValue32)>(fn);
+            cudaGetLastError();
+            return a;
+        }
+    };
+
+    /// what a rank tells its ring neighbours about the two slabs they store into
+    struct FaceExport {
+        cudaIpcMemHandle_t hFirst, hLast, hFlags;
+        unsigned long long offFirst, offLast, offFlags;
+        long long SFirst, SLast;
+        int nxlFirst, nxlLast;
+        int ok;
+    };
+
+    static void ipc_export(void* ptr, cudaIpcMemHandle_t& h, unsigned long long& off) {
+        DriverApi& d = DriverApi::get();
+        if (!d.MemGetAddressRange) throw PlbError("cuMemGetAddressRange is not available");
+        CUdeviceptr base = 0; size_t size = 0;
+        if (d.MemGetAddressRange(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS) throw PlbError("cuMemGetAddressRange failed");
+        // (a small cudaMalloc may be carved out of a larger block: the handle names the block, the mapping starts at its base)
+        PLB_CUDA(cudaIpcGetMemHandle(&h, (void*)base));
+        off = (unsigned long long)((CUdeviceptr)ptr - base);
+    }
+    void* ipc_open(const cudaIpcMemHandle_t& h, unsigned long long off) {
+        const std::string key((const char*)&h, sizeof h);
+        auto it = ipcOpened_.find(key);
+        void* base = nullptr;
+        if (it != ipcOpened_.end()) base = it->second;
+        else {
+            PLB_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            ipcOpened_[key] = base;
+        }
+        return (char*)base + off;
+    }
+
+    /// After ncclCommInitRank: map the slabs of the two ring neighbours (rank - 1: its last slab; rank + 1: its first) and their
+    /// flag words into this process (CUDA IPC; across GPUs the mapping is peer memory over NVLink / NVSwitch), so that the rim
+    /// cells of the sweep store straight into them.  If any rank cannot, all ranks fall back to the copy-based exchange.
+    void map_neighbours() {
+        NcclApi& nc = NcclApi::get();
+        const int R = desc_.nRanks;
+        FaceExport mine;
+        std::memset(&mine, 0, sizeof mine);
+        if (direct_) {
+            try {
+                if (!DriverApi::get().StreamWaitValue32) throw PlbError("cuStreamWaitValue32 is not available");
+                dFlags_ = (unsigned int*)dev_alloc(64 * sizeof(unsigned int));
+                PLB_CUDA(cudaMemsetAsync(dFlags_, 0, 64 * sizeof(unsigned int), stream_));
+                Slab& first = slabs_.front();
+                Slab& last = slabs_.back();
+                ipc_export(first.F, mine.hFirst, mine.offFirst);
+                ipc_export(last.F, mine.hLast, mine.offLast);
+                ipc_export(dFlags_, mine.hFlags, mine.offFlags);
+                mine.SFirst = first.cellsStore; mine.SLast = last.cellsStore; mine.nxlFirst = first.nxl; mine.nxlLast = last.nxl;
+                mine.ok = 1;
+            } catch (const std::exception&) { mine.ok = 0; }
+        }
+        FaceExport* dAll = (FaceExport*)dev_alloc((size_t)R * sizeof(FaceExport));
+        std::vector<FaceExport> all((size_t)R);
+        PLB_CUDA(cudaMemcpyAsync(dAll + desc_.rank, &mine, sizeof mine, cudaMemcpyHostToDevice, stream_));
+        nc.check(nc.AllGather(dAll + desc_.rank, dAll, sizeof(FaceExport), ncclInt8, comm_, stream_), "ncclAllGather");
+        PLB_CUDA(cudaMemcpyAsync(all.data(), dAll, (size_t)R * sizeof(FaceExport), cudaMemcpyDeviceToHost, stream_));
+        PLB_CUDA(cudaStreamSynchronize(stream_));
+        cudaFree(dAll); devBytes_ -= (size_t)R * sizeof(FaceExport);
+        double ok = 1.;
+        for (const FaceExport& e : all) if (!e.ok) ok = 0.;
+        if (ok != 0.) {
+            try {
+                const FaceExport& lo = all[(size_t)((desc_.rank - 1 + R) % R)];
+                const FaceExport& hi = all[(size_t)((desc_.rank + 1) % R)];
+                remoteLo_.F = (T*)ipc_open(lo.hLast, lo.offLast); remoteLo_.S = lo.SLast; remoteLo_.nxl = lo.nxlLast;
+                remoteLo_.flag = (unsigned int*)ipc_open(lo.hFlags, lo.offFlags) + 32;     // I am its neighbour ABOVE
+                remoteHi_.F = (T*)ipc_open(hi.hFirst, hi.offFirst); remoteHi_.S = hi.SFirst; remoteHi_.nxl = hi.nxlFirst;
+                remoteHi_.flag = (unsigned int*)ipc_open(hi.hFlags, hi.offFlags);          // I am its neighbour BELOW
+            } catch (const std::exception&) { ok = 0.; cudaGetLastError(); }
+        }
+        all_reduce(&ok, 1, false);
+        if (ok != (double)R) {          // somebody could not: everybody copies
+            for (auto& kv : ipcOpened_) cudaIpcCloseMemHandle(kv.second);
+            ipcOpened_.clear();
+            remoteLo_ = Remote(); remoteHi_ = Remote();
+            direct_ = false;
+        }
+    }
+
+    /// The neighbouring ranks' stores of the step just launched have landed in this rank's rim / ghost planes: everything
+    /// this rank enqueues from here on (boundary processors, the next sweep, downloads) comes after them.  Normally the
+    /// flags are long there -- the neighbours store within the first ~50 us of their sweep, this point lies after the whole of ours.
+    void wait_neighbours() {
+        if (desc_.nRanks == 1 || G_ == 1) return;
+        DriverApi& d = DriverApi::get();
+        const Geo gFirst = geo(slabs_.front()), gLast = geo(slabs_.back());
+        if (gFirst.lowMode == XMODE_GHOST && !find_slab((slabs_.front().g - 1 + G_) % G_)) {
+            if (d.StreamWaitValue32((CUstream)stream_, (CUdeviceptr)(dFlags_ + 0), stepCount_, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                throw PlbError("cuStreamWaitValue32 failed");
+        }
+        if (gLast.highMode == XMODE_GHOST && !find_slab((slabs_.back().g + 1) % G_)) {
+            if (d.StreamWaitValue32((CUstream)stream_, (CUdeviceptr)(dFlags_ + 32), stepCount_, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                throw PlbError("cuStreamWaitValue32 failed");
+        }
+    }
+
+    /// Copy-based envelope exchange, the fallback (replaces BlockCommunicator3D::duplicateOverlaps, multiBlock/serialBlockCommunicator3D.cpp:44-95
     /// and parallelism/parallelBlockCommunicator3D.cpp:251-297).  Only the populations that cross the slab
     /// face travel -- those with c_x = -1 or c_x = +1 (5 of 19, 9 of 27) -- and each is one contiguous
     /// y-z plane of one slot of the SoA storage, so nothing is packed.  Across the face between slab g
@@ -1284,7 +1466,7 @@ private:
 
     /// second half of the exchange after an odd step (on the lattice's stream, once the copies have arrived)
     void exchange_unpack() {
-        if (G_ == 1) return;
+        if (G_ == 1 || direct_) return;
         if (!swapped_) {
             for (Slab& sl : slabs_) {
                 const Geo g = geo(sl);

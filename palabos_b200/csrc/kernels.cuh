@@ -68,14 +68,7 @@ enum XMode : int { XMODE_EDGE = 0, XMODE_GHOST = 1, XMODE_WRAP = 2 };
 /// Per-cell kind byte: bits 0-5 = index into the dynamics table, bit 7 = the cell carries a plane
 /// boundary record whose completePopulations is fused into the sweep (see "lazy completion" below).
 constexpr int KIND_MASK = 0x3f;
-constexpr int KIND_SPARSE = 0x40;   ///< the cell is processed by the list blocks of the sweep while a completion is pending
 constexpr int KIND_PLANE = 0x80;
-#ifndef PLB_LIST_PLACEMENT
-#define PLB_LIST_PLACEMENT 1        ///< list blocks: 0 interleaved with the streaming blocks, 1 after them, 2 before them
-#endif
-#ifndef PLB_SPARSE_GROUP
-#define PLB_SPARSE_GROUP 4          ///< cells per listed group (4 doubles = one 32-byte sector)
-#endif
 
 struct Geo {
     int nxl, ny, nz;      ///< owned planes, rows, columns
@@ -245,6 +238,20 @@ struct Item {
     signed char a, b, c; ///< edge: plane, normal1, normal2; corner: xNormal, yNormal, zNormal
 };
 
+/// The slab on the other side of a slab face (envelope exchange).  The rim cells of the sweep store the
+/// populations that cross the face straight into that slab's storage: another slab of this process, or the slab of another
+/// rank mapped through CUDA IPC -- the stores then travel over NVLink while the rest of the sweep runs.  F == nullptr: no
+/// slab there, or the copy-based transport (ghost planes + NCCL send/recv + unpack_halo_kernel) is in use.
+template <class T>
+struct PeerSlab {
+    T* F;
+    long long S;         ///< its slot stride
+    int nxl;             ///< its number of owned planes
+};
+
+/// cells [begin, end) of a launch, processed as tiles tile0, tile0 + 1, ... of the launch's tile sequence
+struct TileRange { int begin, end, tile0; };
+
 template <class T>
 struct SweepArgs {
     T* F;
@@ -253,10 +260,10 @@ struct SweepArgs {
     const int* bcIdx;         ///< boundary record index per cell (read for KIND_PLANE cells only)
     const Bc<T>* bcs;         ///< boundary records
     int applyPlanes;          ///< the plane completion of the previous step is pending: apply it on load
-    const int* sparseCells;   ///< KIND_SPARSE cells, processed by nListBlocks blocks spread over the grid
-    int nSparse, nListBlocks;
+    int pendingStamp;         ///< ... under the record values it was deferred with (complete_pending); -1: the current ones
     Geo g;
-    int cellBegin, cellEnd;   ///< storage cell range [begin, end) swept by this launch
+    TileRange range[3];       ///< the planes next to a neighbouring slab first (their stores have the longest way), then the rest
+    int nRanges, nTiles;
     T omega, preFactor;       ///< parameters of dynamics-table entry 0 (the lattice's background dynamics)
     int gatherStats;          ///< BlockStatistics on/off (MultiBlock3D::toggleInternalStatistics)
     double* partials;         ///< [gridDim.x][4] per-block partial sums
@@ -265,6 +272,12 @@ struct SweepArgs {
     const T* ext;             ///< MAIN == DYN_EXTERNAL: rhoBar [cells] followed by j_x, j_y, j_z [cells] each (extStride apart)
     long long extStride;
     int extBcFromFields;      ///< DYN_EXTERNAL_FUSED: the moments of cells with boundary dynamics are stored in the fields (else implied)
+    PeerSlab<T> lo, hi;       ///< neighbouring slabs below X = 1 / above X = nxl that take direct stores
+    int nRimTiles;            ///< > 0: tiles [0, nRimTiles) hold the rim planes of a face towards ANOTHER RANK; when the last of them
+    unsigned int* rimTicket;  ///<      is done, sigValue (the step count) goes to the neighbours' flags: "my stores of this step have landed"
+    unsigned int* sigLo;
+    unsigned int* sigHi;
+    unsigned int sigValue;
 };
 
 /// Deterministic block reduction of the BlockStatistics accumulators (core/blockStatistics.cpp:205-229:
@@ -344,9 +357,13 @@ __device__ __forceinline__ void complete_by_face(int baseType, const Bc<T>& b, T
 
 /// Out-of-line form for the sweep and the on-the-fly readers: the populations travel through local
 /// memory so that the caller's register file is not sized for this rarely taken path.
+/// pendingStamp: number of the sweep that applies the outstanding completion (the caller itself, if it is that sweep): a record
+/// changed since the completion was deferred carries this stamp and answers with its previous values; -1: current values
 template <class T, int Q>
-__device__ __noinline__ void complete_pending(int baseType, const Bc<T>* __restrict__ bcs, int bi, T* f) {
-    complete_by_face<T, Q>(baseType, bcs[bi], f);
+__device__ __noinline__ void complete_pending(int baseType, const Bc<T>* __restrict__ bcs, int bi, int pendingStamp, T* f) {
+    Bc<T> b = bcs[bi];
+    if (b.stamp == pendingStamp) { b.u[0] = b.uPrev[0]; b.u[1] = b.uPrev[1]; b.u[2] = b.uPrev[2]; b.rhoBar = b.rhoBarPrev; }
+    complete_by_face<T, Q>(baseType, b, f);
 }
 
 /// Dynamics::computeRhoBarJ of a cell with boundary dynamics from its (completed) populations and its record; out of line
@@ -356,6 +373,54 @@ __device__ __noinline__ void boundary_moments(const Dyn<T>* __restrict__ dyns, i
     T rb, j[3];
     LB<T, Q>::cell_rhoBar_j(dyns[k], true, bcs[bi], f, rb, j);
     rhoBar_j[0] = rb; rhoBar_j[1] = j[0]; rhoBar_j[2] = j[1]; rhoBar_j[3] = j[2];
+}
+
+/// Stores of the rim cells into the neighbouring slab (PeerSlab).
+///   even half: a cell writes f*_i into slot opp(i) of ITSELF; the neighbour's next (odd) half pulls the slots that point at
+///              it from its ghost plane, so those go there as well -- plane X = 1 sends the f*_i with c_ix = -1 to the high
+///              ghost plane of the slab below, plane X = nxl those with c_ix = +1 to the low ghost plane of the slab above.
+///   odd half:  a cell writes f*_i into slot i of cell x + c_i; where that cell belongs to the neighbouring slab the store
+///              goes to its plane nxl (below) or 1 (above) directly -- unless the cell does not exist (y / z rim of a
+///              non-periodic lattice): then the on-site rule keeps the population at home, as everywhere else.
+template <class T, int Q, int I = 1>
+struct RimStore {
+    template <int CX>
+    __device__ __forceinline__ static void even(const PeerSlab<T>& p, int P, int r, const T* f) {
+        using L = LB<T, Q>;
+        if (L::c(I, 0) == CX) {
+            const long long Xg = CX < 0 ? p.nxl + 1 : 0;
+            p.F[(long long)L::opp(I) * p.S + (Xg * P + r)] = f[I];
+        }
+        RimStore<T, Q, I + 1>::template even<CX>(p, P, r, f);
+    }
+    __device__ __forceinline__ static void odd(T* __restrict__ F, const Geo& g, const Nbr& n, int c, int X,
+                                               const PeerSlab<T>& lo, const PeerSlab<T>& hi, const T* f) {
+        using L = LB<T, Q>;
+        constexpr int sx = L::c(I, 0), sy = L::c(I, 1), sz = L::c(I, 2);
+        if (sx < 0 && X == 1 && lo.F != nullptr && nbr_valid<sx, sy, sz>(n)) {
+            lo.F[(long long)I * lo.S + ((long long)lo.nxl * g.P + (c - g.P) + nbr_off<0, sy, sz>(n))] = f[I];
+        } else if (sx > 0 && X == g.nxl && hi.F != nullptr && nbr_valid<sx, sy, sz>(n)) {
+            hi.F[(long long)I * hi.S + ((long long)g.P + (c - g.nxl * g.P) + nbr_off<0, sy, sz>(n))] = f[I];
+        } else {
+            { T* dst = F + stream_target<T, Q, I>(g, n, c); PLB_SWEEP_ST(dst, f[I]); }
+        }
+        RimStore<T, Q, I + 1>::odd(F, g, n, c, X, lo, hi, f);
+    }
+};
+template <class T, int Q>
+struct RimStore<T, Q, Q> {
+    template <int CX>
+    __device__ __forceinline__ static void even(const PeerSlab<T>&, int, int, const T*) {}
+    __device__ __forceinline__ static void odd(T*, const Geo&, const Nbr&, int, int, const PeerSlab<T>&, const PeerSlab<T>&, const T*) {}
+};
+
+/// "Parking" of sparse plane boundary cells (lazy completion, see sweep_kernel): entries per warp, and the number of flagged
+/// cells among a warp's 32 up to which they are parked rather than completed in line
+constexpr int STASH_CAP = 32;
+constexpr int STASH_MAX_NEW = 8;
+template <class T, int Q>
+__host__ __device__ constexpr size_t sweep_stash_bytes(int threads) {
+    return (size_t)(threads / 32) * STASH_CAP * (Q * sizeof(T) + sizeof(int));
 }
 
 /// The fused collide-and-stream sweep (BlockLattice3D::collideAndStream, atomicBlock/blockLattice3D.hh:253-312,
@@ -368,27 +433,34 @@ __device__ __noinline__ void boundary_moments(const Dyn<T>* __restrict__ dyns, i
 ///            completion"): completePopulations of such a cell is a function of its own post-stream
 ///            populations and its record only, so instead of a pass over the face cells after the
 ///            step, the next sweep applies it to the populations it has just gathered.
+///
+/// Lazy completion, lane-efficiently.  The x- and y-faces fill whole warps (z is the fastest index) and are completed in
+/// line.  A z-face puts ONE plane cell into a warp, and the completion is ~2000 instructions: in line it would nearly
+/// double the instruction count of the sweep.  A warp therefore PARKS such a cell -- its gathered populations go to a
+/// per-warp stash in shared memory and the cell is skipped -- and once the stash holds a warp's worth (or the warp runs out
+/// of tiles) the parked cells are completed, collided and scattered one per lane.  Nothing is read twice and no list
+/// exists on the host.  The AA pattern allows the delay: within a launch every storage location is read and written on
+/// behalf of one cell only, whenever and by whichever thread.  (Round 1 listed these cells and their sector mates on the
+/// host for extra blocks of the same grid: +1.7 GB of DRAM reads per launch at 512^3, profiles/r01_ncu_full_summary_d.md.)
+///
+/// One iteration of a warp's loop is either a tile (32 consecutive cells of the block's 512) or a flush of its stash;
+/// gather / complete / collide / scatter exist once in the instruction stream and serve both.
 template <class T, int Q, int MAIN, bool GENERIC, bool ODD, bool PLANES>
 __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) sweep_kernel(const SweepArgs<T> a) {
     using L = LB<T, Q>;
     constexpr int SWEEP_THREADS = sweep_threads(ODD);
+    extern __shared__ __align__(16) unsigned char sweepSmem[];
     const Geo& g = a.g;
+    const int lane = threadIdx.x & 31;
     double sRho = 0., sU = 0., mU = -DBL_MAX, cnt = 0.;
+    T* stF = nullptr;       // [Q][STASH_CAP] populations of this warp's parked cells
+    int* stC = nullptr;     // [STASH_CAP] their cell indices
+    if (PLANES) {
+        const int warp = threadIdx.x >> 5;
+        stF = reinterpret_cast<T*>(sweepSmem) + (size_t)warp * STASH_CAP * Q;
+        stC = reinterpret_cast<int*>(reinterpret_cast<T*>(sweepSmem) + (size_t)(SWEEP_THREADS / 32) * STASH_CAP * Q) + warp * STASH_CAP;
+    }
 
-    // gather the populations that arrive at cell c = (X, y, z); `interior` (odd half): every neighbour
-    // of the cell exists at its plain offset, so no per-population validity / wrap-around logic is needed
-    auto gather = [&](int c, bool interior, int X, int y, int z, Nbr& n, T* f) {
-        if (ODD) {
-            if (interior) {
-                CellIO<T, Q>::load_pull_interior(a.F, g, c, f);
-            } else {
-                n = make_nbr(g, X, y, z);
-                CellIO<T, Q>::load_pull(a.F, g, n, c, f);
-            }
-        } else {
-            CellIO<T, Q>::load_local(a.F, g, c, f);
-        }
-    };
     // outstanding completePopulations of a plane boundary cell (k = its kind byte)
     auto complete = [&](int c, int k, T* f) {
         const int bi = a.bcIdx[c];
@@ -396,12 +468,12 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
         T tmp[Q];
 #pragma unroll
         for (int i = 0; i < Q; ++i) tmp[i] = f[i];
-        complete_pending<T, Q>(a.dyns[k & KIND_MASK].type, a.bcs, bi, tmp);
+        complete_pending<T, Q>(a.dyns[k & KIND_MASK].type, a.bcs, bi, a.pendingStamp, tmp);
 #pragma unroll
         for (int i = 0; i < Q; ++i) f[i] = tmp[i];
     };
     // Cell::collide, scatter, gatherStatistics
-    auto collide_scatter = [&](int c, int k, bool interior, const Nbr& n, T* f) {
+    auto collide_scatter = [&](int c, int k, bool interior, int X, const Nbr& n, T* f) {
         const int kRaw = k;
         (void)kRaw;
         k &= KIND_MASK;
@@ -452,9 +524,11 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
         }
         if (ODD) {
             if (interior) CellIO<T, Q>::store_push_interior(a.F, g, c, f);
-            else CellIO<T, Q>::store_push(a.F, g, n, c, f);
+            else { PLB_SWEEP_ST(a.F + c, f[0]); RimStore<T, Q>::odd(a.F, g, n, c, X, a.lo, a.hi, f); }
         } else {
             CellIO<T, Q>::store_local_swapped(a.F, g, c, f);
+            if (a.lo.F != nullptr && c < 2 * g.P) RimStore<T, Q>::template even<-1>(a.lo, g.P, c - g.P, f);
+            if (a.hi.F != nullptr && c >= g.nxl * g.P) RimStore<T, Q>::template even<+1>(a.hi, g.P, c - g.nxl * g.P, f);
         }
         if (took) {
             sRho += (double)rhoBar;
@@ -464,89 +538,113 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
         }
     };
 
-    // Lazy completion, lane-efficiently.  The x- and y-faces fill whole warps (z is the fastest index)
-    // and are completed in line.  A z-face puts ONE plane cell into a warp; running the ~2000-instruction
-    // completion for one lane in the streaming loop would nearly double the instruction count of the
-    // sweep.  The host therefore lists such cells (in sector-sized groups of SPARSE_GROUP neighbours,
-    // flagged KIND_SPARSE); the streaming blocks skip them, and "list" blocks interleaved with them in
-    // the same grid process the list one cell per lane.  The AA pattern allows that: within a launch each
-    // storage location is read and written by the thread of one cell only, whichever thread that is.
     const bool planes = PLANES && a.applyPlanes;
-    int mainIdx = blockIdx.x, mainGrid = gridDim.x;
-    if (PLANES && a.nListBlocks > 0) {
-#if PLB_LIST_PLACEMENT == 0
-        const int R = (int)gridDim.x / a.nListBlocks;          // every R-th block is a list block
-        const int b = blockIdx.x;
-        const bool isList = b % R == R - 1 && b / R < a.nListBlocks;
-        const int listIdx = b / R, mainIfNot = b - min(a.nListBlocks, b / R);
-#elif PLB_LIST_PLACEMENT == 1
-        const int b = blockIdx.x, nMain = (int)gridDim.x - a.nListBlocks;
-        const bool isList = b >= nMain;
-        const int listIdx = b - nMain, mainIfNot = b;
-#else
-        const int b = blockIdx.x;
-        const bool isList = b < a.nListBlocks;
-        const int listIdx = b, mainIfNot = b - a.nListBlocks;
-#endif
-        if (isList) {
-            const int t = listIdx * SWEEP_THREADS + threadIdx.x;
-            if (t < a.nSparse) {
-                const int c = a.sparseCells[t];
-                T f[Q];
-                Nbr n;
-                int X = 0, y = 0, z = 0;
-                if (ODD) decode_cell(g, c, X, y, z);
-                gather(c, false, X, y, z, n, f);
-                const int k = a.kind[c];
-                if (k & KIND_PLANE) complete(c, k, f);
-                collide_scatter(c, k, false, n, f);
-            }
-            mainIdx = -1;
-        } else {
-            mainIdx = mainIfNot;
-            mainGrid = (int)gridDim.x - a.nListBlocks;
-        }
-    }
-    if (mainIdx >= 0) {
-        const int nTiles = (a.cellEnd - a.cellBegin + SWEEP_THREADS - 1) / SWEEP_THREADS;
-        for (int tile = mainIdx; tile < nTiles; tile += mainGrid) {
-            const int tileBegin = a.cellBegin + tile * SWEEP_THREADS;      // block-uniform
-            const int c = tileBegin + threadIdx.x;
-            if (c >= a.cellEnd) continue;
-            bool interior = false;
-            int X = 0, y = 0, z = 0;
-            if (ODD) {
-                // decode the first cell of the warp's 32; if the 32 lie in one row of interior y, clear of the
-                // row ends, in a plane whose x-neighbours are plain planes, the whole warp takes the fast path
-                decode_cell(g, tileBegin + (int)(threadIdx.x & ~31u), X, y, z);
-                interior = z > 0 && z + 32 < g.nz && y > 0 && y < g.ny - 1
-                        && (X > 1 || g.lowMode == XMODE_GHOST) && (X < g.nxl || g.highMode == XMODE_GHOST);
-                z += (int)(threadIdx.x & 31u);
-                if (z >= g.nz) decode_cell(g, c, X, y, z);
-            }
-            // cells of the sparse list are left to the list blocks: skip them before their populations are gathered (measured at
-            // 512^3, profiles/r01_fused_planes_variants.log: 7.14 -> 7.05 ms per step against checking after the gather);
-            // without fused planes the kind byte is read after the gather has been issued, as before
-            int k = 0;
-            if (PLANES) {
+    int nStash = 0;                 // warp-uniform
+    bool rimPending = false;        // this warp has worked on a rim tile whose completion it has not reported yet
+    int tile = blockIdx.x;
+    for (;;) {
+        const bool more = tile < a.nTiles;
+        int c = 0, k = 0, X = 0, y = 0, z = 0;
+        bool interior = false, active = false, needComplete = false;
+        T f[Q];
+        Nbr n;
+        if (PLANES && nStash > 0 && (nStash > STASH_CAP - STASH_MAX_NEW || rimPending || !more)) {
+            // ---- the parked cells, one per lane
+            active = lane < nStash;
+            if (active) {
+                c = stC[lane];
+#pragma unroll
+                for (int i = 0; i < Q; ++i) f[i] = stF[i * STASH_CAP + lane];
                 k = a.kind[c];
-                if (planes && (k & KIND_SPARSE)) continue;
+                needComplete = true;
+                if (ODD) { decode_cell(g, c, X, y, z); n = make_nbr(g, X, y, z); }
             }
-            T f[Q];
-            Nbr n;
-            gather(c, interior, X, y, z, n, f);
-            if (sweep_prefetch(ODD) > 0) {
-                const long long delta = (long long)sweep_prefetch(ODD) * mainGrid * SWEEP_THREADS;
-                if (c + delta < a.cellEnd) {
-                    if (ODD && interior) CellIO<T, Q>::prefetch_interior(a.F, g, c + (int)delta);
-                    else CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
+            nStash = 0;
+            __syncwarp();
+        } else if (rimPending) {
+            // ---- the stores of this warp's part of a rim tile have been issued: perform them system-wide, count the warp in,
+            // and let the last warp of the last rim tile tell the neighbouring ranks (they wait on the flag with a stream
+            // memory operation before anything of theirs touches the planes this launch has stored into)
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned int total = (unsigned int)a.nRimTiles * (SWEEP_THREADS / 32);
+                if (atomicAdd(a.rimTicket, 1u) == total - 1u) {
+                    __threadfence_system();
+                    if (a.sigLo) *(volatile unsigned int*)a.sigLo = a.sigValue;
+                    if (a.sigHi) *(volatile unsigned int*)a.sigHi = a.sigValue;
+                    *a.rimTicket = 0u;
                 }
             }
-            if (!PLANES) k = a.kind[c];
-            if (PLANES && planes) {
-                if (k & KIND_PLANE) complete(c, k, f);
+            rimPending = false;
+            continue;
+        } else if (more) {
+            // ---- a tile: which range it falls in (block-uniform)
+            const int r = (a.nRanges > 1 && tile >= a.range[1].tile0 ? 1 : 0) + (a.nRanges > 2 && tile >= a.range[2].tile0 ? 1 : 0);
+            const int rBegin = r == 0 ? a.range[0].begin : (r == 1 ? a.range[1].begin : a.range[2].begin);
+            const int rEnd = r == 0 ? a.range[0].end : (r == 1 ? a.range[1].end : a.range[2].end);
+            const int rTile0 = r == 0 ? a.range[0].tile0 : (r == 1 ? a.range[1].tile0 : a.range[2].tile0);
+            const int tileBegin = rBegin + (tile - rTile0) * SWEEP_THREADS;
+            c = tileBegin + threadIdx.x;
+            active = c < rEnd;
+            if (tile < a.nRimTiles) rimPending = true;
+            tile += gridDim.x;
+            if (ODD) {
+                // decode the first cell of the warp's 32; if the 32 lie in one row of interior y, clear of the row ends, in a
+                // plane whose x-neighbours are planes of this slab (or ghost planes of the copy-based transport), every
+                // neighbour of every cell exists at its plain offset and the whole warp takes the fast path
+                decode_cell(g, tileBegin + (int)(threadIdx.x & ~31u), X, y, z);
+                interior = z > 0 && z + 32 < g.nz && y > 0 && y < g.ny - 1
+                        && (X > 1 || (g.lowMode == XMODE_GHOST && a.lo.F == nullptr))
+                        && (X < g.nxl || (g.highMode == XMODE_GHOST && a.hi.F == nullptr));
+                z += lane;
+                if (z >= g.nz) decode_cell(g, c, X, y, z);
             }
-            collide_scatter(c, k, interior, n, f);
+            if (active) {
+                if (ODD) {
+                    if (interior) {
+                        CellIO<T, Q>::load_pull_interior(a.F, g, c, f);
+                    } else {
+                        n = make_nbr(g, X, y, z);
+                        CellIO<T, Q>::load_pull(a.F, g, n, c, f);
+                    }
+                } else {
+                    CellIO<T, Q>::load_local(a.F, g, c, f);
+                }
+                if (sweep_prefetch(ODD) > 0) {
+                    const long long delta = (long long)sweep_prefetch(ODD) * gridDim.x * SWEEP_THREADS;
+                    if (c + delta < rEnd) {
+                        if (ODD && interior) CellIO<T, Q>::prefetch_interior(a.F, g, c + (int)delta);
+                        else CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
+                    }
+                }
+                k = a.kind[c];
+            }
+            if (PLANES && planes) {
+                const bool flagged = active && (k & KIND_PLANE);
+                const unsigned int m = __ballot_sync(0xffffffffu, flagged);
+                if (m != 0u) {
+                    if (__popc(m) <= STASH_MAX_NEW) {
+                        if (flagged) {
+                            const int e = nStash + __popc(m & ((1u << lane) - 1u));
+                            stC[e] = c;
+#pragma unroll
+                            for (int i = 0; i < Q; ++i) stF[i * STASH_CAP + e] = f[i];
+                            active = false;
+                        }
+                        nStash += __popc(m);
+                        __syncwarp();
+                    } else {
+                        needComplete = flagged;
+                    }
+                }
+            }
+        } else {
+            break;
+        }
+        if (active) {
+            if (PLANES && needComplete) complete(c, k, f);
+            collide_scatter(c, k, interior, X, n, f);
         }
     }
     if (a.gatherStats) reduce_stats(sRho, sU, mU, cnt, a.partials, a.ticket, a.statsOut);
@@ -601,6 +699,7 @@ struct CellCtx {
     Geo g;
     bool swapped;
     bool pending;        ///< plane completion is pending in storage: readers of KIND_PLANE cells apply it on the fly
+    int pendingStamp;    ///< ... under the record values it was deferred with (complete_pending)
 };
 
 template <class T, int Q>
@@ -628,7 +727,7 @@ __device__ __forceinline__ void fetch_cell(const CellCtx<T>& cx, int c, bool nee
         decode_cell(cx.g, c, X, y, z);
         const Nbr n = make_nbr(cx.g, X, y, z);
         CellIO<T, Q>::load(cx.F, cx.g, n, c, cx.swapped, v.f);
-        if (cx.pending && (kb & KIND_PLANE) && v.hasBc) complete_pending<T, Q>(v.d.type, cx.bcs, bi, v.f);
+        if (cx.pending && (kb & KIND_PLANE) && v.hasBc) complete_pending<T, Q>(v.d.type, cx.bcs, bi, cx.pendingStamp, v.f);
     } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) v.f[i] = (T)0;
@@ -713,7 +812,9 @@ __global__ void __launch_bounds__(128) plane_stage_kernel(CellCtx<T> cx, T* F, c
     const int c = items[t].cell;
     const int bi = cx.bcIdx[c];
     if (bi < 0) return;
-    const Bc<T> b = cx.bcs[bi];
+    Bc<T> b = cx.bcs[bi];
+    // materialising a deferred completion: a record changed since answers with the values the completion was deferred under
+    if (b.stamp == cx.pendingStamp) { b.u[0] = b.uPrev[0]; b.u[1] = b.uPrev[1]; b.u[2] = b.uPrev[2]; b.rhoBar = b.rhoBarPrev; }
     const int baseType = cx.dyns[cx.kind[c] & KIND_MASK].type;
     int X, y, z;
     decode_cell(cx.g, c, X, y, z);
@@ -901,7 +1002,7 @@ __device__ __forceinline__ void rhobar_j_cell(const CellCtx<T>& cx, int c, int X
     if (L::rhoBar_j_reads_pops(d.type, hasBc, b.kind)) {
         const Nbr n = make_nbr(cx.g, X, y, z);
         CellIO<T, Q>::load(cx.F, cx.g, n, c, cx.swapped, f);
-        if (cx.pending && (kb & KIND_PLANE) && hasBc) complete_pending<T, Q>(d.type, cx.bcs, bi, f);
+        if (cx.pending && (kb & KIND_PLANE) && hasBc) complete_pending<T, Q>(d.type, cx.bcs, bi, cx.pendingStamp, f);
     } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) f[i] = (T)0;
@@ -959,14 +1060,33 @@ __global__ void __launch_bounds__(256) box_sum_kernel(CellCtx<T> cx, BoxL box, i
     }
 }
 
+/// setBoundaryVelocity (what = 0; dataInitializerFunctional3D.hh:830-845 -> StoreVelocityDynamics::defineVelocity, boundaryDynamics.hh:333-339)
+/// and setBoundaryDensity (what = 1; StoreDensityDynamics::defineDensity :239-243) on the records of the cells of a box, on the
+/// device: the time loop of an unsteady inlet changes values every step, and neither a host walk over the records nor an eager
+/// pass over the pending plane cells belongs there.  nextSweep: see Bc::stamp.
+template <class T, int Q>
+__global__ void set_bc_values_kernel(const int* __restrict__ bcIdx, Bc<T>* bcs, Geo g, BoxL box, int what, T u0, T u1, T u2, T rhoBar, int nextSweep) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= box.cells()) return;
+    int X, y, z;
+    const int c = box_cell(g, box, k, X, y, z);
+    const int bi = bcIdx[c];
+    if (bi < 0) return;
+    Bc<T>& b = bcs[bi];
+    const bool isRho = LB<T, Q>::is_rho_plane(b.kind);
+    if ((what == 0) == isRho) return;
+    if (b.stamp != nextSweep) {
+        b.uPrev[0] = b.u[0]; b.uPrev[1] = b.u[1]; b.uPrev[2] = b.u[2]; b.rhoBarPrev = b.rhoBar;
+        b.stamp = nextSweep;
+    }
+    if (what == 0) { b.u[0] = u0; b.u[1] = u1; b.u[2] = u2; }
+    else b.rhoBar = rhoBar;
+}
+
 /// Mark the cells of the plane items whose completion is fused into the sweep.
 static __global__ void flag_plane_cells_kernel(const Item* items, int n, uint8_t* kind) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) kind[items[t].cell] |= (uint8_t)KIND_PLANE;
-}
-static __global__ void flag_sparse_cells_kernel(const int* cells, int n, uint8_t* kind) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) kind[cells[t]] |= (uint8_t)KIND_SPARSE;
 }
 
 /// Scatter the sparse (cell -> boundary record) map into the dense per-cell index.

@@ -20,6 +20,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
     const char* (*GetErrorString)(ncclResult_t);
 
     static NcclApi& get() {
@@ -54,6 +55,7 @@ private:
         sym(h, "ncclSend", a.Send);
         sym(h, "ncclRecv", a.Recv);
         sym(h, "ncclAllReduce", a.AllReduce);
+        sym(h, "ncclAllGather", a.AllGather);
         sym(h, "ncclGetErrorString", a.GetErrorString);
         return a;
     }

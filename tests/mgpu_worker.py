@@ -33,22 +33,27 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     spr = int(os.environ.get("PLB_TEST_SLABS_PER_RANK", "1"))
     bad = []
-    for name in NAMES:
-        sc = CASES[name][0]()
-        if sc.nx < world * spr:
-            continue
-        eng = DistEngine(pb, sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2, slabs_per_rank=spr, device=dev,
-                         enveloped_periodic=sc.periodicity if sc.external else None)
-        got = replay(sc, eng)
-        eng.close()
-        if rank == 0:
-            want = run_oracle(sc)
-            ok = all(np.array_equal(got[k], want[k]) for k in want if k not in ("stats", "time"))
-            rel = 1e-12 if sc.prec == "f64" else 1e-6
-            ok = ok and np.allclose(got["stats"], want["stats"], rtol=rel, atol=1e-300, equal_nan=True)
-            print("%-28s %d ranks x %d slabs: %s" % (name, world, spr, "identical" if ok else "DIFFERENT"), flush=True)
-            if not ok:
-                bad.append(name)
+    # both transports of the envelope exchange: direct stores into the neighbouring rank's slab (CUDA IPC), and the fallback
+    for halo in ("direct", "nccl"):
+        os.environ["PLB_B200_HALO"] = halo
+        for name in NAMES:
+            sc = CASES[name][0]()
+            if sc.nx < world * spr:
+                continue
+            eng = DistEngine(pb, sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2, slabs_per_rank=spr, device=dev,
+                             enveloped_periodic=sc.periodicity if sc.external else None)
+            transport = eng.halo_transport()
+            got = replay(sc, eng)
+            eng.close()
+            if rank == 0:
+                want = run_oracle(sc)
+                ok = all(np.array_equal(got[k], want[k]) for k in want if k not in ("stats", "time"))
+                rel = 1e-12 if sc.prec == "f64" else 1e-6
+                ok = ok and np.allclose(got["stats"], want["stats"], rtol=rel, atol=1e-300, equal_nan=True)
+                ok = ok and (("direct stores" in transport) == (halo == "direct"))
+                print("%-28s %d ranks x %d slabs [%s]: %s" % (name, world, spr, transport[:40], "identical" if ok else "DIFFERENT"), flush=True)
+                if not ok:
+                    bad.append(name + "/" + halo)
     flag = torch.tensor([len(bad)], device=dev)
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()

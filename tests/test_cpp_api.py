@@ -28,6 +28,7 @@ def test_examples_build_against_the_header():
     subprocess.run(["make", "-C", EX], check=True, capture_output=True)
     assert os.path.exists(os.path.join(EX, "cavity3d")) and os.path.exists(os.path.join(EX, "channel3d"))
     assert os.path.exists(os.path.join(EX, "voxelize_stl")) and os.path.exists(os.path.join(EX, "external_rhoj3d"))
+    assert os.path.exists(os.path.join(EX, "coprocessor3d"))
 
 
 @pytest.mark.gpu
@@ -159,3 +160,47 @@ def test_cavity3d_cpp_dynamics_based_boundary_managers(model):
                        env=dict(os.environ, CAVITY3D_BC=model))
         got = np.fromfile(dump, dtype=np.float64).reshape(nx, ny, nz, 19)
     assert np.array_equal(got, gold["f_end_full"])
+
+
+# ---- the reference's accelerator plug-in interface plb::CoProcessor3D<T> ------------------------------------
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_coprocessor_adapter_cpp_matches_oracle(prec):
+    """plb::B200CoProcessor3D<T> (include/palabos_b200/coprocessor_adapter.h) through global::defaultCoProcessor3D<T>(): addDomain,
+    send (whole block and a sub-domain), N x collideAndStream, receive -- against the oracle stepped from the same populations.
+    The interface leaves the outer layer of a domain undefined (coProcessor3D.h:105-108); the engine is defined there too
+    (on-site rule of the reference's own sweep) and agrees with the oracle on every cell."""
+    from scenario import Scenario
+    nx, ny, nz, steps, omega = 14, 11, 9, 15, 1.3
+    dt = np.float64 if prec == "f64" else np.float32
+    k = np.arange(nx * ny * nz * 19, dtype=np.float64)
+    pops = (1e-3 * np.sin(0.37 * k) / 19.0).astype(dt).reshape(nx, ny, nz, 19)
+    sub = (2e-3 * np.cos(0.11 * np.arange(2 * 3 * nz * 19, dtype=np.float64)) / 19.0).astype(dt).reshape(2, 3, nz, 19)
+    pops[1:3, 1:4, :, :] = sub
+    with tempfile.TemporaryDirectory() as tmp:
+        dump = os.path.join(tmp, "f.bin")
+        subprocess.run([_exe("coprocessor3d"), str(nx), str(ny), str(nz), repr(omega), str(steps), dump] + (["f32"] if prec == "f32" else []),
+                       check=True, capture_output=True, text=True)
+        got = np.fromfile(dump, dtype=dt).reshape(nx, ny, nz, 19)
+    sc = Scenario(19, prec, nx, ny, nz, "BGK", float(dt(omega)))
+    sc.upload(pops)
+    sc.run(steps).stats().dump("f_end")
+    want = run_oracle(sc)["f_end"]
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_b200_coprocessor_inside_the_unmodified_reference():
+    """examples/ref_coprocessor.cpp: the REAL Palabos (oracle/_ref/libplb.a, built from /root/reference where that exists) with
+    global::defaultCoProcessor3D<T>() answering with B200CoProcessor3D<T>: initiateCoProcessors -> addDomain per pure block,
+    transferToCoProcessors / collideAndStream() / transferFromCoProcessors per step, compared inside the program bit for bit
+    with the reference stepping the same lattice alone (periodic box: 8 of 8 blocks on the device; cavity: the centre block of
+    27).  The binary travels to the GPU box prebuilt, like the reference driver."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_coprocessor")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_coprocessor not built (needs the reference sources)")
+    r = subprocess.run([exe, "20"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "REF_COPROCESSOR_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "8 of 8 blocks on the co-processor" in r.stdout and "1 of 27 blocks on the co-processor" in r.stdout

@@ -336,16 +336,35 @@ def test_long_rows_take_the_interior_fast_path_of_the_odd_half(shape, slabs):
             eng.close()
 
 
-@pytest.mark.parametrize("mode", ["0", "1"])
-@pytest.mark.parametrize("name,slabs", [("cavity_bgk_10x9x8", 2), ("cavity_zouhe_10x9x8", 5), ("channel_trt_16x12x10", 4), ("periodic_rlb_q27", 2)])
-def test_exchange_overlapped_with_the_interior_sweep_or_not(name, slabs, mode, monkeypatch):
-    """PLB_B200_OVERLAP=1: rim planes swept first, exchange on a second stream while the interior planes are swept
-    (three launches per slab and step); =0: one launch, exchange afterwards.  Same populations and statistics."""
-    monkeypatch.setenv("PLB_B200_OVERLAP", mode)
+COPY_CASES = [("cavity_bgk_10x9x8", 2), ("cavity_zouhe_10x9x8", 5), ("channel_trt_16x12x10", 4), ("periodic_rlb_q27", 2),
+              ("channel_smago_q27_f32", 3), ("obstacle_zouhe_24x12x10", 4), ("cavity_dynlocal_10x9x8", 3), ("ext_channel_trt", 3),
+              ("ext_cavity_incbgk", 2)]
+
+
+@pytest.mark.parametrize("name,slabs", COPY_CASES)
+def test_copy_based_exchange_gives_the_same_populations(name, slabs, monkeypatch):
+    """Default: the rim cells of the sweep store the face-crossing populations straight into the neighbouring slab (what the
+    decomposition tests above run).  PLB_B200_HALO=nccl selects the fallback -- ghost planes, plane copies (cudaMemcpy inside
+    a process, ncclSend / ncclRecv between ranks) and unpack_halo_kernel after odd steps.  Same populations and statistics."""
+    import palabos_b200 as pb
+    monkeypatch.setenv("PLB_B200_HALO", "nccl")
     sc = CASES[name][0]()
+    eng = pb.Lattice(sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2, slabs_per_rank=slabs,
+                     enveloped_periodic=sc.periodicity if sc.external else None)
+    assert "ghost planes" in eng.halo_transport()
+    eng.close()
     got = run_gpu(sc, slabs=slabs)
     assert_same(name, got, run_oracle(sc), sc.prec)
     check_golden(name, got)
+
+
+def test_direct_exchange_is_the_default():
+    import palabos_b200 as pb
+    eng = pb.Lattice(19, "f64", 12, 8, 8, "BGK", 1.5, slabs_per_rank=3)
+    try:
+        assert eng.halo_transport().startswith("direct stores")
+    finally:
+        eng.close()
 
 
 # ---- the external-moment sweep (SURVEY.md 8f rank 2): decompositions, error behaviour ----------------------------------

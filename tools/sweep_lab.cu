@@ -70,7 +70,12 @@ int main(int argc, char** argv) {
     fill<<<148 * 8, 256>>>(F, nF, Q);
     CK(cudaDeviceSynchronize());
     SweepArgs<T> a;
-    a.F = F; a.kind = kind; a.dyns = dyns; a.bcIdx = nullptr; a.bcs = nullptr; a.applyPlanes = 0; a.sparseCells = nullptr; a.nSparse = 0; a.nListBlocks = 0; a.g = g; a.cellBegin = g.P; a.cellEnd = (n + 1) * g.P;
+    a.F = F; a.kind = kind; a.dyns = dyns; a.bcIdx = nullptr; a.bcs = nullptr; a.applyPlanes = 0; a.pendingStamp = -1; a.g = g;
+    a.lo.F = a.hi.F = nullptr; a.lo.S = a.hi.S = 0; a.lo.nxl = a.hi.nxl = 0; a.nRimTiles = 0; a.rimTicket = nullptr; a.sigLo = a.sigHi = nullptr; a.sigValue = 0;
+    a.ext = nullptr; a.extStride = 0; a.extBcFromFields = 0;
+    const int cellBegin = g.P, cellEnd = (n + 1) * g.P;
+    for (int k = 0; k < 3; ++k) { a.range[k].begin = a.range[k].end = a.range[k].tile0 = 0; }
+    a.range[0].begin = cellBegin; a.range[0].end = cellEnd; a.nRanges = 1;
     a.omega = (T)1.2388; a.preFactor = (T)0.01; a.gatherStats = 1; a.partials = partials; a.ticket = ticket; a.statsOut = stats;
     auto kEven = sweep_kernel<T, Q, LAB_DYN, false, false, false>;
     auto kOdd = sweep_kernel<T, Q, LAB_DYN, false, true, false>;
@@ -81,7 +86,7 @@ int main(int argc, char** argv) {
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     cudaFuncAttributes fe, fo;
     CK(cudaFuncGetAttributes(&fe, kEven)); CK(cudaFuncGetAttributes(&fo, kOdd));
-    auto gridOf = [&](int gf, int threads) { const int nTiles = (a.cellEnd - a.cellBegin + threads - 1) / threads; return gf * sms < nTiles ? gf * sms : nTiles; };
+    auto gridOf = [&](int gf, int threads) { const int nTiles = (cellEnd - cellBegin + threads - 1) / threads; a.nTiles = nTiles; return gf * sms < nTiles ? gf * sms : nTiles; };
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     double msE = 0, msO = 0;
