@@ -49,8 +49,8 @@ class LatticeImpl : public LatticeBase {
         T* dExt = nullptr;                 ///< external-moment sweep: rhoBar [cellsStore] | j_x | j_y | j_z, zero where nothing writes
         int* dBcCells = nullptr; size_t dBcCellsCap = 0;   ///< ... cells that carry a boundary record (-1: dead record)
         int nBcCells = 0;
-        double* dStats = nullptr;          ///< [4] sum rhoBar, sum uSqr, max uSqr, cell count of the last sweep
-        int statSlots = 0;                 ///< 1 once a sweep has reported
+        double* dStats = nullptr;          ///< [2][4] sum rhoBar, sum uSqr, max uSqr, cell count of the last sweep and of its drain launch
+        int statSlots = 0;                 ///< launches of the last step that have reported
         unsigned int* dTicket = nullptr;
         int nAuto = 0;                     ///< items [0, nAuto): plane cells that complete at collision time (never executed as a stage)
         std::vector<uint8_t> hKind;
@@ -61,6 +61,10 @@ class LatticeImpl : public LatticeBase {
         std::vector<int> stageSplit;       ///< ... plane items first, finite-difference items from stageSplit[s]
         size_t nItems = 0;
         unsigned int* dRimTicket = nullptr; ///< counts the rim tiles of a launch that signals a neighbouring rank
+        int* dMbCount = nullptr;            ///< mailboxes of the parked plane boundary cells (sweep_kernel), one per (SM, warp)
+        int* dMbCell = nullptr;
+        T* dMbF = nullptr;
+        bool deferWanted = false;           ///< the slab has plane cells that sit alone in their warp (z-faces): park them
         bool valuesOnDevice = false;       ///< the records on the device hold newer u / rhoBar than `recs` (set_values_on_device)
         bool dirtyKind = true, dirtyBcIndex = true, dirtySched = true;
         bool kindUnflagged = true;         ///< dKind was uploaded from hKind and carries no KIND_PLANE flags
@@ -149,7 +153,7 @@ public:
             PLB_CUDA(cudaMemsetAsync(sl.F, 0, nF * sizeof(T), stream_));
             sl.dKind = (uint8_t*)dev_alloc(sl.cellsStore);
             sl.dBcIdx = (int*)dev_alloc(sl.cellsStore * sizeof(int));
-            sl.dStats = (double*)dev_alloc(4 * sizeof(double));
+            sl.dStats = (double*)dev_alloc(2 * 4 * sizeof(double));
             sl.dRimTicket = (unsigned int*)dev_alloc(sizeof(unsigned int));
             PLB_CUDA(cudaMemsetAsync(sl.dRimTicket, 0, sizeof(unsigned int), stream_));
             sl.dTicket = (unsigned int*)dev_alloc(sizeof(unsigned int));
@@ -170,7 +174,7 @@ public:
         cudaFree(dFlags_);
         for (Slab& sl : slabs_) {
             cudaFree(sl.F); cudaFree(sl.dExt); cudaFree(sl.dBcCells); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems);
-            cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket); cudaFree(sl.dRimTicket);
+            cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket); cudaFree(sl.dRimTicket); cudaFree(sl.dMbCount); cudaFree(sl.dMbCell); cudaFree(sl.dMbF);
         }
         cudaFree(dDyns_); cudaFree(dStage_); cudaFree(dReduce_);
         if (comm_) NcclApi::get().CommDestroy(comm_);
@@ -581,7 +585,7 @@ public:
             // direct transport nothing else is needed -- the neighbour reads what was stored into it one step later; the wait
             // below only orders this rank's NEXT accesses to its rim / ghost planes after the neighbours' stores of THIS step.
             ++stepCount_;
-            for (Slab& sl : slabs_) { launch_sweep(sl); sl.statSlots = 1; }
+            for (Slab& sl : slabs_) launch_sweep(sl);
             swapped_ = !swapped_;
             pending_ = false;                  // the sweep has applied the outstanding completion
             if (direct_) wait_neighbours();
@@ -612,11 +616,11 @@ public:
         if (stepped_ && statsOn_) {
             PLB_CUDA(cudaStreamSynchronize(stream_));
             for (Slab& sl : slabs_) {
-                double h[4];
+                double h[8];
                 PLB_CUDA(cudaMemcpy(h, sl.dStats, sizeof h, cudaMemcpyDeviceToHost));
-                if (sl.statSlots > 0) {
-                    sum[0] += h[0]; sum[1] += h[1]; sum[2] += h[3];
-                    mx = std::max(mx, h[2]);
+                for (int k = 0; k < sl.statSlots; ++k) {
+                    sum[0] += h[4 * k]; sum[1] += h[4 * k + 1]; sum[2] += h[4 * k + 3];
+                    mx = std::max(mx, h[4 * k + 2]);
                 }
             }
         }
@@ -997,6 +1001,16 @@ private:
         // count[2*stage + (0|1)] as before; the cells the sweep completes on load: the automatic ones if the lattice has
         // any (the wrapped ones then run eagerly), else the wrapped plane items of stage 0
         const int* count = count0.data() + 1;
+        {
+            // do plane cells that the sweep completes on load sit alone in the 32-cell piece a warp covers (a z-face: one per
+            // row)?  Then the sweep defers them to its drain launch (sweep_kernel); the device decides cell by cell, this only
+            // switches the mechanism on
+            const int flagLo = autoPlanes_ ? 0 : (nStages > 0 ? count[0] : 0), flagHi = autoPlanes_ ? sl.nAuto : (nStages > 0 ? count[1] : 0);
+            std::unordered_map<int, int> perPiece;
+            for (int k = flagLo; k < flagHi; ++k) ++perPiece[(sorted[k].cell - P_) / 32];
+            sl.deferWanted = false;
+            for (const auto& kv : perPiece) if (kv.second <= STASH_MAX_NEW) { sl.deferWanted = true; break; }
+        }
         sl.stageOffsets.assign(nStages + 1, 0);
         sl.stageSplit.assign(nStages, 0);
         for (int st = 0; st < nStages; ++st) { sl.stageOffsets[st] = count[2 * st]; sl.stageSplit[st] = count[2 * st + 1]; }
@@ -1183,20 +1197,43 @@ private:
                                      std::getenv("PLB_B200_GRID_ODD") ? std::atoi(std::getenv("PLB_B200_GRID_ODD")) : 0};
         const int gf = gfEnv[ODD ? 1 : 0] > 0 ? gfEnv[ODD ? 1 : 0] : sweep_grid_factor(ODD);
         const int grid = std::max(1, std::min(a.nTiles, numSMs_ * gf));
-        if (grid > sl.partialsCap) {
+        const bool defer = PLANES && a.applyPlanes && sl.deferWanted;
+        const int drainGrid = defer ? MAILBOX_SMS : 0;
+        if (std::max(grid, drainGrid) > sl.partialsCap) {
             if (sl.dPartials) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dPartials); devBytes_ -= (size_t)sl.partialsCap * 4 * sizeof(double); }
-            sl.partialsCap = std::max(grid, numSMs_ * 16);
+            sl.partialsCap = std::max(std::max(grid, drainGrid), numSMs_ * 16);
             sl.dPartials = (double*)dev_alloc((size_t)sl.partialsCap * 4 * sizeof(double));
         }
         a.partials = sl.dPartials;
-        const bool prof = profiling_ && profUsed_ < 2 * 8192;
-        if (prof) {
-            while (profEvents_.size() < profUsed_ + 2) { cudaEvent_t e; PLB_CUDA(cudaEventCreate(&e)); profEvents_.push_back(e); }
-            PLB_CUDA(cudaEventRecord(profEvents_[profUsed_], stream_));
+        a.drain = 0; a.mbCount = nullptr; a.mbCell = nullptr; a.mbF = nullptr;
+        if (defer) {
+            if (!sl.dMbCount) {
+                const size_t slots = (size_t)MAILBOX_SMS * (SWEEP_MAX_THREADS / 32);
+                sl.dMbCount = (int*)dev_alloc(slots * sizeof(int));
+                sl.dMbCell = (int*)dev_alloc(slots * STASH_CAP * sizeof(int));
+                sl.dMbF = (T*)dev_alloc(slots * STASH_CAP * Q * sizeof(T));
+                PLB_CUDA(cudaMemsetAsync(sl.dMbCount, 0, slots * sizeof(int), stream_));
+            }
+            a.mbCount = sl.dMbCount; a.mbCell = sl.dMbCell; a.mbF = sl.dMbF;
         }
-        launch_sweep_kernel<T, Q, MAIN, GEN, ODD, PLANES>(grid, stream_, a);
-        launched();
-        if (prof) { PLB_CUDA(cudaEventRecord(profEvents_[profUsed_ + 1], stream_)); profUsed_ += 2; }
+        auto timed_launch = [&](int gridSize) {
+            const bool prof = profiling_ && profUsed_ < 2 * 8192;
+            if (prof) {
+                while (profEvents_.size() < profUsed_ + 2) { cudaEvent_t e; PLB_CUDA(cudaEventCreate(&e)); profEvents_.push_back(e); }
+                PLB_CUDA(cudaEventRecord(profEvents_[profUsed_], stream_));
+            }
+            launch_sweep_kernel<T, Q, MAIN, GEN, ODD, PLANES>(gridSize, stream_, a);
+            launched();
+            if (prof) { PLB_CUDA(cudaEventRecord(profEvents_[profUsed_ + 1], stream_)); profUsed_ += 2; }
+        };
+        timed_launch(grid);
+        sl.statSlots = 1;
+        if (defer) {
+            // the drain launch: what the last blocks of the sweep left in the mailboxes of their SMs
+            a.drain = 1; a.nRimTiles = 0; a.statsOut = sl.dStats + 4;
+            timed_launch(drainGrid);
+            sl.statSlots = 2;
+        }
     }
 
     /// the slab on the other side of a face of `sl`, if the rim cells store into it directly
@@ -1231,6 +1268,18 @@ private:
         a.pendingStamp = sl.nAuto > 0 ? -1 : (int)stepCount_;
         peers_of(sl, a.g, a);
         a.rimTicket = sl.dRimTicket; a.sigValue = stepCount_; a.nRimTiles = 0;
+        for (int i = 0; i < 27; ++i) a.ldBase[i] = a.stBase[i] = nullptr;
+        for (int i = 0; i < Q; ++i) {
+            const int o = L::opp(i);
+            if (!swapped_) {            // even half: the cell itself
+                a.ldBase[i] = sl.F + (long long)i * sl.cellsStore;
+                a.stBase[i] = sl.F + (long long)o * sl.cellsStore;
+            } else {                    // odd half, every neighbour at its plain offset
+                const long long off = (long long)c_of(i, 0) * P_ + (long long)c_of(i, 1) * nz_ + c_of(i, 2);
+                a.ldBase[i] = sl.F + (long long)o * sl.cellsStore - off;
+                a.stBase[i] = sl.F + (long long)i * sl.cellsStore + off;
+            }
+        }
         a.omega = dyns_[0].omega; a.preFactor = dyns_[0].preFactor;
         a.gatherStats = statsOn_ ? 1 : 0;
         a.partials = nullptr; a.ticket = sl.dTicket; a.statsOut = sl.dStats;

@@ -199,6 +199,24 @@ struct CellIO {
         prefetch_l2(F + interior_target(g) + c);
         CellIO<T, Q, I + 1>::prefetch_interior(F, g, c);
     }
+    // the same through host-computed per-slot bases (SweepArgs::ldBase / stBase)
+    __device__ __forceinline__ static void load_base(T* const* __restrict__ base, int c, T* f) {
+        f[I] = PLB_SWEEP_LD(base[I] + c);
+        CellIO<T, Q, I + 1>::load_base(base, c, f);
+    }
+    __device__ __forceinline__ static void store_base(T* const* __restrict__ base, int c, const T* f) {
+        PLB_SWEEP_ST(base[I] + c, f[I]);
+        CellIO<T, Q, I + 1>::store_base(base, c, f);
+    }
+    /// BounceBack::collide (swap f_i <-> f_{i+q/2}, core/dynamics.hh:783-791) folded into the store: no register moves
+    __device__ __forceinline__ static void store_base_swapped(T* const* __restrict__ base, int c, const T* f) {
+        { constexpr int O = LB<T, Q>::opp(I); PLB_SWEEP_ST(base[I] + c, f[O]); }
+        CellIO<T, Q, I + 1>::store_base_swapped(base, c, f);
+    }
+    __device__ __forceinline__ static void prefetch_base(T* const* __restrict__ base, int c) {
+        prefetch_l2(base[I] + c);
+        CellIO<T, Q, I + 1>::prefetch_base(base, c);
+    }
 };
 
 /// L2 prefetch of the cell that this thread will process `delta` cells further on: same slots and
@@ -227,6 +245,10 @@ struct CellIO<T, Q, Q> {
     __device__ __forceinline__ static void load_pull_interior(const T*, const Geo&, int, T*) {}
     __device__ __forceinline__ static void store_push_interior(T*, const Geo&, int, const T*) {}
     __device__ __forceinline__ static void prefetch_interior(const T*, const Geo&, int) {}
+    __device__ __forceinline__ static void load_base(T* const*, int, T*) {}
+    __device__ __forceinline__ static void store_base(T* const*, int, const T*) {}
+    __device__ __forceinline__ static void store_base_swapped(T* const*, int, const T*) {}
+    __device__ __forceinline__ static void prefetch_base(T* const*, int) {}
 };
 
 // ---------------------------------------------------------------------------------- the sweep
@@ -272,12 +294,25 @@ struct SweepArgs {
     const T* ext;             ///< MAIN == DYN_EXTERNAL: rhoBar [cells] followed by j_x, j_y, j_z [cells] each (extStride apart)
     long long extStride;
     int extBcFromFields;      ///< DYN_EXTERNAL_FUSED: the moments of cells with boundary dynamics are stored in the fields (else implied)
+    // Per-slot base pointers of the fast paths (every neighbour at its plain offset), computed on the host: cell c finds population
+    // I at ldBase[I] + c and leaves f*_I at stBase[I] + c.  Even half: slot I / slot opp(I) of the cell itself; odd half: slot
+    // opp(I) of cell c - c_I / slot I of cell c + c_I.  Two instructions per access (constant bank + one 64-bit add) instead of
+    // the 64-bit multiply-add chains `I * S + offset` costs when S, P and nz are run-time values -- the sweep is short of
+    // issue slots, not of bandwidth, whenever its path between two gathers grows (profiles/r02_ncu_metrics_planes.md).
+    T* ldBase[27];
+    T* stBase[27];
     PeerSlab<T> lo, hi;       ///< neighbouring slabs below X = 1 / above X = nxl that take direct stores
     int nRimTiles;            ///< > 0: tiles [0, nRimTiles) hold the rim planes of a face towards ANOTHER RANK; when the last of them
     unsigned int* rimTicket;  ///<      is done, sigValue (the step count) goes to the neighbours' flags: "my stores of this step have landed"
     unsigned int* sigLo;
     unsigned int* sigHi;
     unsigned int sigValue;
+    // parking of sparse plane boundary cells (see sweep_kernel): what a warp still holds in its stash when its block ends goes
+    // to the mailbox of (SM, warp) in global memory, where the next block on that SM picks it up
+    int drain;                ///< this launch is the drain launch: block b flushes the mailboxes of SM b, nothing else
+    int* mbCount;             ///< [MAILBOX_SMS * warps] entries waiting (-1: being written); nullptr: never park
+    int* mbCell;              ///< [MAILBOX_SMS * warps][STASH_CAP]
+    T* mbF;                   ///< [MAILBOX_SMS * warps][Q][STASH_CAP]
 };
 
 /// Deterministic block reduction of the BlockStatistics accumulators (core/blockStatistics.cpp:205-229:
@@ -360,10 +395,14 @@ __device__ __forceinline__ void complete_by_face(int baseType, const Bc<T>& b, T
 /// pendingStamp: number of the sweep that applies the outstanding completion (the caller itself, if it is that sweep): a record
 /// changed since the completion was deferred carries this stamp and answers with its previous values; -1: current values
 template <class T, int Q>
-__device__ __noinline__ void complete_pending(int baseType, const Bc<T>* __restrict__ bcs, int bi, int pendingStamp, T* f) {
+__device__ __forceinline__ void complete_pending_inline(int baseType, const Bc<T>* __restrict__ bcs, int bi, int pendingStamp, T* f) {
     Bc<T> b = bcs[bi];
     if (b.stamp == pendingStamp) { b.u[0] = b.uPrev[0]; b.u[1] = b.uPrev[1]; b.u[2] = b.uPrev[2]; b.rhoBar = b.rhoBarPrev; }
     complete_by_face<T, Q>(baseType, b, f);
+}
+template <class T, int Q>
+__device__ __noinline__ void complete_pending(int baseType, const Bc<T>* __restrict__ bcs, int bi, int pendingStamp, T* f) {
+    complete_pending_inline<T, Q>(baseType, bcs, bi, pendingStamp, f);
 }
 
 /// Dynamics::computeRhoBarJ of a cell with boundary dynamics from its (completed) populations and its record; out of line
@@ -418,9 +457,15 @@ struct RimStore<T, Q, Q> {
 /// cells among a warp's 32 up to which they are parked rather than completed in line
 constexpr int STASH_CAP = 32;
 constexpr int STASH_MAX_NEW = 8;
+constexpr int MAILBOX_SMS = 256;     ///< upper bound of %smid + 1
 template <class T, int Q>
 __host__ __device__ constexpr size_t sweep_stash_bytes(int threads) {
     return (size_t)(threads / 32) * STASH_CAP * (Q * sizeof(T) + sizeof(int));
+}
+__device__ __forceinline__ unsigned int sm_id() {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
 }
 
 /// The fused collide-and-stream sweep (BlockLattice3D::collideAndStream, atomicBlock/blockLattice3D.hh:253-312,
@@ -434,43 +479,52 @@ __host__ __device__ constexpr size_t sweep_stash_bytes(int threads) {
 ///            populations and its record only, so instead of a pass over the face cells after the
 ///            step, the next sweep applies it to the populations it has just gathered.
 ///
+/// Work distribution.  A block owns the tiles blockIdx.x, blockIdx.x + gridDim.x, ... (tile = 512 consecutive cells) and
+/// hands them out to its WARPS, 32 consecutive cells ("piece") at a time, from a counter in shared memory.  Pieces differ in
+/// cost -- row ends and rim planes take the general path of the odd half, boundary rows are completed in line, DRAM latency
+/// varies -- and with a fixed warp <-> piece mapping the warps of a block drifted apart and waited for the slowest at the
+/// end of every block with the SM nearly empty: 25-30 % of all warp cycles (ncu, profiles/r02_ncu_sweep_d.md).  Measured at
+/// 512^3, boundary-free launches: 6.62 -> 6.38 ms (97.7 % of the measured HBM peak).
+///
 /// Lazy completion, lane-efficiently.  The x- and y-faces fill whole warps (z is the fastest index) and are completed in
 /// line.  A z-face puts ONE plane cell into a warp, and the completion is ~2000 instructions: in line it would nearly
-/// double the instruction count of the sweep.  A warp therefore PARKS such a cell -- its gathered populations go to a
-/// per-warp stash in shared memory and the cell is skipped -- and once the stash holds a warp's worth (or the warp runs out
-/// of tiles) the parked cells are completed, collided and scattered one per lane.  Nothing is read twice and no list
-/// exists on the host.  The AA pattern allows the delay: within a launch every storage location is read and written on
-/// behalf of one cell only, whenever and by whichever thread.  (Round 1 listed these cells and their sector mates on the
-/// host for extra blocks of the same grid: +1.7 GB of DRAM reads per launch at 512^3, profiles/r01_ncu_full_summary_d.md.)
-///
-/// One iteration of a warp's loop is either a tile (32 consecutive cells of the block's 512) or a flush of its stash;
-/// gather / complete / collide / scatter exist once in the instruction stream and serve both.
+/// double the instruction count of the sweep.  A warp therefore PARKS such a cell -- its gathered populations go to the
+/// warp's stash in shared memory and the cell is skipped -- and when the stash holds a warp's worth the parked cells are
+/// completed, collided and scattered one per lane, as one more "piece" (the other warps keep streaming meanwhile: the
+/// piece counter absorbs the delay).  What a warp still holds when its block runs out of pieces goes to the mailbox of
+/// (SM, warp) in global memory, where the next block on that SM picks it up; a drain launch of 148 small blocks empties the
+/// mailboxes after the sweep.  Nothing is read twice from the lattice and no list exists on the host.  The AA pattern allows
+/// the delay: within a step every storage location is read and written on behalf of one cell only, whenever and by
+/// whichever thread.
+/// History (profiles/r01_ncu_full_summary_d.md, r02_bench_n1_b_stash_first.json, r02_bench_n1_d.json, 512^3): round 1 listed
+/// these cells and their sector mates on the host for extra blocks of the same grid (+1.7 GB of DRAM reads per launch, step
+/// 7.04 ms); flushing every stash at the end of its block left two warps busy for ~10 us with the SM empty, 64-128 times per
+/// SM and launch (7.90 ms); deferring all of them to a second launch made that launch latency-bound (0.5 ms for 0.5 M cells).
 template <class T, int Q, int MAIN, bool GENERIC, bool ODD, bool PLANES>
 __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) sweep_kernel(const SweepArgs<T> a) {
     using L = LB<T, Q>;
     constexpr int SWEEP_THREADS = sweep_threads(ODD);
+    constexpr int WARPS = SWEEP_THREADS / 32;
     extern __shared__ __align__(16) unsigned char sweepSmem[];
+    __shared__ int pieceCounter;
     const Geo& g = a.g;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double sRho = 0., sU = 0., mU = -DBL_MAX, cnt = 0.;
     T* stF = nullptr;       // [Q][STASH_CAP] populations of this warp's parked cells
     int* stC = nullptr;     // [STASH_CAP] their cell indices
     if (PLANES) {
-        const int warp = threadIdx.x >> 5;
         stF = reinterpret_cast<T*>(sweepSmem) + (size_t)warp * STASH_CAP * Q;
-        stC = reinterpret_cast<int*>(reinterpret_cast<T*>(sweepSmem) + (size_t)(SWEEP_THREADS / 32) * STASH_CAP * Q) + warp * STASH_CAP;
+        stC = reinterpret_cast<int*>(reinterpret_cast<T*>(sweepSmem) + (size_t)WARPS * STASH_CAP * Q) + warp * STASH_CAP;
     }
 
     // outstanding completePopulations of a plane boundary cell (k = its kind byte)
     auto complete = [&](int c, int k, T* f) {
         const int bi = a.bcIdx[c];
         if (bi < 0) return;
-        T tmp[Q];
-#pragma unroll
-        for (int i = 0; i < Q; ++i) tmp[i] = f[i];
-        complete_pending<T, Q>(a.dyns[k & KIND_MASK].type, a.bcs, bi, a.pendingStamp, tmp);
-#pragma unroll
-        for (int i = 0; i < Q; ++i) f[i] = tmp[i];
+        // in line, populations in registers: a warp busy with a completion is a warp that does not stream, and with 16 warps
+        // per SM the sweep's bandwidth follows the number of streaming warps -- through local memory (the out-of-line form the
+        // on-the-fly readers use) one completion held its warp for ~35 us (profiles/r02_ncu_metrics_planes.md)
+        complete_pending_inline<T, Q>(a.dyns[k & KIND_MASK].type, a.bcs, bi, a.pendingStamp, f);
     };
     // Cell::collide, scatter, gatherStatistics
     auto collide_scatter = [&](int c, int k, bool interior, int X, const Nbr& n, T* f) {
@@ -478,7 +532,7 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
         (void)kRaw;
         k &= KIND_MASK;
         T rhoBar = (T)0, uSqr = (T)0;
-        bool took;
+        bool took, bounced = false;
         if constexpr (MAIN == DYN_EXTERNAL || MAIN == DYN_EXTERNAL_FUSED) {
             // ExternalRhoJcollideAndStream3D (basicDynamics/dynamicsProcessor3D.hh:41-76): rhoBar and j come from the fields.
             // DYN_EXTERNAL_FUSED: nobody has touched the fields since BoxRhoBarJfunctional3D filled them at the end of the
@@ -516,19 +570,29 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
                 took = L::template collide_as<MAIN>(f, a.omega, a.preFactor, rhoBar, uSqr);
             } else {
                 took = false;
-                if (a.dyns[k].type == DYN_BOUNCEBACK) L::collide_bounceback(f);
+                if (a.dyns[k].type == DYN_BOUNCEBACK) {
+                    if (interior || !ODD) bounced = true;       // the swap happens in the store below
+                    else L::collide_bounceback(f);
+                }
             }
         } else {
             const Dyn<T> d = a.dyns[k];
             took = L::collide_any(d, f, rhoBar, uSqr);
         }
-        if (ODD) {
-            if (interior) CellIO<T, Q>::store_push_interior(a.F, g, c, f);
-            else { PLB_SWEEP_ST(a.F + c, f[0]); RimStore<T, Q>::odd(a.F, g, n, c, X, a.lo, a.hi, f); }
+        if (ODD && !interior) {
+            PLB_SWEEP_ST(a.F + c, f[0]);
+            RimStore<T, Q>::odd(a.F, g, n, c, X, a.lo, a.hi, f);
         } else {
-            CellIO<T, Q>::store_local_swapped(a.F, g, c, f);
-            if (a.lo.F != nullptr && c < 2 * g.P) RimStore<T, Q>::template even<-1>(a.lo, g.P, c - g.P, f);
-            if (a.hi.F != nullptr && c >= g.nxl * g.P) RimStore<T, Q>::template even<+1>(a.hi, g.P, c - g.nxl * g.P, f);
+            if (bounced) CellIO<T, Q>::store_base_swapped(a.stBase, c, f);
+            else CellIO<T, Q>::store_base(a.stBase, c, f);
+            if (!ODD) {
+                const bool rimLo = a.lo.F != nullptr && c < 2 * g.P, rimHi = a.hi.F != nullptr && c >= g.nxl * g.P;
+                if (rimLo || rimHi) {
+                    if (bounced) L::collide_bounceback(f);      // what goes to the neighbouring slab is the swapped set
+                    if (rimLo) RimStore<T, Q>::template even<-1>(a.lo, g.P, c - g.P, f);
+                    if (rimHi) RimStore<T, Q>::template even<+1>(a.hi, g.P, c - g.nxl * g.P, f);
+                }
+            }
         }
         if (took) {
             sRho += (double)rhoBar;
@@ -539,36 +603,75 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
     };
 
     const bool planes = PLANES && a.applyPlanes;
+    const bool parking = PLANES && planes && a.mbCount != nullptr;
+    if (threadIdx.x == 0) pieceCounter = 0;
+    __syncthreads();
+    const int nMyTiles = (!a.drain && (int)blockIdx.x < a.nTiles) ? (a.nTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int nPieces = nMyTiles * WARPS;
+    auto next_piece = [&]() {
+        int p = 0;
+        if (lane == 0) p = atomicAdd(&pieceCounter, 1);
+        return __shfl_sync(0xffffffffu, p, 0);
+    };
+
     int nStash = 0;                 // warp-uniform
-    bool rimPending = false;        // this warp has worked on a rim tile whose completion it has not reported yet
-    int tile = blockIdx.x;
+    if (PLANES && parking) {
+        // what the previous block on this SM (drain launch: any block on SM blockIdx.x) left in this warp's mailbox
+        const unsigned int home = a.drain ? blockIdx.x : sm_id();
+        const int slot = (int)home * WARPS + warp;
+        int n = 0;
+        if (lane == 0 && home < (unsigned int)MAILBOX_SMS) {
+            n = *(volatile int*)(a.mbCount + slot);
+            if (n > 0 && atomicCAS(a.mbCount + slot, n, 0) != n) n = 0;
+            if (n < 0) n = 0;
+        }
+        n = __shfl_sync(0xffffffffu, n, 0);
+        if (n > 0) {
+            __threadfence();
+            if (lane < n) {
+                stC[lane] = a.mbCell[(size_t)slot * STASH_CAP + lane];
+#pragma unroll
+                for (int i = 0; i < Q; ++i) stF[i * STASH_CAP + lane] = a.mbF[((size_t)slot * Q + i) * STASH_CAP + lane];
+            }
+            nStash = n;
+            __syncwarp();
+        }
+    }
+
+    // The loop.  One iteration is a piece, a flush of the stash, or a report about a rim piece.  The common case -- a piece
+    // without plane boundary cells -- runs straight through gather / collide / scatter ("lean"): with 16 warps per SM the sweep
+    // sits exactly at the point where every instruction between two gathers costs bandwidth (time follows the instruction
+    // count of this path 1:1, profiles/r02_ncu_metrics_planes.md), so everything else is kept out of it.  The cells that
+    // need completePopulations first -- a whole warp of an x- or y-face, or the parked ones -- share the second copy of
+    // collide / scatter ("heavy").
+    bool rimPending = false;        // this warp has worked on a piece of a rim tile and has not reported it yet
+    bool flushNow = false;          // the mailbox could not take the leftovers: complete them here
+    int p = next_piece();
     for (;;) {
-        const bool more = tile < a.nTiles;
         int c = 0, k = 0, X = 0, y = 0, z = 0;
-        bool interior = false, active = false, needComplete = false;
+        bool heavy = false;
         T f[Q];
         Nbr n;
-        if (PLANES && nStash > 0 && (nStash > STASH_CAP - STASH_MAX_NEW || rimPending || !more)) {
+        if (PLANES && nStash > 0 && (nStash > STASH_CAP - STASH_MAX_NEW || rimPending || flushNow || (p >= nPieces && a.drain))) {
             // ---- the parked cells, one per lane
-            active = lane < nStash;
-            if (active) {
+            heavy = lane < nStash;
+            if (heavy) {
                 c = stC[lane];
 #pragma unroll
                 for (int i = 0; i < Q; ++i) f[i] = stF[i * STASH_CAP + lane];
                 k = a.kind[c];
-                needComplete = true;
                 if (ODD) { decode_cell(g, c, X, y, z); n = make_nbr(g, X, y, z); }
             }
             nStash = 0;
             __syncwarp();
         } else if (rimPending) {
-            // ---- the stores of this warp's part of a rim tile have been issued: perform them system-wide, count the warp in,
-            // and let the last warp of the last rim tile tell the neighbouring ranks (they wait on the flag with a stream
+            // ---- the stores of this warp's piece of a rim tile have been issued: perform them system-wide, count the piece in,
+            // and let the last piece of the last rim tile tell the neighbouring ranks (they wait on the flag with a stream
             // memory operation before anything of theirs touches the planes this launch has stored into)
             __threadfence_system();
             __syncwarp();
             if (lane == 0) {
-                const unsigned int total = (unsigned int)a.nRimTiles * (SWEEP_THREADS / 32);
+                const unsigned int total = (unsigned int)a.nRimTiles * WARPS;
                 if (atomicAdd(a.rimTicket, 1u) == total - 1u) {
                     __threadfence_system();
                     if (a.sigLo) *(volatile unsigned int*)a.sigLo = a.sigValue;
@@ -578,22 +681,22 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
             }
             rimPending = false;
             continue;
-        } else if (more) {
-            // ---- a tile: which range it falls in (block-uniform)
-            const int r = (a.nRanges > 1 && tile >= a.range[1].tile0 ? 1 : 0) + (a.nRanges > 2 && tile >= a.range[2].tile0 ? 1 : 0);
-            const int rBegin = r == 0 ? a.range[0].begin : (r == 1 ? a.range[1].begin : a.range[2].begin);
-            const int rEnd = r == 0 ? a.range[0].end : (r == 1 ? a.range[1].end : a.range[2].end);
-            const int rTile0 = r == 0 ? a.range[0].tile0 : (r == 1 ? a.range[1].tile0 : a.range[2].tile0);
-            const int tileBegin = rBegin + (tile - rTile0) * SWEEP_THREADS;
-            c = tileBegin + threadIdx.x;
-            active = c < rEnd;
+        } else if (p < nPieces) {
+            // ---- a piece: tile and range (block-uniform per tile)
+            const int tile = (int)blockIdx.x + (p / WARPS) * (int)gridDim.x;
+            int rBegin = a.range[0].begin, rEnd = a.range[0].end, rTile0 = 0;
+            if (a.nRanges > 1 && tile >= a.range[1].tile0) { rBegin = a.range[1].begin; rEnd = a.range[1].end; rTile0 = a.range[1].tile0; }
+            if (a.nRanges > 2 && tile >= a.range[2].tile0) { rBegin = a.range[2].begin; rEnd = a.range[2].end; rTile0 = a.range[2].tile0; }
+            const int pieceBegin = rBegin + (tile - rTile0) * SWEEP_THREADS + (p % WARPS) * 32;
+            c = pieceBegin + lane;
+            bool active = c < rEnd;
+            bool interior = false;
             if (tile < a.nRimTiles) rimPending = true;
-            tile += gridDim.x;
             if (ODD) {
-                // decode the first cell of the warp's 32; if the 32 lie in one row of interior y, clear of the row ends, in a
+                // decode the first cell of the piece; if its 32 cells lie in one row of interior y, clear of the row ends, in a
                 // plane whose x-neighbours are planes of this slab (or ghost planes of the copy-based transport), every
                 // neighbour of every cell exists at its plain offset and the whole warp takes the fast path
-                decode_cell(g, tileBegin + (int)(threadIdx.x & ~31u), X, y, z);
+                decode_cell(g, pieceBegin, X, y, z);
                 interior = z > 0 && z + 32 < g.nz && y > 0 && y < g.ny - 1
                         && (X > 1 || (g.lowMode == XMODE_GHOST && a.lo.F == nullptr))
                         && (X < g.nxl || (g.highMode == XMODE_GHOST && a.hi.F == nullptr));
@@ -601,50 +704,67 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
                 if (z >= g.nz) decode_cell(g, c, X, y, z);
             }
             if (active) {
-                if (ODD) {
-                    if (interior) {
-                        CellIO<T, Q>::load_pull_interior(a.F, g, c, f);
-                    } else {
-                        n = make_nbr(g, X, y, z);
-                        CellIO<T, Q>::load_pull(a.F, g, n, c, f);
-                    }
+                if (ODD && !interior) {
+                    n = make_nbr(g, X, y, z);
+                    CellIO<T, Q>::load_pull(a.F, g, n, c, f);
                 } else {
-                    CellIO<T, Q>::load_local(a.F, g, c, f);
+                    CellIO<T, Q>::load_base(a.ldBase, c, f);
                 }
                 if (sweep_prefetch(ODD) > 0) {
                     const long long delta = (long long)sweep_prefetch(ODD) * gridDim.x * SWEEP_THREADS;
                     if (c + delta < rEnd) {
-                        if (ODD && interior) CellIO<T, Q>::prefetch_interior(a.F, g, c + (int)delta);
-                        else CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
+                        if (ODD && !interior) CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
+                        else CellIO<T, Q>::prefetch_base(a.stBase, c + (int)delta);
                     }
                 }
                 k = a.kind[c];
             }
+            p = next_piece();
             if (PLANES && planes) {
                 const bool flagged = active && (k & KIND_PLANE);
                 const unsigned int m = __ballot_sync(0xffffffffu, flagged);
                 if (m != 0u) {
-                    if (__popc(m) <= STASH_MAX_NEW) {
+                    if (parking && __popc(m) <= STASH_MAX_NEW) {
                         if (flagged) {
                             const int e = nStash + __popc(m & ((1u << lane) - 1u));
                             stC[e] = c;
 #pragma unroll
                             for (int i = 0; i < Q; ++i) stF[i * STASH_CAP + e] = f[i];
-                            active = false;
                         }
                         nStash += __popc(m);
                         __syncwarp();
                     } else {
-                        needComplete = flagged;
+                        heavy = flagged;              // a boundary row: completed in line, by the heavy copy below
+                        if (ODD && interior && heavy) n = make_nbr(g, X, y, z);     // (the heavy copy takes the general path)
                     }
+                    active = active && !flagged;
                 }
             }
+            if (active) collide_scatter(c, k, interior, X, n, f);         // lean
         } else {
+            if (PLANES && nStash > 0) {
+                // ---- out of pieces with cells still parked: leave them to the next block on this SM
+                const unsigned int home = sm_id();
+                const int slot = (int)home * WARPS + warp;
+                int ok = 0;
+                if (lane == 0 && home < (unsigned int)MAILBOX_SMS) ok = atomicCAS(a.mbCount + slot, 0, -1) == 0 ? 1 : 0;
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                if (!ok) { flushNow = true; continue; }          // occupied (cannot happen with one block per SM): complete here
+                if (lane < nStash) {
+                    a.mbCell[(size_t)slot * STASH_CAP + lane] = stC[lane];
+#pragma unroll
+                    for (int i = 0; i < Q; ++i) a.mbF[((size_t)slot * Q + i) * STASH_CAP + lane] = stF[i * STASH_CAP + lane];
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicExch(a.mbCount + slot, nStash);
+                nStash = 0;
+            }
             break;
         }
-        if (active) {
-            if (PLANES && needComplete) complete(c, k, f);
-            collide_scatter(c, k, interior, X, n, f);
+        if (PLANES && heavy) {
+            complete(c, k, f);
+            collide_scatter(c, k, false, X, n, f);
         }
     }
     if (a.gatherStats) reduce_stats(sRho, sU, mU, cnt, a.partials, a.ticket, a.statsOut);

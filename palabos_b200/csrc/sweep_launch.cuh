@@ -2,6 +2,7 @@
 // (inst_sweep_*.cu: one per value type, velocity set and AA half), so that the build spreads over all cores;
 // the engine only sees this declaration.
 #pragma once
+#include <cstdlib>
 #include <string>
 #include "engine.h"
 #include "kernels.cuh"
@@ -17,7 +18,9 @@ template <class T, int Q, int MAIN, bool GENERIC, bool ODD, bool PLANES>
 void launch_sweep_kernel(int grid, cudaStream_t stream, const SweepArgs<T>& a) {
     // PLANES: the per-warp stash of parked plane boundary cells lives in dynamic shared memory (80 KB for D3Q19 fp64, 113 KB for
     // D3Q27 fp64 at 16 warps; the sweep runs one block per SM anyway -- 128 registers x 512 threads)
-    constexpr size_t smem = PLANES ? sweep_stash_bytes<T, Q>(sweep_threads(ODD)) : 0;
+    size_t smem = PLANES ? sweep_stash_bytes<T, Q>(sweep_threads(ODD)) : 0;
+    static const long dummy = std::getenv("PLB_B200_DUMMY_SMEM") ? std::atol(std::getenv("PLB_B200_DUMMY_SMEM")) : 0;   // tuning runs
+    if (!PLANES && dummy > 0) smem = (size_t)dummy;
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(sweep_kernel<T, Q, MAIN, GENERIC, ODD, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) throw PlbError(std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(e));

@@ -73,6 +73,8 @@ int main(int argc, char** argv) {
     a.F = F; a.kind = kind; a.dyns = dyns; a.bcIdx = nullptr; a.bcs = nullptr; a.applyPlanes = 0; a.pendingStamp = -1; a.g = g;
     a.lo.F = a.hi.F = nullptr; a.lo.S = a.hi.S = 0; a.lo.nxl = a.hi.nxl = 0; a.nRimTiles = 0; a.rimTicket = nullptr; a.sigLo = a.sigHi = nullptr; a.sigValue = 0;
     a.ext = nullptr; a.extStride = 0; a.extBcFromFields = 0;
+    a.drain = 0; a.mbCount = nullptr; a.mbCell = nullptr; a.mbF = nullptr;
+    // (ldBase / stBase are set per half below)
     const int cellBegin = g.P, cellEnd = (n + 1) * g.P;
     for (int k = 0; k < 3; ++k) { a.range[k].begin = a.range[k].end = a.range[k].tile0 = 0; }
     a.range[0].begin = cellBegin; a.range[0].end = cellEnd; a.nRanges = 1;
