@@ -57,7 +57,7 @@ def kernel_sources_hash():
     """sha256 over the sources of the sweep kernel -- the key profiles/traffic.json is valid for"""
     import hashlib
     h = hashlib.sha256()
-    for f in ("lb_core.cuh", "kernels.cuh", "sweep_launch.cuh", "Makefile"):
+    for f in ("lb_core.cuh", "cell_io.cuh", "sweep_kernel.cuh", "kernels.cuh", "sweep_launch.cuh", "Makefile"):
         h.update(open(os.path.join(ROOT, "palabos_b200", "csrc", f), "rb").read())
     return h.hexdigest()
 

@@ -49,10 +49,10 @@ class LatticeImpl : public LatticeBase {
         T* dExt = nullptr;                 ///< external-moment sweep: rhoBar [cellsStore] | j_x | j_y | j_z, zero where nothing writes
         int* dBcCells = nullptr; size_t dBcCellsCap = 0;   ///< ... cells that carry a boundary record (-1: dead record)
         int nBcCells = 0;
-        double* dStats = nullptr;          ///< [2][4] sum rhoBar, sum uSqr, max uSqr, cell count of the last sweep and of its drain launch
-        int statSlots = 0;                 ///< launches of the last step that have reported
+        double* dStats = nullptr;          ///< [4] sum rhoBar, sum uSqr, max uSqr, cell count of the last sweep
+        int statSlots = 0;                 ///< 1 once a sweep has reported
         unsigned int* dTicket = nullptr;
-        int nAuto = 0;                     ///< items [0, nAuto): plane cells that complete at collision time (never executed as a stage)
+        int nAuto = 0;                     ///< items [0, nAuto): plane cells that complete at collision time (completed right before the sweep, never as a stage)
         std::vector<uint8_t> hKind;
         std::vector<BcRec> recs;
         std::vector<Group> groups;
@@ -61,10 +61,6 @@ class LatticeImpl : public LatticeBase {
         std::vector<int> stageSplit;       ///< ... plane items first, finite-difference items from stageSplit[s]
         size_t nItems = 0;
         unsigned int* dRimTicket = nullptr; ///< counts the rim tiles of a launch that signals a neighbouring rank
-        int* dMbCount = nullptr;            ///< mailboxes of the parked plane boundary cells (sweep_kernel), one per (SM, warp)
-        int* dMbCell = nullptr;
-        T* dMbF = nullptr;
-        bool deferWanted = false;           ///< the slab has plane cells that sit alone in their warp (z-faces): park them
         bool valuesOnDevice = false;       ///< the records on the device hold newer u / rhoBar than `recs` (set_values_on_device)
         bool dirtyKind = true, dirtyBcIndex = true, dirtySched = true;
         bool kindUnflagged = true;         ///< dKind was uploaded from hKind and carries no KIND_PLANE flags
@@ -82,10 +78,7 @@ class LatticeImpl : public LatticeBase {
     bool dirtyDyns_ = true;
     std::vector<Proc> procs_;
     bool swapped_ = false;
-    bool allowFuse_ = true;                  ///< PLB_B200_EAGER_PLANES=1 in the environment turns the fusion off (A/B tests)
-    bool autoPlanes_ = false;                ///< some plane boundaries complete at collision time (dynamics-based models): those are the flagged cells, the wrapped ones run eagerly
-    bool fused_ = false;                     ///< stage-0 plane items are completed by the next sweep, not by plane_stage_kernel
-    bool pending_ = false;                   ///< ... and that completion is currently outstanding in storage
+    bool autoPlanes_ = false;                ///< some plane boundaries complete at collision time (dynamics-based models)
     bool statsOn_ = true;
     bool ext_ = false;                       ///< the lattice is stepped by ExternalRhoJcollideAndStream3D + BoxRhoBarJfunctional3D
     int bulk_[6] = {0, 0, 0, 0, 0, 0};       ///< ... whose level-3 domain is this box (the user's lattice; the rest is envelope)
@@ -133,7 +126,6 @@ public:
         G_ = d.nRanks * d.slabsPerRank;
         if (G_ > nx_) throw PlbError("more slabs than x-planes");
         if ((long long)ny_ * nz_ >= (1ll << 30)) throw PlbError("y-z plane too large");
-        if (const char* e = std::getenv("PLB_B200_EAGER_PLANES")) allowFuse_ = !(e[0] == '1');
         if (const char* e = std::getenv("PLB_B200_HALO")) direct_ = !(std::strcmp(e, "nccl") == 0 || std::strcmp(e, "copy") == 0);
         if (const char* e = std::getenv("PLB_B200_EXT_EXPLICIT")) extFuse_ = !(e[0] == '1');
         add_dyn(d.dynamics, d.p1, d.p2);     // entry 0: the background dynamics
@@ -153,7 +145,7 @@ public:
             PLB_CUDA(cudaMemsetAsync(sl.F, 0, nF * sizeof(T), stream_));
             sl.dKind = (uint8_t*)dev_alloc(sl.cellsStore);
             sl.dBcIdx = (int*)dev_alloc(sl.cellsStore * sizeof(int));
-            sl.dStats = (double*)dev_alloc(2 * 4 * sizeof(double));
+            sl.dStats = (double*)dev_alloc(4 * sizeof(double));
             sl.dRimTicket = (unsigned int*)dev_alloc(sizeof(unsigned int));
             PLB_CUDA(cudaMemsetAsync(sl.dRimTicket, 0, sizeof(unsigned int), stream_));
             sl.dTicket = (unsigned int*)dev_alloc(sizeof(unsigned int));
@@ -174,7 +166,7 @@ public:
         cudaFree(dFlags_);
         for (Slab& sl : slabs_) {
             cudaFree(sl.F); cudaFree(sl.dExt); cudaFree(sl.dBcCells); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems);
-            cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket); cudaFree(sl.dRimTicket); cudaFree(sl.dMbCount); cudaFree(sl.dMbCell); cudaFree(sl.dMbF);
+            cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket); cudaFree(sl.dRimTicket);
         }
         cudaFree(dDyns_); cudaFree(dStage_); cudaFree(dReduce_);
         if (comm_) NcclApi::get().CommDestroy(comm_);
@@ -376,7 +368,6 @@ public:
         check_box(box);
         ext_detach();
         sync_setup();
-        materialize();
         for (Slab& sl : slabs_) {
             BoxL b;
             if (!local_box(sl, box, b)) continue;
@@ -392,7 +383,6 @@ public:
         if (!ru) throw PlbError("null field");
         ext_detach();
         sync_setup();
-        materialize();
         const long long rowCells = (long long)(box[3] - box[2] + 1) * (box[5] - box[4] + 1);
         for (Slab& sl : slabs_) {
             BoxL b;
@@ -441,7 +431,6 @@ public:
         std::memcpy(bulk_, bulk, sizeof bulk_);
         ext_ = true;
         extImplied_ = false; extComplete_ = true; extBcStored_ = true;   // zero fields, as generateMultiScalarField / generateMultiTensorField leave them
-        if (!extFuse_) allowFuse_ = false;     // the stored-fields path reads completed populations right after the processors
         for (Slab& sl : slabs_) sl.dirtySched = true;
     }
 
@@ -458,7 +447,6 @@ public:
         int b[6];
         if (!intersect(box, bulk_, b)) return;
         sync_setup();
-        materialize();
         const bool whole = std::memcmp(b, bulk_, sizeof b) == 0;
         if (!whole) ext_complete();            // the rest of the fields keeps its values
         rhobar_j_box(b);
@@ -540,7 +528,6 @@ public:
         check_box(box);
         if (bytes != local_bytes(box) / Q * 4) throw PlbError("buffer size does not match the box");
         sync_setup();
-        materialize();
         char* host = (char*)out;
         for (Slab& sl : slabs_) {
             BoxL b;
@@ -580,14 +567,14 @@ public:
     }
     void advance_steps(int n, bool ext) {
         for (int s = 0; s < n; ++s) {
-            if (ext && !(extImplied_ && extFuse_)) materialize();   // the stored-fields sweep has no completion on load
             // One launch per slab: rim planes first (their stores go to the neighbouring slab), then the interior.  With the
             // direct transport nothing else is needed -- the neighbour reads what was stored into it one step later; the wait
             // below only orders this rank's NEXT accesses to its rim / ghost planes after the neighbours' stores of THIS step.
             ++stepCount_;
+            // plane cells of the dynamics-based boundary managers complete at collision time: right before the sweep
+            for (Slab& sl : slabs_) if (sl.nAuto > 0) launch_plane_stage(sl, 0, sl.nAuto);
             for (Slab& sl : slabs_) launch_sweep(sl);
             swapped_ = !swapped_;
-            pending_ = false;                  // the sweep has applied the outstanding completion
             if (direct_) wait_neighbours();
             else exchange_copies(stream_);
             exchange_unpack();
@@ -616,11 +603,11 @@ public:
         if (stepped_ && statsOn_) {
             PLB_CUDA(cudaStreamSynchronize(stream_));
             for (Slab& sl : slabs_) {
-                double h[8];
+                double h[4];
                 PLB_CUDA(cudaMemcpy(h, sl.dStats, sizeof h, cudaMemcpyDeviceToHost));
-                for (int k = 0; k < sl.statSlots; ++k) {
-                    sum[0] += h[4 * k]; sum[1] += h[4 * k + 1]; sum[2] += h[4 * k + 3];
-                    mx = std::max(mx, h[4 * k + 2]);
+                if (sl.statSlots > 0) {
+                    sum[0] += h[0]; sum[1] += h[1]; sum[2] += h[3];
+                    mx = std::max(mx, h[2]);
                 }
             }
         }
@@ -738,8 +725,7 @@ private:
     CellCtx<T> ctx(const Slab& sl) const {
         CellCtx<T> c;
         c.F = sl.F; c.kind = sl.dKind; c.bcIdx = sl.dBcIdx; c.dyns = dDyns_; c.bcs = sl.dBcs;
-        c.g = geo(sl); c.swapped = swapped_; c.pending = pending_;
-        c.pendingStamp = (int)(stepCount_ + 1);     // the next sweep applies what is pending now
+        c.g = geo(sl); c.swapped = swapped_;
         return c;
     }
 
@@ -846,7 +832,7 @@ private:
             for (int k = 0; k < nParts; ++k) {
                 const long long n = parts[k].cells();
                 set_bc_values_kernel<T, Q><<<(unsigned)((n + 127) / 128), 128, 0, stream_>>>(
-                    sl.dBcIdx, sl.dBcs, geo(sl), parts[k], what, u[0], u[1], u[2], rhoBar, (int)(stepCount_ + 1));
+                    sl.dBcIdx, sl.dBcs, geo(sl), parts[k], what, u[0], u[1], u[2], rhoBar);
                 launched();
             }
             sl.valuesOnDevice = true;
@@ -945,7 +931,7 @@ private:
                     if (!sl.cellToRec.count(cell)) continue;
                     if (p.a == 1) {            // completes at collision time: no processor, no dependencies
                         Item it;
-                        it.cell = cell; it.cls = (signed char)PROC_PLANE; it.a = 1; it.b = 0; it.c = 0;
+                        it.cell = cell; it.bc = sl.cellToRec.at(cell); it.cls = (signed char)PROC_PLANE; it.a = 1; it.b = 0; it.c = 0;
                         items.push_back(it);
                         stageOf.push_back(-1);
                         continue;
@@ -982,6 +968,8 @@ private:
                 lastWrite[cell] = st;
                 Item it;
                 it.cell = cell; it.cls = (signed char)p.cls; it.a = (signed char)p.a; it.b = (signed char)p.b; it.c = (signed char)p.c;
+                it.bc = -1;
+                if (p.cls == PROC_PLANE) it.bc = sl.cellToRec.at(cell);
                 items.push_back(it);
                 stageOf.push_back(st);
             }
@@ -998,19 +986,8 @@ private:
         std::vector<int> cursor(count0.begin(), count0.begin() + nBuckets);
         for (size_t k = 0; k < items.size(); ++k) sorted[cursor[bucket(k)]++] = items[k];
         sl.nAuto = count0[1];
-        // count[2*stage + (0|1)] as before; the cells the sweep completes on load: the automatic ones if the lattice has
-        // any (the wrapped ones then run eagerly), else the wrapped plane items of stage 0
+        // count[2*stage + (0|1)] as before
         const int* count = count0.data() + 1;
-        {
-            // do plane cells that the sweep completes on load sit alone in the 32-cell piece a warp covers (a z-face: one per
-            // row)?  Then the sweep defers them to its drain launch (sweep_kernel); the device decides cell by cell, this only
-            // switches the mechanism on
-            const int flagLo = autoPlanes_ ? 0 : (nStages > 0 ? count[0] : 0), flagHi = autoPlanes_ ? sl.nAuto : (nStages > 0 ? count[1] : 0);
-            std::unordered_map<int, int> perPiece;
-            for (int k = flagLo; k < flagHi; ++k) ++perPiece[(sorted[k].cell - P_) / 32];
-            sl.deferWanted = false;
-            for (const auto& kv : perPiece) if (kv.second <= STASH_MAX_NEW) { sl.deferWanted = true; break; }
-        }
         sl.stageOffsets.assign(nStages + 1, 0);
         sl.stageSplit.assign(nStages, 0);
         for (int st = 0; st < nStages; ++st) { sl.stageOffsets[st] = count[2 * st]; sl.stageSplit[st] = count[2 * st + 1]; }
@@ -1027,28 +1004,18 @@ private:
         }
     }
 
-    /// Run the outstanding plane completion as a pass of its own (what the eager path does after
-    /// every step).  Needed before anything changes its inputs (boundary records, dynamics, uploaded
-    /// or re-initialised populations) and before the populations are read back in bulk.
-    void materialize() {
-        if (!pending_) return;
-        for (Slab& sl : slabs_) {
-            if (sl.stageOffsets.size() < 2) continue;
-            const int first = sl.stageOffsets[0], split = sl.stageSplit[0];
-            if (split > first) {
-                const int n = split - first;
-                plane_stage_kernel<T, Q><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
-                launched();
-            }
-        }
-        pending_ = false;
+    /// completePopulations of the plane items [first, first + n) of a slab, in the current layout
+    void launch_plane_stage(Slab& sl, int first, int n) {
+        if (n <= 0) return;
+        if (swapped_) plane_stage_kernel<T, Q, true><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
+        else plane_stage_kernel<T, Q, false><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
+        launched();
     }
 
     void sync_setup() {
         bool anyDirty = dirtyDyns_;
         for (Slab& sl : slabs_) anyDirty = anyDirty || sl.dirtyKind || sl.dirtyBcIndex || sl.dirtySched || sl.bcDirtyHi > sl.bcDirtyLo;
         if (!anyDirty) return;
-        materialize();                         // with the device state the completion was deferred under
         pull_record_values();
         bool reflag = false;
         bool structural = false;               // (external-moment sweep) which cells read their moments from the fields may have changed
@@ -1130,51 +1097,27 @@ private:
             if (sl.dirtySched) { build_schedule(sl); sl.dirtySched = false; reflag = true; }
             if (sl.kindUnflagged) reflag = true;
         }
-        if (reflag) {
-            // fuse when every plane item is in stage 0, i.e. no processor of the reference's sequence
-            // reads or writes a plane cell before its completion runs (then "complete on load" == eager)
-            fused_ = allowFuse_ && !autoPlanes_;
-            for (Slab& sl : slabs_)
-                for (size_t s = 1; s + 1 < sl.stageOffsets.size(); ++s)
-                    if (sl.stageSplit[s] > sl.stageOffsets[s]) fused_ = false;
+        if (ext_ && (structural || reflag)) {
+            // KIND_PLANE (external-moment sweep): "boundary dynamics on top, or envelope layer" -- the cells whose moments are
+            // not those of a bulk cell
             for (Slab& sl : slabs_) {
-                if (!sl.kindUnflagged) {   // drop flags of an earlier schedule
+                if (!sl.kindUnflagged) {   // drop the flags of an earlier set-up
                     PLB_CUDA(cudaMemcpyAsync(sl.dKind, sl.hKind.data(), (size_t)sl.cellsStore, cudaMemcpyHostToDevice, stream_));
                     PLB_CUDA(cudaStreamSynchronize(stream_));
                 }
-                sl.kindUnflagged = false;
-                int first = 0, n = 0;
-                if (autoPlanes_) { first = 0; n = sl.nAuto; }
-                else if (fused_ && sl.stageOffsets.size() >= 2) { first = sl.stageOffsets[0]; n = sl.stageSplit[0] - sl.stageOffsets[0]; }
-                if (n > 0) {
-                    flag_plane_cells_kernel<<<(n + 255) / 256, 256, 0, stream_>>>(sl.dItems + first, n, sl.dKind);
-                    launched();
-                }
-            }
-        }
-        if (ext_ && (structural || reflag)) {
-            // KIND_PLANE means more in this mode: "boundary dynamics on top, or envelope layer" -- the cells whose moments are
-            // not those of a bulk cell (the block above has just restored the kind bytes and flagged the fused plane cells,
-            // a subset of these; completing a cell without a plane record is a no-op)
-            for (Slab& sl : slabs_) {
                 BoxL lb;
                 if (!local_box(sl, bulk_, lb)) { lb.X0 = 1; lb.X1 = 0; lb.y0 = lb.z0 = 0; lb.y1 = lb.z1 = -1; }
                 flag_ext_cells_kernel<<<(unsigned)((sl.cellsStore + 255) / 256), 256, 0, stream_>>>(sl.dKind, sl.dBcIdx, geo(sl), lb, (int)sl.cellsStore);
                 launched();
             }
         }
+        for (Slab& sl : slabs_) sl.kindUnflagged = false;
     }
 
     // ------------------------------------------------------------------------------ the step
 
     template <int MAIN, bool GEN, bool ODD>
     void launch_sweep_as(Slab& sl, SweepArgs<T>& a, int mainIdx) {
-        if (a.applyPlanes) launch_sweep_with<MAIN, GEN, ODD, true>(sl, a, mainIdx);
-        else launch_sweep_with<MAIN, GEN, ODD, false>(sl, a, mainIdx);
-    }
-
-    template <int MAIN, bool GEN, bool ODD, bool PLANES>
-    void launch_sweep_with(Slab& sl, SweepArgs<T>& a, int mainIdx) {
         constexpr int threads = sweep_threads(ODD);
         (void)mainIdx;
         // tile sequence: the planes next to a slab that takes direct stores first, then the rest
@@ -1197,43 +1140,21 @@ private:
                                      std::getenv("PLB_B200_GRID_ODD") ? std::atoi(std::getenv("PLB_B200_GRID_ODD")) : 0};
         const int gf = gfEnv[ODD ? 1 : 0] > 0 ? gfEnv[ODD ? 1 : 0] : sweep_grid_factor(ODD);
         const int grid = std::max(1, std::min(a.nTiles, numSMs_ * gf));
-        const bool defer = PLANES && a.applyPlanes && sl.deferWanted;
-        const int drainGrid = defer ? MAILBOX_SMS : 0;
-        if (std::max(grid, drainGrid) > sl.partialsCap) {
+        if (grid > sl.partialsCap) {
             if (sl.dPartials) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dPartials); devBytes_ -= (size_t)sl.partialsCap * 4 * sizeof(double); }
-            sl.partialsCap = std::max(std::max(grid, drainGrid), numSMs_ * 16);
+            sl.partialsCap = std::max(grid, numSMs_ * 16);
             sl.dPartials = (double*)dev_alloc((size_t)sl.partialsCap * 4 * sizeof(double));
         }
         a.partials = sl.dPartials;
-        a.drain = 0; a.mbCount = nullptr; a.mbCell = nullptr; a.mbF = nullptr;
-        if (defer) {
-            if (!sl.dMbCount) {
-                const size_t slots = (size_t)MAILBOX_SMS * (SWEEP_MAX_THREADS / 32);
-                sl.dMbCount = (int*)dev_alloc(slots * sizeof(int));
-                sl.dMbCell = (int*)dev_alloc(slots * STASH_CAP * sizeof(int));
-                sl.dMbF = (T*)dev_alloc(slots * STASH_CAP * Q * sizeof(T));
-                PLB_CUDA(cudaMemsetAsync(sl.dMbCount, 0, slots * sizeof(int), stream_));
-            }
-            a.mbCount = sl.dMbCount; a.mbCell = sl.dMbCell; a.mbF = sl.dMbF;
+        const bool prof = profiling_ && profUsed_ < 2 * 8192;
+        if (prof) {
+            while (profEvents_.size() < profUsed_ + 2) { cudaEvent_t e; PLB_CUDA(cudaEventCreate(&e)); profEvents_.push_back(e); }
+            PLB_CUDA(cudaEventRecord(profEvents_[profUsed_], stream_));
         }
-        auto timed_launch = [&](int gridSize) {
-            const bool prof = profiling_ && profUsed_ < 2 * 8192;
-            if (prof) {
-                while (profEvents_.size() < profUsed_ + 2) { cudaEvent_t e; PLB_CUDA(cudaEventCreate(&e)); profEvents_.push_back(e); }
-                PLB_CUDA(cudaEventRecord(profEvents_[profUsed_], stream_));
-            }
-            launch_sweep_kernel<T, Q, MAIN, GEN, ODD, PLANES>(gridSize, stream_, a);
-            launched();
-            if (prof) { PLB_CUDA(cudaEventRecord(profEvents_[profUsed_ + 1], stream_)); profUsed_ += 2; }
-        };
-        timed_launch(grid);
+        launch_sweep_kernel<T, Q, MAIN, GEN, ODD>(grid, stream_, a);
+        launched();
+        if (prof) { PLB_CUDA(cudaEventRecord(profEvents_[profUsed_ + 1], stream_)); profUsed_ += 2; }
         sl.statSlots = 1;
-        if (defer) {
-            // the drain launch: what the last blocks of the sweep left in the mailboxes of their SMs
-            a.drain = 1; a.nRimTiles = 0; a.statsOut = sl.dStats + 4;
-            timed_launch(drainGrid);
-            sl.statSlots = 2;
-        }
     }
 
     /// the slab on the other side of a face of `sl`, if the rim cells store into it directly
@@ -1262,10 +1183,6 @@ private:
         SweepArgs<T> a;
         a.F = sl.F; a.kind = sl.dKind; a.dyns = dDyns_; a.g = geo(sl);
         a.bcIdx = sl.dBcIdx; a.bcs = sl.dBcs;
-        a.applyPlanes = ((pending_ && sl.stageOffsets.size() >= 2 && sl.stageSplit[0] > sl.stageOffsets[0]) || sl.nAuto > 0) ? 1 : 0;
-        // wrapped planes: the completion applied on load belongs to the step before (values as of then); planes that complete at
-        // collision time (dynamics-based managers) take the current values
-        a.pendingStamp = sl.nAuto > 0 ? -1 : (int)stepCount_;
         peers_of(sl, a.g, a);
         a.rimTicket = sl.dRimTicket; a.sigValue = stepCount_; a.nRimTiles = 0;
         for (int i = 0; i < 27; ++i) a.ldBase[i] = a.stBase[i] = nullptr;
@@ -1292,9 +1209,8 @@ private:
                 if (swapped_) launch_sweep_as<DYN_EXTERNAL_FUSED, true, true>(sl, a, 7);
                 else launch_sweep_as<DYN_EXTERNAL_FUSED, true, false>(sl, a, 7);
             } else {
-                a.applyPlanes = 0;
-                if (swapped_) launch_sweep_with<DYN_EXTERNAL, true, true, false>(sl, a, 6);
-                else launch_sweep_with<DYN_EXTERNAL, true, false, false>(sl, a, 6);
+                if (swapped_) launch_sweep_as<DYN_EXTERNAL, true, true>(sl, a, 6);
+                else launch_sweep_as<DYN_EXTERNAL, true, false>(sl, a, 6);
             }
             return;
         }
@@ -1315,17 +1231,11 @@ private:
     }
 
     void run_processors() {
-        materialize();                         // processors run twice in a row (initialize() called again)
-        if (fused_) pending_ = true;           // stage-0 plane items: left to the next sweep; later readers complete on the fly
         for (Slab& sl : slabs_) {
             const int nStages = (int)sl.stageOffsets.size() - 1;
             for (int s = 0; s < nStages; ++s) {
                 const int first = sl.stageOffsets[s], split = sl.stageSplit[s], last = sl.stageOffsets[s + 1];
-                if (split > first && !(fused_ && s == 0)) {
-                    const int n = split - first;
-                    plane_stage_kernel<T, Q><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
-                    launched();
-                }
+                launch_plane_stage(sl, first, split - first);
                 if (last > split) {
                     const int n = last - split;
                     fd_stage_kernel<T, Q><<<(n + 63) / 64, 64, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + split, n);
@@ -1556,7 +1466,6 @@ private:
         if (!data && bytes) throw PlbError("null buffer");
         if (up) ext_detach();
         sync_setup();
-        materialize();
         if (!copyStream_) {
             PLB_CUDA(cudaStreamCreateWithFlags(&copyStream_, cudaStreamNonBlocking));
             for (int k = 0; k < 2; ++k) {

@@ -35,15 +35,8 @@ struct Dyn {
 template <class T>
 struct Bc {
     int kind, dir, ori;
-    /// setBoundaryVelocity / setBoundaryDensity between two steps changes u / rhoBar on the device (set_bc_values_kernel) while the
-    /// completePopulations of the step before may still be outstanding (lazy completion, kernels.cuh): that one must see the
-    /// values it was deferred under.  stamp = number of the sweep that will apply it; a record with that stamp answers a pending
-    /// completion with uPrev / rhoBarPrev.
-    int stamp;
     T u[3];
     T rhoBar;
-    T uPrev[3];
-    T rhoBarPrev;
 };
 
 // ------------------------------------------------------------------------------ descriptors

@@ -211,42 +211,28 @@ def test_coprocessor_surface_bgk_pure_block():
     assert np.array_equal(out, want)        # we also reproduce the reference's rim rule
 
 
-# ---- plane boundaries fused into the sweep ("lazy completion") against the eager
-# ---- plane_stage_kernel path of the same engine, and the cases where the fusion must not be used
+# ---- the plane boundary pass (plane_stage_kernel, one launch per stage and slab) and the processor staging
 
-def _launches_per_step(sc_factory, monkeypatch, eager):
+@pytest.mark.parametrize("name", ["cavity_bgk_10x9x8", "inlet_outlet_local"])
+def test_launches_per_step(name):
+    """one sweep + one plane pass + the finite-difference stages the case has (edges, corners): nothing else runs in a step"""
     import palabos_b200 as pb
-    if eager:
-        monkeypatch.setenv("PLB_B200_EAGER_PLANES", "1")
-    else:
-        monkeypatch.delenv("PLB_B200_EAGER_PLANES", raising=False)
-    sc = sc_factory()
+    sc = CASES[name][0]()
     eng = pb.Lattice(sc.q, sc.prec, sc.nx, sc.ny, sc.nz, sc.dyn, sc.p1, sc.p2)
     try:
         replay(sc, eng)
         a = eng.launch_count()
         eng.collide_and_stream(4)
-        b = eng.launch_count()
-        return (b - a) / 4.0, eng.download(), eng.compute_density_velocity()
+        per_step = (eng.launch_count() - a) / 4.0
+        stages, _ = eng.boundary_stages()
+        assert per_step <= 1 + 2 * stages, per_step
     finally:
         eng.close()
 
 
-@pytest.mark.parametrize("name", ["cavity_bgk_10x9x8", "cavity_zouhe_10x9x8", "inlet_outlet_local", "cavity_bgk_q27_8x8x9",
-                                  "cavity_bgk_f32_10x9x8", "obstacle_zouhe_24x12x10"])
-def test_fused_plane_completion_equals_eager_pass(name, monkeypatch):
-    fused = _launches_per_step(CASES[name][0], monkeypatch, eager=False)
-    eager = _launches_per_step(CASES[name][0], monkeypatch, eager=True)
-    # the eager pass over the plane cells is gone; where plane cells sit alone in their warp (z-faces) the sweep parks them and a
-    # small drain launch empties the mailboxes of the last blocks (kernels.cuh, sweep_kernel) -- never more launches than eager
-    assert fused[0] <= eager[0], "the plane_stage launch must have disappeared: %r vs %r" % (fused[0], eager[0])
-    assert np.array_equal(fused[1], eager[1])
-    assert np.array_equal(fused[2], eager[2])
-
-
-def test_plane_added_after_the_edge_that_reads_it_is_not_fused():
+def test_plane_added_after_the_edge_that_reads_it_runs_in_a_later_stage():
     """An edge processor inserted BEFORE the plane it reads sees the un-completed plane cells in the
-    reference's sequential order: the plane items land in a later stage and the fusion is off."""
+    reference's sequential order: the plane items land in a later stage."""
     import palabos_b200 as pb
     from scenario import OracleEngine
     nx, ny, nz = 8, 7, 9
@@ -269,9 +255,9 @@ def test_plane_added_after_the_edge_that_reads_it_is_not_fused():
         eng.close()
 
 
-def test_pending_completion_survives_every_reader_and_writer():
-    """Between steps the completion is pending in storage; each API that reads or writes populations or
-    boundary records must behave as if it had been applied eagerly."""
+def test_boundary_cells_survive_every_reader_and_writer():
+    """Readers and writers of populations and boundary records between steps (reductions, defineDynamics over plane records,
+    re-initialisation of boundary cells, value changes on the device) against the oracle."""
     import palabos_b200 as pb
     from scenario import OracleEngine
     sc = cavity(10, 8, 9, 0)
@@ -285,13 +271,13 @@ def test_pending_completion_survives_every_reader_and_writer():
         eng.initialize()
         eng.initialize()                                               # processors twice in a row
         eng.collide_and_stream(3)
-    energy = [eng.compute_average_energy(box) for eng in engines]              # on-the-fly completion in the reduction
+    energy = [eng.compute_average_energy(box) for eng in engines]              # a reduction over boundary cells
     assert energy[0] == pytest.approx(energy[1], rel=1e-13)
     for eng in engines:
         eng.collide_and_stream(2)
-        eng.define_dynamics((3, 5, 0, 0, 3, 4), "BB", 1.0)             # kills plane records while pending
+        eng.define_dynamics((3, 5, 0, 0, 3, 4), "BB", 1.0)             # kills plane records
         eng.collide_and_stream(2)
-        eng.initialize_at_equilibrium((0, 9, 0, 7, 6, 8), 1.01, (0.0, 0.01, 0.0))   # overwrites pending cells
+        eng.initialize_at_equilibrium((0, 9, 0, 7, 6, 8), 1.01, (0.0, 0.01, 0.0))   # overwrites boundary cells
         eng.collide_and_stream(1)
         eng.set_boundary_velocity((1, 8, 1, 6, 8, 8), (0.03, 0.0, 0))
         eng.collide_and_stream(2)
@@ -299,7 +285,7 @@ def test_pending_completion_survives_every_reader_and_writer():
     assert np.array_equal(a, b)
     pops = engines[1].download()
     for eng in engines:
-        eng.upload(pops * 0.75)                                        # upload over pending cells
+        eng.upload(pops * 0.75)                                        # upload over boundary cells
         eng.collide_and_stream(3)
     assert np.array_equal(engines[0].download(), engines[1].download())
     assert np.array_equal(engines[0].compute_density_velocity(), engines[1].compute_density_velocity())
@@ -380,15 +366,6 @@ def test_external_sweep_with_stored_fields(name, monkeypatch):
     the populations it gathers); PLB_B200_EXT_EXPLICIT=1 stores them after every step and reads them back, as the reference
     does.  Both must reproduce the reference's dump."""
     monkeypatch.setenv("PLB_B200_EXT_EXPLICIT", "1")
-    check_golden(name, run_gpu(CASES[name][0]()))
-
-
-@pytest.mark.parametrize("name", EXT)
-def test_external_sweep_with_eager_plane_completion(name, monkeypatch):
-    """By default the plane boundaries of an enveloped lattice are completed by the next sweep on load (as in the plain
-    path) and the moments of boundary cells are recomputed from the completed populations inside the sweep;
-    PLB_B200_EAGER_PLANES=1 completes them in a pass of their own after the step."""
-    monkeypatch.setenv("PLB_B200_EAGER_PLANES", "1")
     check_golden(name, run_gpu(CASES[name][0]()))
 
 

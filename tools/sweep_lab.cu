@@ -1,5 +1,5 @@
 // tools/sweep_lab.cu -- development tool (not part of the product): times the production sweep kernel
-// of palabos_b200/csrc/kernels.cuh under different launch shapes / cache policies, selected at
+// of palabos_b200/csrc/sweep_kernel.cuh under different launch shapes / cache policies, selected at
 // compile time with -DPLB_SWEEP_THREADS=.. -DPLB_SWEEP_MINBLOCKS=.. -DLAB_POLICY=..
 //   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -fmad=false -Ipalabos_b200/csrc tools/sweep_lab.cu -o lab
 //   ./lab <n> <iters> [gridFactor] [q27]
@@ -25,7 +25,7 @@
 #define PLB_SWEEP_LD(p) __ldcg(p)
 #define PLB_SWEEP_ST(p, v) __stcg(p, v)
 #endif
-#include "kernels.cuh"
+#include "sweep_kernel.cuh"
 
 using namespace plb200;
 
