@@ -23,7 +23,9 @@
 
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <fstream>
+#include <sstream>
 #include <limits>
 #include <stdexcept>
 #include <string>
@@ -164,10 +166,17 @@ template <typename T, template <typename U> class Descriptor> class MultiBlockLa
 /// list of integrateProcessingFunctional / applyProcessingFunctional needs
 class MultiBlock3D {
 public:
+    MultiBlock3D() : id(nextId()++) {}
+    MultiBlock3D(MultiBlock3D const&) : id(nextId()++) {}
     virtual ~MultiBlock3D() {}
     virtual plint getNx() const = 0;
     virtual plint getNy() const = 0;
     virtual plint getNz() const = 0;
+    /// multiBlock/multiBlock3D.cpp: the multi-blocks of a program are numbered in the order of their construction
+    plint getId() const { return id; }
+private:
+    static plint& nextId() { static plint next = 0; return next; }
+    plint id;
 };
 
 /// Tag of the lattice constructor for the time loop of the fork's own application (src/variables.hh:461-486): the lattice
@@ -392,6 +401,137 @@ void saveBinaryBlock(MultiBlockLattice3D<T, Descriptor>& lattice, std::string fN
 template <typename T, template <typename U> class Descriptor>
 void loadBinaryBlock(MultiBlockLattice3D<T, Descriptor>& lattice, std::string fName, bool /*enforceUint*/ = false) {
     detail::check(plb_b200_load_binary_block(lattice.b200Handle(), fName.c_str()));
+}
+
+// ------------------------------------------- checkpoint / restart (io/plbFiles.h, io/multiBlockWriter3D.h, io/utilIO_3D.h)
+
+/// io/plbFiles.cpp:35-120: path / name / extension of a file name
+class FileName {
+public:
+    FileName() {}
+    FileName(std::string file) { initialize(file); }
+    FileName(const char* file) { initialize(file); }
+    std::string get() const {
+        std::string composite;
+        if (path != "") composite = path + "/";
+        composite += name;
+        if (ext != "") composite += "." + ext;
+        return composite;
+    }
+    operator std::string() const { return get(); }
+    std::string getPath() const { return path; }
+    std::string getName() const { return name; }
+    std::string getExt() const { return ext; }
+    FileName& setPath(std::string path_) {
+        path = path_;
+        if (!path.empty() && (path[path.size() - 1] == '/' || path[path.size() - 1] == '\\')) path.erase(path.end() - 1);
+        return *this;
+    }
+    FileName& setName(std::string name_) { name = name_; return *this; }
+    FileName& setExt(std::string ext_) {
+        ext = ext_;
+        if (!ext.empty() && ext[0] == '.') ext.erase(ext.begin());
+        return *this;
+    }
+    FileName& defaultPath(std::string path_) { return path == "" ? setPath(path_) : *this; }
+    FileName& defaultExt(std::string ext_) { return ext == "" ? setExt(ext_) : *this; }
+private:
+    void initialize(std::string file) {
+        std::string fullName;
+        const size_t sep = file.find_last_of("\\/");
+        if (sep != std::string::npos) { fullName = file.substr(sep + 1); path = file.substr(0, sep); }
+        else fullName = file;
+        const size_t dot = fullName.find_last_of(".");
+        if (dot != std::string::npos) { name = fullName.substr(0, dot); ext = fullName.substr(dot + 1); }
+        else { name = fullName; ext = ""; }
+    }
+    std::string path, name, ext;
+};
+
+namespace global {
+/// core/globalDefs.cpp:90-140
+class Directories {
+public:
+    void setOutputDir(std::string d) { outputDir = d; }
+    void setInputDir(std::string d) { inputDir = d; }
+    std::string getOutputDir() const { return outputDir; }
+    std::string getInputDir() const { return inputDir; }
+private:
+    std::string outputDir, inputDir;
+};
+inline Directories& directories() { static Directories instance; return instance; }
+}  // namespace global
+
+/// io/imageWriter.h:131-135
+inline std::string createFileName(std::string name, plint number, plint width) {
+    std::ostringstream s;
+    s << name;
+    s.fill('0'); s.width(width);
+    s << number;
+    return s.str();
+}
+
+namespace parallelIO {
+/// parallelIO::save io/multiBlockWriter3D.cpp:226-238.  dynamicContent = true (the reference's default: the dynamics object of
+/// every cell serialized next to its populations) is not available: the set-up of a lattice lives in the program.
+template <typename T, template <typename U> class Descriptor>
+void save(MultiBlockLattice3D<T, Descriptor>& lattice, FileName fName, bool dynamicContent = true) {
+    if (dynamicContent) throw PlbLogicException("parallelIO::save: dynamicContent = true is not supported, pass false (populations only)");
+    fName.defaultExt("plb");
+    const std::string entry = FileName(fName).setExt("dat").get();
+    FileName target(fName);
+    target.defaultPath(global::directories().getOutputDir());
+    detail::check(plb_b200_parallel_save(lattice.b200Handle(), FileName(target).setExt("").get().c_str(), entry.c_str(), (int)lattice.getId()));
+}
+/// parallelIO::load io/multiBlockReader3D.cpp:251-259
+template <typename T, template <typename U> class Descriptor>
+void load(FileName fName, MultiBlockLattice3D<T, Descriptor>& intoBlock, bool dynamicContent = true) {
+    if (dynamicContent) throw PlbLogicException("parallelIO::load: dynamicContent = true is not supported, pass false (populations only)");
+    fName.defaultPath(global::directories().getInputDir());
+    detail::check(plb_b200_parallel_load(intoBlock.b200Handle(), FileName(fName).setExt("").get().c_str()));
+}
+}  // namespace parallelIO
+
+/// saveState io/utilIO_3D.cpp:45-60: every block through parallelIO::save, and the XML file a restart reads
+template <typename T, template <typename U> class Descriptor>
+void saveState(std::vector<MultiBlockLattice3D<T, Descriptor>*> blocks, plint iteration, bool saveDynamicContent,
+               FileName xmlFileName, FileName baseFileName, plint fileNamePadding = 8) {
+    const std::string fname_base = createFileName(baseFileName.get(), iteration, fileNamePadding);
+    for (size_t i = 0; i < blocks.size(); ++i) {
+        std::ostringstream fname;
+        fname << fname_base << "_" << i;
+        parallelIO::save(*blocks[i], fname.str(), saveDynamicContent);
+    }
+    xmlFileName.defaultPath(global::directories().getOutputDir());   // (XMLwriter::print takes the name as it is; the usual call passes a plain name)
+    std::ofstream xml(xmlFileName.get().c_str());
+    if (!xml) throw PlbLogicException("saveState: cannot write " + xmlFileName.get());
+    xml << "<?xml version=\"1.0\" ?>\n<continue>\n    <name> " << FileName(fname_base).defaultPath(global::directories().getOutputDir()).get() << " </name>\n"
+        << "    <num_blocks> " << blocks.size() << " </num_blocks>\n    <iteration> " << iteration << " </iteration>\n</continue>\n";
+}
+/// loadState io/utilIO_3D.cpp:62-76
+template <typename T, template <typename U> class Descriptor>
+void loadState(std::vector<MultiBlockLattice3D<T, Descriptor>*> blocks, plint& iteration, bool saveDynamicContent, FileName xmlFileName) {
+    std::ifstream in(xmlFileName.get().c_str());
+    if (!in) throw PlbLogicException("loadState: cannot read " + xmlFileName.get());
+    std::stringstream all;
+    all << in.rdbuf();
+    const std::string xml = all.str();
+    auto field = [&](const std::string& tag) {
+        const size_t a = xml.find("<" + tag + ">"), b = xml.find("</" + tag + ">");
+        if (a == std::string::npos || b == std::string::npos) throw PlbLogicException("loadState: no <" + tag + "> in " + xmlFileName.get());
+        std::string t = xml.substr(a + tag.size() + 2, b - a - tag.size() - 2);
+        const size_t p = t.find_first_not_of(" \t\r\n"), q = t.find_last_not_of(" \t\r\n");
+        return p == std::string::npos ? std::string() : t.substr(p, q - p + 1);
+    };
+    const std::string fname_base = field("name");
+    const size_t numBlocks = (size_t)std::atol(field("num_blocks").c_str());
+    iteration = (plint)std::atol(field("iteration").c_str());
+    if (blocks.size() != numBlocks) throw PlbLogicException("loadState: the file holds another number of blocks");
+    for (size_t i = 0; i < blocks.size(); ++i) {
+        std::ostringstream fname;
+        fname << fname_base << "_" << i;
+        parallelIO::load(fname.str(), *blocks[i], saveDynamicContent);
+    }
 }
 
 // ------------------------------------------- boundary conditions (boundaryCondition/boundaryCondition3D.h)

@@ -146,6 +146,16 @@ int plb_b200_download(plb_b200_lattice* L, const int box[6], void* data, size_t 
  * (checkpoint / restart).  One rank only. */
 int plb_b200_save_binary_block(plb_b200_lattice* L, const char* path);
 int plb_b200_load_binary_block(plb_b200_lattice* L, const char* path);
+/* parallelIO::save(multiBlock, fName, dynamicContent = false) io/multiBlockWriter3D.cpp:226-238 and parallelIO::load
+ * io/multiBlockReader3D.cpp:251-259: <base_path>.plb (the XML description: family, data type, descriptor, bounding box, one
+ * component per x-slab with its byte offset) + <base_path>.dat (the populations of the slabs back to back, raw T, wire format
+ * above -- byte-identical to the reference's file for the same blocks).  Files are interchangeable with the reference's: it
+ * loads ours, and plb_b200_parallel_load reads a file the reference wrote with any block structure.  Static variables only: a
+ * file saved with dynamicContent = true (serialized dynamics objects per cell) is refused -- the set-up lives in the program.
+ * With several ranks every rank calls; each writes / reads the slabs it owns, rank 0 writes the .plb.
+ * data_file_entry: the <File> entry of the .plb (NULL: <base_path>.dat); global_id: MultiBlock3D::getId() of the block. */
+int plb_b200_parallel_save(plb_b200_lattice* L, const char* base_path, const char* data_file_entry, int global_id);
+int plb_b200_parallel_load(plb_b200_lattice* L, const char* base_path);
 /* bytes a rank must supply to upload/download for `box` (cells it owns inside the box * q * sizeof(T)) */
 size_t plb_b200_local_bytes(plb_b200_lattice* L, const int box[6]);
 

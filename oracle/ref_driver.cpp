@@ -357,6 +357,28 @@ static int runScenario(std::vector<std::string> const& lines, size_t first,
         } else if (cmd == "load_block") {
             std::string file; in >> file;
             loadBinaryBlock(lattice, file);
+        } else if (cmd == "psave") {
+            // parallelIO::save io/multiBlockWriter3D.cpp:226-238: <file>.plb (XML) + <file>.dat (raw serialized blocks)
+            std::string file; int dyn; in >> file >> dyn;
+            global::directories().setOutputDir("./");
+            parallelIO::save(lattice, file, dyn != 0);
+        } else if (cmd == "pload") {
+            std::string file; int dyn; in >> file >> dyn;
+            global::directories().setOutputDir("./");
+            parallelIO::load(file, lattice, dyn != 0);
+        } else if (cmd == "save_state") {
+            // saveState io/utilIO_3D.cpp:45-60
+            plint it; int dyn; std::string xml, base; in >> it >> dyn >> xml >> base;
+            global::directories().setOutputDir("./");
+            std::vector<MultiBlock3D*> blocks; blocks.push_back(&lattice);
+            saveState(blocks, it, dyn != 0, xml, base, 8);
+        } else if (cmd == "load_state") {
+            int dyn; std::string xml; in >> dyn >> xml;
+            global::directories().setOutputDir("./");
+            std::vector<MultiBlock3D*> blocks; blocks.push_back(&lattice);
+            plint it = -1;
+            loadState(blocks, it, dyn != 0, xml);
+            std::printf("LOADED_ITERATION %ld\n", (long)it);
         } else if (cmd == "dump_rho_u") {
             // rho and u through Cell::computeDensity / computeVelocity (dynamics-aware).
             std::string file; in >> file;

@@ -39,7 +39,7 @@ SYMBOLS = [
     "plb_b200_compute_density_velocity", "plb_b200_launch_count", "plb_b200_device_bytes",
     "plb_b200_boundary_stages", "plb_b200_profile_sweeps", "plb_b200_profile_read", "plb_b200_halo_transport", "plb_b200_coproc_add_domain", "plb_b200_coproc_send",
     "plb_b200_coproc_receive", "plb_b200_coproc_collide_and_stream", "plb_b200_coproc_remove_domain",
-    "plb_b200_save_binary_block", "plb_b200_load_binary_block",
+    "plb_b200_save_binary_block", "plb_b200_load_binary_block", "plb_b200_parallel_save", "plb_b200_parallel_load",
     "plb_b200_create_enveloped", "plb_b200_execute_internal_processors", "plb_b200_apply_rhobar_j",
     "plb_b200_upload_rhobar_j", "plb_b200_download_rhobar_j",
     "plb_b200_voxelize", "plb_b200_stl_read", "plb_b200_stl_free", "plb_b200_mesh_to_lattice",
@@ -123,6 +123,8 @@ def lib():
         L.plb_b200_coproc_remove_domain.argtypes = [ci]
         L.plb_b200_save_binary_block.argtypes = [vp, ctypes.c_char_p]
         L.plb_b200_load_binary_block.argtypes = [vp, ctypes.c_char_p]
+        L.plb_b200_parallel_save.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+        L.plb_b200_parallel_load.argtypes = [vp, ctypes.c_char_p]
         L.plb_b200_voxelize.argtypes = [vp, ctypes.c_int64, ci, ci, ci, ci, vp, vp]
         L.plb_b200_stl_read.argtypes = [ctypes.c_char_p, vp, vp]
         L.plb_b200_stl_free.restype = None
@@ -382,6 +384,15 @@ class Lattice:
     def save_binary_block(self, path):
         """saveBinaryBlock(lattice, fName): checkpoint file in the reference's format"""
         self._ck(self.lib.plb_b200_save_binary_block(self.h, str(path).encode()))
+
+    def parallel_save(self, base_path, data_file_entry=None, global_id=0):
+        """parallelIO::save(lattice, fName, dynamicContent=False): <base_path>.plb + <base_path>.dat"""
+        entry = None if data_file_entry is None else str(data_file_entry).encode()
+        self._ck(self.lib.plb_b200_parallel_save(self.h, str(base_path).encode(), entry, int(global_id)))
+
+    def parallel_load(self, base_path):
+        """parallelIO::load(fName, lattice, dynamicContent=False)"""
+        self._ck(self.lib.plb_b200_parallel_load(self.h, str(base_path).encode()))
 
     def load_binary_block(self, path):
         self._ck(self.lib.plb_b200_load_binary_block(self.h, str(path).encode()))

@@ -255,6 +255,199 @@ int plb_b200_load_binary_block(plb_b200_lattice* L, const char* path) {
     } catch (const std::exception& e) { if (fp) std::fclose(fp); return fail(e.what()); }
 }
 
+// ---- parallelIO::save / load (io/multiBlockWriter3D.cpp:226-238, io/multiBlockReader3D.cpp:251-259), static variables
+
+namespace {
+struct Component { int box[6]; long long begin, end; };      ///< a block of the file: its bulk and its byte range in the .dat
+
+/// the blocks a lattice is saved as: its x-slabs (all ranks), clipped to the user's lattice
+std::vector<Component> slab_components(const plb_b200_lattice* L) {
+    const CreateDesc& d = L->desc;
+    const int G = d.nRanks * d.slabsPerRank, implNx = d.nx + 2 * L->off[0];
+    std::vector<Component> comps;
+    long long pos = 0;
+    for (int g = 0; g < G; ++g) {
+        int x0, x1;
+        slab_range(implNx, G, g, x0, x1);
+        x0 = std::max(0, x0 - L->off[0]); x1 = std::min(d.nx - 1, x1 - L->off[0]);
+        if (x1 < x0) continue;
+        Component c;
+        c.box[0] = x0; c.box[1] = x1; c.box[2] = 0; c.box[3] = d.ny - 1; c.box[4] = 0; c.box[5] = d.nz - 1;
+        c.begin = pos;
+        pos += (long long)(x1 - x0 + 1) * d.ny * d.nz * d.q * d.prec;
+        c.end = pos;
+        comps.push_back(c);
+    }
+    return comps;
+}
+
+/// text between <tag ...> and </tag>, starting the search at `from`; npos-safe
+bool xml_field(const std::string& xml, const std::string& tag, size_t from, std::string& out, size_t* next = nullptr) {
+    const size_t a = xml.find("<" + tag, from);
+    if (a == std::string::npos) return false;
+    const size_t b = xml.find('>', a);
+    const size_t c = xml.find("</" + tag + ">", b);
+    if (b == std::string::npos || c == std::string::npos) return false;
+    out = xml.substr(b + 1, c - b - 1);
+    if (next) *next = c + tag.size() + 3;
+    return true;
+}
+std::vector<long long> xml_ints(const std::string& text) {
+    std::vector<long long> v;
+    const char* p = text.c_str();
+    char* e = nullptr;
+    for (;;) {
+        const long long x = std::strtoll(p, &e, 10);
+        if (e == p) break;
+        v.push_back(x);
+        p = e;
+    }
+    return v;
+}
+std::string trimmed(const std::string& t) {
+    const size_t a = t.find_first_not_of(" \t\r\n"), b = t.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? std::string() : t.substr(a, b - a + 1);
+}
+}  // namespace
+
+int plb_b200_parallel_save(plb_b200_lattice* L, const char* base_path, const char* data_file_entry, int global_id) {
+    if (!L || !L->impl) return fail("null lattice handle");
+    FILE* fp = nullptr;
+    try {
+        if (!base_path) throw PlbError("null path");
+        const CreateDesc& d = L->desc;
+        const std::string base(base_path), dat = base + ".dat";
+        const std::vector<Component> comps = slab_components(L);
+        // every rank writes the bulks of its own slabs at their offsets (the reference: writeRawData, MPI-IO or gathered)
+        fp = std::fopen(dat.c_str(), d.rank == 0 ? "wb" : "r+b");
+        if (!fp && d.rank != 0) fp = std::fopen(dat.c_str(), "wb");
+        if (!fp) throw PlbError("Could not open file " + dat + " for saving");
+        const size_t planeBytes = (size_t)d.ny * d.nz * d.q * d.prec;
+        const int planes = (int)std::max<size_t>(1, (size_t(64) << 20) / planeBytes);
+        std::vector<unsigned char> buf;
+        for (const Component& c : comps) {
+            for (int x = c.box[0]; x <= c.box[1]; x += planes) {
+                const int box[6] = {x, std::min(c.box[1], x + planes - 1), 0, d.ny - 1, 0, d.nz - 1};
+                const size_t bytes = L->impl->local_bytes(SBox(L, box));
+                if (bytes == 0) continue;                                  // another rank's slab
+                if (bytes != (size_t)(box[1] - box[0] + 1) * planeBytes) throw PlbError("a slab is split over ranks");
+                buf.resize(bytes);
+                L->impl->download(SBox(L, box), buf.data(), bytes);
+                if (fseeko(fp, (off_t)(c.begin + (long long)(x - c.box[0]) * (long long)planeBytes), SEEK_SET) != 0 ||
+                    std::fwrite(buf.data(), 1, bytes, fp) != bytes) throw PlbError("write error on " + dat);
+            }
+        }
+        if (std::fclose(fp) != 0) { fp = nullptr; throw PlbError("write error on " + dat); }
+        fp = nullptr;
+        if (d.rank == 0) {
+            // writeXmlSpec io/multiBlockWriter3D.cpp:52-142, without the dynamics dictionary and the processor list: both are
+            // optional to the reader (multiBlockReader3D.cpp:66-120) and describe the set-up, which lives in the program here
+            const std::string plb = base + ".plb";
+            fp = std::fopen(plb.c_str(), "wb");
+            if (!fp) throw PlbError("Could not open file " + plb + " for saving");
+            std::fprintf(fp, "<?xml version=\"1.0\" ?>\n<Block3D>\n    <General>\n        <Family> BlockLattice3D </Family>\n"
+                             "        <Datatype> %s </Datatype>\n        <Descriptor> D3Q%d </Descriptor>\n        <cellDim> %d </cellDim>\n"
+                             "        <dynamicContent> False </dynamicContent>\n        <globalId> %d </globalId>\n    </General>\n",
+                         d.prec == 8 ? "double" : "float", d.q, d.q, global_id);
+            std::fprintf(fp, "    <Structure>\n        <BoundingBox> 0 %d 0 %d 0 %d </BoundingBox>\n        <EnvelopeWidth> 1 </EnvelopeWidth>\n"
+                             "        <GridLevel> 0 </GridLevel>\n        <NumComponents> %d </NumComponents>\n    </Structure>\n",
+                         d.nx - 1, d.ny - 1, d.nz - 1, (int)comps.size());
+            std::fprintf(fp, "    <Data>\n        <File> %s </File>\n", data_file_entry ? data_file_entry : dat.c_str());
+            for (size_t k = 0; k < comps.size(); ++k) {
+                const int* b = comps[k].box;
+                if (comps.size() == 1) std::fprintf(fp, "        <Component> %d %d %d %d %d %d </Component>\n", b[0], b[1], b[2], b[3], b[4], b[5]);
+                else std::fprintf(fp, "        <Component id=\"%d\"> %d %d %d %d %d %d </Component>\n", (int)k, b[0], b[1], b[2], b[3], b[4], b[5]);
+            }
+            std::fprintf(fp, "        <Offsets>");
+            for (const Component& c : comps) std::fprintf(fp, " %lld", c.end);
+            std::fprintf(fp, " </Offsets>\n    </Data>\n</Block3D>\n");
+            if (std::fclose(fp) != 0) { fp = nullptr; throw PlbError("write error on " + plb); }
+        }
+        return 1;
+    } catch (const std::exception& e) { if (fp) std::fclose(fp); return fail(e.what()); }
+}
+
+int plb_b200_parallel_load(plb_b200_lattice* L, const char* base_path) {
+    if (!L || !L->impl) return fail("null lattice handle");
+    FILE* fp = nullptr;
+    try {
+        if (!base_path) throw PlbError("null path");
+        const CreateDesc& d = L->desc;
+        const std::string base(base_path), plb = base + ".plb";
+        fp = std::fopen(plb.c_str(), "rb");
+        if (!fp) throw PlbError("Could not open file " + plb + " for reading");
+        std::string xml;
+        char chunk[4096];
+        for (size_t n; (n = std::fread(chunk, 1, sizeof chunk, fp)) > 0;) xml.append(chunk, n);
+        std::fclose(fp); fp = nullptr;
+        // readXmlSpec io/multiBlockReader3D.cpp:122-207
+        std::string t;
+        if (!xml_field(xml, "Family", 0, t) || trimmed(t) != "BlockLattice3D") throw PlbError(plb + " does not hold a BlockLattice3D");
+        if (!xml_field(xml, "Datatype", 0, t) || trimmed(t) != (d.prec == 8 ? "double" : "float")) throw PlbError(plb + ": data type does not match the lattice");
+        if (xml_field(xml, "Descriptor", 0, t) && trimmed(t) != "D3Q" + std::to_string(d.q)) throw PlbError(plb + ": descriptor does not match the lattice");
+        if (!xml_field(xml, "cellDim", 0, t) || xml_ints(t) != std::vector<long long>{d.q}) throw PlbError(plb + ": cellDim does not match the lattice");
+        if (xml_field(xml, "dynamicContent", 0, t) && trimmed(t) != "False" && trimmed(t) != "false" && trimmed(t) != "0")
+            throw PlbError(plb + " was saved with dynamic content (serialized dynamics objects): only static variables can be loaded");
+        if (!xml_field(xml, "BoundingBox", 0, t) || xml_ints(t) != std::vector<long long>{0, d.nx - 1, 0, d.ny - 1, 0, d.nz - 1})
+            throw PlbError(plb + ": bounding box does not match the lattice");
+        if (xml_field(xml, "IndexOrdering", 0, t) && trimmed(t) != "zIsFastest") throw PlbError("Backward ordering not accepted while reading data.");
+        if (!xml_field(xml, "Offsets", 0, t)) throw PlbError(plb + ": no offsets");
+        const std::vector<long long> offsets = xml_ints(t);
+        std::vector<Component> comps;
+        size_t pos = 0;
+        while (xml_field(xml, "Component", pos, t, &pos)) {
+            const std::vector<long long> b = xml_ints(t);
+            if (b.size() != 6) throw PlbError(plb + ": malformed component");
+            Component c;
+            for (int k = 0; k < 6; ++k) c.box[k] = (int)b[k];
+            c.begin = comps.empty() ? 0 : comps.back().end;
+            if (comps.size() >= offsets.size()) throw PlbError("Number of offsets does not match number of components in XML file.");
+            c.end = offsets[comps.size()];
+            const long long want = (long long)(c.box[1] - c.box[0] + 1) * (c.box[3] - c.box[2] + 1) * (c.box[5] - c.box[4] + 1) * d.q * d.prec;
+            if (c.box[0] < 0 || c.box[1] >= d.nx || c.box[2] < 0 || c.box[3] >= d.ny || c.box[4] < 0 || c.box[5] >= d.nz || c.box[1] < c.box[0] ||
+                c.box[3] < c.box[2] || c.box[5] < c.box[4] || c.end - c.begin != want) throw PlbError(plb + ": component does not fit the lattice");
+            comps.push_back(c);
+        }
+        if (comps.size() != offsets.size() || comps.empty()) throw PlbError("Number of offsets does not match number of components in XML file.");
+        // the data file: next to the .plb unless the entry carries a path of its own
+        if (!xml_field(xml, "File", 0, t)) throw PlbError(plb + ": no data file");
+        std::string dat = trimmed(t);
+        if (dat.find('/') == std::string::npos) {
+            const size_t slash = base.rfind('/');
+            if (slash != std::string::npos) dat = base.substr(0, slash + 1) + dat;
+        }
+        fp = std::fopen(dat.c_str(), "rb");
+        if (!fp) throw PlbError("Could not open file " + dat + " for reading");
+        std::vector<unsigned char> buf;
+        for (const Component& c : comps) {
+            const size_t planeBytes = (size_t)(c.box[3] - c.box[2] + 1) * (c.box[5] - c.box[4] + 1) * d.q * d.prec;
+            const int planes = (int)std::max<size_t>(1, (size_t(64) << 20) / planeBytes);
+            for (int x = c.box[0]; x <= c.box[1]; ) {
+                // planes [x, x1] of this component that lie on this rank (a contiguous run: slabs are x-ranges)
+                int x1 = x;
+                const int one[6] = {x, x, c.box[2], c.box[3], c.box[4], c.box[5]};
+                const bool mine = L->impl->local_bytes(SBox(L, one)) != 0;
+                while (x1 < c.box[1] && x1 - x + 1 < planes) {
+                    const int nxt[6] = {x1 + 1, x1 + 1, c.box[2], c.box[3], c.box[4], c.box[5]};
+                    if ((L->impl->local_bytes(SBox(L, nxt)) != 0) != mine) break;
+                    ++x1;
+                }
+                if (mine) {
+                    const int box[6] = {x, x1, c.box[2], c.box[3], c.box[4], c.box[5]};
+                    const size_t bytes = (size_t)(x1 - x + 1) * planeBytes;
+                    buf.resize(bytes);
+                    if (fseeko(fp, (off_t)(c.begin + (long long)(x - c.box[0]) * (long long)planeBytes), SEEK_SET) != 0 ||
+                        std::fread(buf.data(), 1, bytes, fp) != bytes) throw PlbError("read error on " + dat);
+                    L->impl->upload(SBox(L, box), buf.data(), bytes);
+                }
+                x = x1 + 1;
+            }
+        }
+        std::fclose(fp);
+        return 1;
+    } catch (const std::exception& e) { if (fp) std::fclose(fp); return fail(e.what()); }
+}
+
 int plb_b200_set_stream(plb_b200_lattice* L, void* s) { PLB_TRY(L, L->impl->set_stream((cudaStream_t)s)) }
 int plb_b200_set_periodicity(plb_b200_lattice* L, int px, int py, int pz) {
     PLB_TRY(L, {

@@ -24,27 +24,21 @@
 
 namespace plb200 {
 
-// Launch shape and cache policy of the sweep.  The defaults are the measured optimum on B200 for
-// D3Q19 fp64 at 512^3 (profiles/r01_sweep_lab.log): 512-thread blocks for both halves, the odd
-// (neighbour) half with an L2 prefetch one grid stride ahead; both use many more blocks than are
-// resident (grid = SMs x factor), which staggers the load / compute / store phases of the resident blocks.  The macros exist for tools/sweep_lab.cu, which explores the alternatives.
+// Launch shape and cache policy of the sweep, per value type and velocity set: the measured optima on B200 at 512^3
+// (profiles/r01_sweep_lab.log, profiles/r02_sweep_lab.md).  512-thread blocks for both halves; many more blocks than are
+// resident (grid = SMs x factor), which staggers the load / compute / store phases of the resident blocks.
+//   registers   double: 128 per thread, one block per SM (D3Q19 needs 38 for the populations alone);
+//               float: 64, two blocks per SM -- the fp32 sweeps are short of warps, not of registers
+//               (D3Q19 BGK 4.52 -> 5.43 TB/s, D3Q27 Smagorinsky 3.88 -> 4.31 TB/s)
+//   L2 prefetch one tile ahead in the odd (neighbour) half: pays for D3Q19 fp64 only (6.96 -> 6.59 ms); elsewhere the 2 x Q
+//               extra instructions cost more than the latency they hide (D3Q27 fp64 odd half 10.97 -> 10.19 ms without,
+//               D3Q27 fp32 8.32 -> 7.16 ms)
+// The macros exist for tools/sweep_lab.cu, which explores the alternatives.
 #ifndef PLB_SWEEP_THREADS_EVEN
 #define PLB_SWEEP_THREADS_EVEN 512
 #endif
 #ifndef PLB_SWEEP_THREADS_ODD
 #define PLB_SWEEP_THREADS_ODD 512
-#endif
-#ifndef PLB_SWEEP_PF_EVEN       // L2 prefetch distance in grid strides (0 = off)
-#define PLB_SWEEP_PF_EVEN 0
-#endif
-#ifndef PLB_SWEEP_PF_ODD
-#define PLB_SWEEP_PF_ODD 1
-#endif
-#ifndef PLB_SWEEP_GRID_EVEN     // blocks per SM in the grid
-#define PLB_SWEEP_GRID_EVEN 64
-#endif
-#ifndef PLB_SWEEP_GRID_ODD
-#define PLB_SWEEP_GRID_ODD 128
 #endif
 #ifndef PLB_SWEEP_LD
 #define PLB_SWEEP_LD(p) (*(p))
@@ -53,14 +47,37 @@ namespace plb200 {
 #define PLB_SWEEP_ST(p, v) (*(p) = (v))
 #endif
 __host__ __device__ constexpr int sweep_threads(bool odd) { return odd ? PLB_SWEEP_THREADS_ODD : PLB_SWEEP_THREADS_EVEN; }
-#ifndef PLB_SWEEP_REGS          // register budget per thread that the launch bounds ask the compiler to keep
-#define PLB_SWEEP_REGS 128
+/// register budget per thread that the launch bounds ask the compiler to keep
+template <class T>
+__host__ __device__ constexpr int sweep_regs() {
+#ifdef PLB_SWEEP_REGS
+    return PLB_SWEEP_REGS;
+#else
+    return sizeof(T) == 4 ? 64 : 128;
 #endif
-__host__ __device__ constexpr int sweep_minblocks(bool odd) {
-    return 65536 / PLB_SWEEP_REGS / sweep_threads(odd) > 0 ? 65536 / PLB_SWEEP_REGS / sweep_threads(odd) : 1;
 }
-__host__ __device__ constexpr int sweep_prefetch(bool odd) { return odd ? PLB_SWEEP_PF_ODD : PLB_SWEEP_PF_EVEN; }
-__host__ __device__ constexpr int sweep_grid_factor(bool odd) { return odd ? PLB_SWEEP_GRID_ODD : PLB_SWEEP_GRID_EVEN; }
+template <class T>
+__host__ __device__ constexpr int sweep_minblocks(bool odd) {
+    return 65536 / sweep_regs<T>() / sweep_threads(odd) > 0 ? 65536 / sweep_regs<T>() / sweep_threads(odd) : 1;
+}
+/// L2 prefetch distance in tiles of the block (0 = off)
+template <class T, int Q>
+__host__ __device__ constexpr int sweep_prefetch(bool odd) {
+#ifdef PLB_SWEEP_PF_ODD
+    return odd ? PLB_SWEEP_PF_ODD : 0;
+#else
+    return (odd && sizeof(T) == 8 && Q == 19) ? 1 : 0;
+#endif
+}
+/// blocks per SM in the grid (profiles/r02_sweep_lab.md: flat within 1 % between 32 and 128, falling off on both sides)
+template <class T, int Q>
+__host__ __device__ constexpr int sweep_grid_factor(bool odd) {
+#ifdef PLB_SWEEP_GRID
+    return PLB_SWEEP_GRID;
+#else
+    return sizeof(T) == 4 ? (odd ? 16 : 64) : (Q == 19 ? 128 : (odd ? 64 : 128));
+#endif
+}
 constexpr int SWEEP_MAX_THREADS = 1024;
 
 enum XMode : int { XMODE_EDGE = 0, XMODE_GHOST = 1, XMODE_WRAP = 2 };

@@ -61,6 +61,7 @@ class LatticeImpl : public LatticeBase {
         std::vector<int> stageSplit;       ///< ... plane items first, finite-difference items from stageSplit[s]
         size_t nItems = 0;
         unsigned int* dRimTicket = nullptr; ///< counts the rim tiles of a launch that signals a neighbouring rank
+        bool bcAllInPasses = false;        ///< every owned cell with a boundary record is completed by a plane or finite-difference item
         bool valuesOnDevice = false;       ///< the records on the device hold newer u / rhoBar than `recs` (set_values_on_device)
         bool dirtyKind = true, dirtyBcIndex = true, dirtySched = true;
         bool kindUnflagged = true;         ///< dKind was uploaded from hKind and carries no KIND_PLANE flags
@@ -85,6 +86,7 @@ class LatticeImpl : public LatticeBase {
     bool extImplied_ = false;                ///< the fields are what BoxRhoBarJfunctional3D makes of the CURRENT populations: the fused sweep may recompute them
     bool extComplete_ = true;                ///< the fields are stored for every cell (false: implied by the populations and the boundary records)
     bool extBcStored_ = true;                ///< ... at least for the cells with boundary dynamics (stored under the records they were computed with)
+    bool storeBcMoments_ = false;            ///< the boundary passes running now also store the moments of their cells in the fields
     bool extFuse_ = true;                    ///< PLB_B200_EXT_EXPLICIT=1 in the environment: always store and re-read the fields (A/B tests)
     bool anySetup_ = false;
     bool stepped_ = false;
@@ -578,12 +580,18 @@ public:
             if (direct_) wait_neighbours();
             else exchange_copies(stream_);
             exchange_unpack();
+            storeBcMoments_ = ext && extFuse_;     // (level 3 of this step, for the cells the boundary passes complete)
             run_processors();
+            storeBcMoments_ = false;
             if (ext) {
                 // level 3: BoxRhoBarJfunctional3D on the whole lattice.  Stored only for the cells with boundary dynamics; for the
                 // others the next sweep recomputes it from the populations it gathers (launch_sweep), or ext_complete() stores it
                 if (extFuse_) {
-                    extComplete_ = false; extBcStored_ = false;     // all of it implied: nothing to run
+                    // all of it implied, nothing to run -- except that the boundary passes have left the moments of the cells
+                    // they completed in the fields (plane_stage_kernel), which is all cells with boundary dynamics if every
+                    // such cell belongs to a processor
+                    extComplete_ = false; extBcStored_ = true;
+                    for (const Slab& sl : slabs_) extBcStored_ = extBcStored_ && sl.bcAllInPasses;
                 } else {
                     rhobar_j_box(bulk_);
                     extComplete_ = true; extBcStored_ = true;
@@ -726,6 +734,7 @@ private:
         CellCtx<T> c;
         c.F = sl.F; c.kind = sl.dKind; c.bcIdx = sl.dBcIdx; c.dyns = dDyns_; c.bcs = sl.dBcs;
         c.g = geo(sl); c.swapped = swapped_;
+        c.ext = storeBcMoments_ ? sl.dExt : nullptr; c.extStride = sl.cellsStore;
         return c;
     }
 
@@ -988,6 +997,15 @@ private:
         sl.nAuto = count0[1];
         // count[2*stage + (0|1)] as before
         const int* count = count0.data() + 1;
+        {
+            std::unordered_map<int, int> seen;
+            for (const Item& it : sorted) seen[it.cell] = 1;
+            sl.bcAllInPasses = sl.nAuto == 0;
+            for (const BcRec& rec : sl.recs) {
+                if (!rec.alive || rec.cell < P_ || rec.cell >= (sl.nxl + 1) * P_) continue;
+                if (!seen.count(rec.cell)) { sl.bcAllInPasses = false; break; }
+            }
+        }
         sl.stageOffsets.assign(nStages + 1, 0);
         sl.stageSplit.assign(nStages, 0);
         for (int st = 0; st < nStages; ++st) { sl.stageOffsets[st] = count[2 * st]; sl.stageSplit[st] = count[2 * st + 1]; }
@@ -1138,7 +1156,7 @@ private:
         // blocks per SM in the grid: the measured optimum (kernels.cuh), or PLB_B200_GRID_EVEN / PLB_B200_GRID_ODD (tuning runs)
         static const int gfEnv[2] = {std::getenv("PLB_B200_GRID_EVEN") ? std::atoi(std::getenv("PLB_B200_GRID_EVEN")) : 0,
                                      std::getenv("PLB_B200_GRID_ODD") ? std::atoi(std::getenv("PLB_B200_GRID_ODD")) : 0};
-        const int gf = gfEnv[ODD ? 1 : 0] > 0 ? gfEnv[ODD ? 1 : 0] : sweep_grid_factor(ODD);
+        const int gf = gfEnv[ODD ? 1 : 0] > 0 ? gfEnv[ODD ? 1 : 0] : sweep_grid_factor<T, Q>(ODD);
         const int grid = std::max(1, std::min(a.nTiles, numSMs_ * gf));
         if (grid > sl.partialsCap) {
             if (sl.dPartials) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dPartials); devBytes_ -= (size_t)sl.partialsCap * 4 * sizeof(double); }

@@ -53,6 +53,8 @@ struct CellCtx {
     const Bc<T>* bcs;
     Geo g;
     bool swapped;
+    T* ext;              ///< external-moment sweep: the rhoBar / j fields (rhoBar [cells] | j_x | j_y | j_z, extStride apart), else nullptr:
+    long long extStride; ///< the boundary passes leave Dynamics::computeRhoBarJ of the cells they complete there (see plane_stage_kernel)
 };
 
 template <class T, int Q>
@@ -146,6 +148,11 @@ __device__ __forceinline__ void fd_regularize(const CellCtx<T>& cx, T* F, int c,
     decode_cell(cx.g, c, X, y, z);
     const Nbr n = make_nbr(cx.g, X, y, z);
     CellIO<T, Q>::store(F, cx.g, n, c, cx.swapped, v.f);
+    if (cx.ext && v.hasBc) {    // (see plane_stage_kernel)
+        T rb, jj[3];
+        L::cell_rhoBar_j(v.d, true, v.b, v.f, rb, jj);
+        cx.ext[c] = rb; cx.ext[cx.extStride + c] = jj[0]; cx.ext[2 * cx.extStride + c] = jj[1]; cx.ext[3 * cx.extStride + c] = jj[2];
+    }
 }
 
 /// One stage of the level-0 data processors (AtomicBlock3D::executeInternalProcessors,
@@ -177,9 +184,16 @@ __global__ void __launch_bounds__(128, 6) plane_stage_kernel(CellCtx<T> cx, T* F
     const Nbr n = make_nbr(cx.g, X, y, z);
     T f[Q];
     CellIO<T, Q>::load(F, cx.g, n, c, SWAPPED, f);
-    const int baseType = cx.dyns[kb & KIND_MASK].type;
-    complete_by_face<T, Q>(baseType, b, f);
+    const Dyn<T> d = cx.dyns[kb & KIND_MASK];
+    complete_by_face<T, Q>(d.type, b, f);
     CellIO<T, Q>::store(F, cx.g, n, c, SWAPPED, f);
+    if (cx.ext) {
+        // BoxRhoBarJfunctional3D (level 3) of this cell, while its completed populations are at hand: the next external-moment
+        // sweep reads the four values instead of recomputing them with one lane of a warp (a z-face has one such cell per row)
+        T rhoBar, j[3];
+        LB<T, Q>::cell_rhoBar_j(d, true, b, f, rhoBar, j);
+        cx.ext[c] = rhoBar; cx.ext[cx.extStride + c] = j[0]; cx.ext[2 * cx.extStride + c] = j[1]; cx.ext[3 * cx.extStride + c] = j[2];
+    }
 }
 
 template <class T, int Q>

@@ -118,7 +118,7 @@ struct RimStore<T, Q, Q> {
 /// flushed at block end: 7.90 ms; stash + per-SM mailbox + drain launch: 7.6 ms, with a 1 KB stack frame in the rare path),
 /// is a pass of its own again (plane_stage_kernel, kernels.cuh).
 template <class T, int Q, int MAIN, bool GENERIC, bool ODD>
-__global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) sweep_kernel(const SweepArgs<T> a) {
+__global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks<T>(ODD)) sweep_kernel(const SweepArgs<T> a) {
     using L = LB<T, Q>;
     constexpr int SWEEP_THREADS = sweep_threads(ODD);
     constexpr int WARPS = SWEEP_THREADS / 32;
@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks(ODD)) swee
             } else {
                 CellIO<T, Q>::load_base(a.ldBase, c, f);
             }
-            if (sweep_prefetch(ODD) > 0) {
-                const long long delta = (long long)sweep_prefetch(ODD) * gridDim.x * SWEEP_THREADS;
+            if (sweep_prefetch<T, Q>(ODD) > 0) {
+                const long long delta = (long long)sweep_prefetch<T, Q>(ODD) * gridDim.x * SWEEP_THREADS;
                 if (c + delta < rEnd) {
                     if (ODD && !interior) CellPrefetch<T, Q, ODD>::run(a.F, g, n, c, (int)delta);
                     else CellIO<T, Q>::prefetch_base(a.stBase, c + (int)delta);

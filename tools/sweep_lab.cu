@@ -51,8 +51,8 @@ __global__ void fill(T* F, long long n, int q) {
 int main(int argc, char** argv) {
     const int n = argc > 1 ? atoi(argv[1]) : 512;
     const int iters = argc > 2 ? atoi(argv[2]) : 10;
-    const int gfE = argc > 3 ? atoi(argv[3]) : sweep_grid_factor(false);   // blocks per SM in the grid (even half)
-    const int gfO = argc > 4 ? atoi(argv[4]) : sweep_grid_factor(true);    // (odd half)
+    const int gfE = argc > 3 ? atoi(argv[3]) : sweep_grid_factor<T, Q>(false);   // blocks per SM in the grid (even half)
+    const int gfO = argc > 4 ? atoi(argv[4]) : sweep_grid_factor<T, Q>(true);    // (odd half)
     Geo g;
     g.nxl = n; g.ny = n; g.nz = n; g.P = n * n; g.S = (long long)(n + 2) * n * n;
     g.perY = 0; g.perZ = 0; g.lowMode = XMODE_EDGE; g.highMode = XMODE_EDGE;
@@ -70,17 +70,15 @@ int main(int argc, char** argv) {
     fill<<<148 * 8, 256>>>(F, nF, Q);
     CK(cudaDeviceSynchronize());
     SweepArgs<T> a;
-    a.F = F; a.kind = kind; a.dyns = dyns; a.bcIdx = nullptr; a.bcs = nullptr; a.applyPlanes = 0; a.pendingStamp = -1; a.g = g;
+    a.F = F; a.kind = kind; a.dyns = dyns; a.bcIdx = nullptr; a.bcs = nullptr; a.g = g;
     a.lo.F = a.hi.F = nullptr; a.lo.S = a.hi.S = 0; a.lo.nxl = a.hi.nxl = 0; a.nRimTiles = 0; a.rimTicket = nullptr; a.sigLo = a.sigHi = nullptr; a.sigValue = 0;
     a.ext = nullptr; a.extStride = 0; a.extBcFromFields = 0;
-    a.drain = 0; a.mbCount = nullptr; a.mbCell = nullptr; a.mbF = nullptr;
-    // (ldBase / stBase are set per half below)
     const int cellBegin = g.P, cellEnd = (n + 1) * g.P;
     for (int k = 0; k < 3; ++k) { a.range[k].begin = a.range[k].end = a.range[k].tile0 = 0; }
     a.range[0].begin = cellBegin; a.range[0].end = cellEnd; a.nRanges = 1;
     a.omega = (T)1.2388; a.preFactor = (T)0.01; a.gatherStats = 1; a.partials = partials; a.ticket = ticket; a.statsOut = stats;
-    auto kEven = sweep_kernel<T, Q, LAB_DYN, false, false, false>;
-    auto kOdd = sweep_kernel<T, Q, LAB_DYN, false, true, false>;
+    auto kEven = sweep_kernel<T, Q, LAB_DYN, false, false>;
+    auto kOdd = sweep_kernel<T, Q, LAB_DYN, false, true>;
     int occE = 0, occO = 0, sms = 0;
     constexpr int TE = sweep_threads(false), TO = sweep_threads(true);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kEven, TE, 0));
@@ -91,14 +89,29 @@ int main(int argc, char** argv) {
     auto gridOf = [&](int gf, int threads) { const int nTiles = (cellEnd - cellBegin + threads - 1) / threads; a.nTiles = nTiles; return gf * sms < nTiles ? gf * sms : nTiles; };
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    // per-slot base pointers of the fast paths, as LatticeImpl::launch_sweep sets them
+    auto bases = [&](bool odd) {
+        using L = LB<T, Q>;
+        for (int i = 0; i < 27; ++i) a.ldBase[i] = a.stBase[i] = nullptr;
+        for (int i = 0; i < Q; ++i) {
+            const int o = L::opp(i);
+            if (!odd) { a.ldBase[i] = F + (long long)i * g.S; a.stBase[i] = F + (long long)o * g.S; }
+            else {
+                const long long off = (long long)L::c(i, 0) * g.P + (long long)L::c(i, 1) * g.nz + L::c(i, 2);
+                a.ldBase[i] = F + (long long)o * g.S - off; a.stBase[i] = F + (long long)i * g.S + off;
+            }
+        }
+    };
     double msE = 0, msO = 0;
     for (int it = 0; it < iters + 2; ++it) {
         float t;
         CK(cudaEventRecord(e0));
+        bases(false);
         kEven<<<gridOf(gfE, TE), TE>>>(a);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&t, e0, e1));
         if (it >= 2) msE += t;
         CK(cudaEventRecord(e0));
+        bases(true);
         kOdd<<<gridOf(gfO, TO), TO>>>(a);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&t, e0, e1));
         if (it >= 2) msO += t;
@@ -107,7 +120,7 @@ int main(int argc, char** argv) {
     msE /= iters; msO /= iters;
     const double bytes = (double)n * n * n * 2 * Q * sizeof(T);
     printf("T=%zu Q=%d dyn=%d n=%d policy=%d | even: thr %d pf %d gf %d regs %d occ %d | odd: thr %d pf %d gf %d regs %d occ %d | even %.3f ms %.0f GB/s | odd %.3f ms %.0f GB/s | avg %.0f GB/s %.0f MLUPS\n",
-           sizeof(T), Q, (int)LAB_DYN, n, LAB_POLICY, TE, sweep_prefetch(false), gfE, fe.numRegs, occE, TO, sweep_prefetch(true), gfO, fo.numRegs, occO,
+           sizeof(T), Q, (int)LAB_DYN, n, LAB_POLICY, TE, sweep_prefetch<T, Q>(false), gfE, fe.numRegs, occE, TO, sweep_prefetch<T, Q>(true), gfO, fo.numRegs, occO,
            msE, bytes / msE / 1e6, msO, bytes / msO / 1e6, 2 * bytes / (msE + msO) / 1e6, 2.0 * n * n * n / (msE + msO) / 1e3);
     return 0;
 }
