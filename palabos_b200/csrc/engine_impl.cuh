@@ -61,6 +61,7 @@ class LatticeImpl : public LatticeBase {
         std::vector<int> stageSplit;       ///< ... plane items first, finite-difference items from stageSplit[s]
         size_t nItems = 0;
         unsigned int* dRimTicket = nullptr; ///< counts the rim tiles of a launch that signals a neighbouring rank
+        int nReadPlanes0 = 0;              ///< the first nReadPlanes0 plane items of stage 0 are read by items of later stages
         bool bcAllInPasses = false;        ///< every owned cell with a boundary record is completed by a plane or finite-difference item
         bool valuesOnDevice = false;       ///< the records on the device hold newer u / rhoBar than `recs` (set_values_on_device)
         bool dirtyKind = true, dirtyBcIndex = true, dirtySched = true;
@@ -114,6 +115,9 @@ class LatticeImpl : public LatticeBase {
     unsigned int* dFlags_ = nullptr;         ///< [0]: step count of the neighbour below, [32]: of the neighbour above (128 bytes apart)
     unsigned int stepCount_ = 0;
     std::map<std::string, void*> ipcOpened_; ///< CUDA IPC mappings by handle (an allocation can be opened once per process)
+    cudaStream_t sideStream_ = nullptr;      ///< the finite-difference stages beside the plane pass (run_processors)
+    cudaEvent_t forkEvent_ = nullptr, joinEvent_ = nullptr;
+    bool overlapStages_ = true;              ///< PLB_B200_SERIAL_STAGES=1 in the environment: one stream (A/B tests)
     cudaStream_t copyStream_ = nullptr;
     cudaEvent_t copied_[2] = {nullptr, nullptr}, transposed_[2] = {nullptr, nullptr};
 
@@ -130,6 +134,7 @@ public:
         if ((long long)ny_ * nz_ >= (1ll << 30)) throw PlbError("y-z plane too large");
         if (const char* e = std::getenv("PLB_B200_HALO")) direct_ = !(std::strcmp(e, "nccl") == 0 || std::strcmp(e, "copy") == 0);
         if (const char* e = std::getenv("PLB_B200_EXT_EXPLICIT")) extFuse_ = !(e[0] == '1');
+        if (const char* e = std::getenv("PLB_B200_SERIAL_STAGES")) overlapStages_ = !(e[0] == '1');
         add_dyn(d.dynamics, d.p1, d.p2);     // entry 0: the background dynamics
         for (int s = 0; s < d.slabsPerRank; ++s) {
             Slab sl;
@@ -173,6 +178,7 @@ public:
         cudaFree(dDyns_); cudaFree(dStage_); cudaFree(dReduce_);
         if (comm_) NcclApi::get().CommDestroy(comm_);
         for (cudaEvent_t e : profEvents_) cudaEventDestroy(e);
+        if (sideStream_) { cudaStreamDestroy(sideStream_); cudaEventDestroy(forkEvent_); cudaEventDestroy(joinEvent_); }
         if (copyStream_) {
             cudaStreamDestroy(copyStream_);
             for (int k = 0; k < 2; ++k) { cudaEventDestroy(copied_[k]); cudaEventDestroy(transposed_[k]); }
@@ -574,7 +580,7 @@ public:
             // below only orders this rank's NEXT accesses to its rim / ghost planes after the neighbours' stores of THIS step.
             ++stepCount_;
             // plane cells of the dynamics-based boundary managers complete at collision time: right before the sweep
-            for (Slab& sl : slabs_) if (sl.nAuto > 0) launch_plane_stage(sl, 0, sl.nAuto);
+            for (Slab& sl : slabs_) if (sl.nAuto > 0) launch_plane_stage(sl, 0, sl.nAuto, stream_);
             for (Slab& sl : slabs_) launch_sweep(sl);
             swapped_ = !swapped_;
             if (direct_) wait_neighbours();
@@ -993,7 +999,17 @@ private:
         for (int b = 0; b < nBuckets; ++b) count0[b + 1] += count0[b];
         std::vector<Item> sorted(items.size());
         std::vector<int> cursor(count0.begin(), count0.begin() + nBuckets);
-        for (size_t k = 0; k < items.size(); ++k) sorted[cursor[bucket(k)]++] = items[k];
+        // (the plane items of stage 0 whose cells a later item reads go first: run_processors can then let the rest of the plane
+        // pass run beside the finite-difference stages)
+        sl.nReadPlanes0 = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t k = 0; k < items.size(); ++k) {
+                const bool plane0 = stageOf[k] == 0 && items[k].cls == PROC_PLANE;
+                const bool readLater = plane0 && rd(items[k].cell) > 0;
+                if ((pass == 0) != (readLater || !plane0)) continue;
+                sorted[cursor[bucket(k)]++] = items[k];
+                if (readLater) ++sl.nReadPlanes0;
+            }
         sl.nAuto = count0[1];
         // count[2*stage + (0|1)] as before
         const int* count = count0.data() + 1;
@@ -1023,10 +1039,10 @@ private:
     }
 
     /// completePopulations of the plane items [first, first + n) of a slab, in the current layout
-    void launch_plane_stage(Slab& sl, int first, int n) {
+    void launch_plane_stage(Slab& sl, int first, int n, cudaStream_t st) {
         if (n <= 0) return;
-        if (swapped_) plane_stage_kernel<T, Q, true><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
-        else plane_stage_kernel<T, Q, false><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
+        if (swapped_) plane_stage_kernel<T, Q, true><<<(n + 127) / 128, 128, 0, st>>>(ctx(sl), sl.F, sl.dItems + first, n);
+        else plane_stage_kernel<T, Q, false><<<(n + 127) / 128, 128, 0, st>>>(ctx(sl), sl.F, sl.dItems + first, n);
         launched();
     }
 
@@ -1251,9 +1267,37 @@ private:
     void run_processors() {
         for (Slab& sl : slabs_) {
             const int nStages = (int)sl.stageOffsets.size() - 1;
+            // The usual shape -- all plane items in stage 0, edges and corners behind them -- runs as a fork: the few plane cells
+            // that the later stages read first, then the finite-difference stages (short dependent launches, ~45 us each) on a
+            // side stream BESIDE the rest of the plane pass.  Safe because every storage location belongs to one (population,
+            // cell) pair and an item writes the locations of its own cell only.
+            bool fork = overlapStages_ && nStages >= 2 && sl.stageSplit[0] - sl.stageOffsets[0] - sl.nReadPlanes0 >= 4096;
+            for (int s = 1; s < nStages && fork; ++s) if (sl.stageSplit[s] > sl.stageOffsets[s]) fork = false;    // a plane item in a later stage
+            if (fork && sl.stageOffsets[1] > sl.stageSplit[0]) fork = false;                                       // finite-difference items in stage 0
+            if (fork) {
+                if (!sideStream_) {
+                    PLB_CUDA(cudaStreamCreateWithFlags(&sideStream_, cudaStreamNonBlocking));
+                    PLB_CUDA(cudaEventCreateWithFlags(&forkEvent_, cudaEventDisableTiming));
+                    PLB_CUDA(cudaEventCreateWithFlags(&joinEvent_, cudaEventDisableTiming));
+                }
+                const int first = sl.stageOffsets[0], split = sl.stageSplit[0];
+                launch_plane_stage(sl, first, sl.nReadPlanes0, stream_);
+                PLB_CUDA(cudaEventRecord(forkEvent_, stream_));
+                PLB_CUDA(cudaStreamWaitEvent(sideStream_, forkEvent_, 0));
+                launch_plane_stage(sl, first + sl.nReadPlanes0, split - first - sl.nReadPlanes0, stream_);
+                for (int s = 1; s < nStages; ++s) {
+                    const int n = sl.stageOffsets[s + 1] - sl.stageSplit[s];
+                    if (n <= 0) continue;
+                    fd_stage_kernel<T, Q><<<(n + 63) / 64, 64, 0, sideStream_>>>(ctx(sl), sl.F, sl.dItems + sl.stageSplit[s], n);
+                    launched();
+                }
+                PLB_CUDA(cudaEventRecord(joinEvent_, sideStream_));
+                PLB_CUDA(cudaStreamWaitEvent(stream_, joinEvent_, 0));
+                continue;
+            }
             for (int s = 0; s < nStages; ++s) {
                 const int first = sl.stageOffsets[s], split = sl.stageSplit[s], last = sl.stageOffsets[s + 1];
-                launch_plane_stage(sl, first, split - first);
+                launch_plane_stage(sl, first, split - first, stream_);
                 if (last > split) {
                     const int n = last - split;
                     fd_stage_kernel<T, Q><<<(n + 63) / 64, 64, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + split, n);

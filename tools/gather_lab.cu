@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) gather(double* F, long long S, int P, int
 #pragma unroll
             for (int i = 0; i < Q; ++i) f[i] = sh[i * 128];
         }
-    } else {
+    } else if (MODE == 2) {
         double2* sh = reinterpret_cast<double2*>(smem) + threadIdx.x;   // [Q][128] pairs
         const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar);
         if (threadIdx.x == 0) {
@@ -71,6 +71,28 @@ __global__ void __launch_bounds__(128) gather(double* F, long long S, int P, int
 #pragma unroll
             for (int i = 0; i < Q; ++i) { const double2 v = sh[i * 128]; f[i] = (c & 1) ? v.y : v.x; }
         }
+    }
+    if (MODE == 3) {
+        // 256-bit accesses (sm_100): the whole 32-byte sector of each population, so that the store is a full-sector write
+        if (act) {
+            const long long ca = c & ~3ll;
+            double s = 0.;
+            double v[Q][4];
+#pragma unroll
+            for (int i = 0; i < Q; ++i)
+                asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[i][0]), "=d"(v[i][1]), "=d"(v[i][2]), "=d"(v[i][3]) : "l"(F + i * S + ca));
+#pragma unroll
+            for (int i = 0; i < Q; ++i) f[i] = v[i][c & 3];
+            s = work(f);
+            if (STORE) {
+#pragma unroll
+                for (int i = 0; i < Q; ++i) {
+                    v[i][c & 3] = f[i] + 1e-9 * s;
+                    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(F + i * S + ca), "d"(v[i][0]), "d"(v[i][1]), "d"(v[i][2]), "d"(v[i][3]) : "memory");
+                }
+            } else if (s == 12345.678) F[c] = s;
+        }
+        return;
     }
     if (act) {
         const double s = work(f);
@@ -109,6 +131,8 @@ int main(int argc, char** argv) {
     run("ldg          gather+scatter", gather<0, true>, 0);
     run("cp.async 8B  gather only", gather<1, false>, Q * 128 * 8);
     run("cp.async 8B  gather+scatter", gather<1, true>, Q * 128 * 8);
+    run("256-bit      gather only", gather<3, false>, 0);
+    run("256-bit      gather+scatter", gather<3, true>, 0);
     run("bulk 16B     gather only", gather<2, false>, Q * 128 * 16);
     run("bulk 16B     gather+scatter", gather<2, true>, Q * 128 * 16);
     return 0;
