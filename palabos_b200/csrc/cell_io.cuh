@@ -84,7 +84,11 @@ enum XMode : int { XMODE_EDGE = 0, XMODE_GHOST = 1, XMODE_WRAP = 2 };
 
 /// Per-cell kind byte: bits 0-5 = index into the dynamics table; bit 7 (external-moment sweep only) = the moments of the
 /// cell are not those of a bulk cell: boundary dynamics on top, or envelope layer (flag_ext_cells_kernel).
+/// bit 6 = "handoff" cell: a plane boundary cell that sits alone among the 32 cells of a warp (a z-face: one per row).  The
+/// plane pass leaves its completed populations in a compact buffer (indexed by boundary record) instead of scattering 19
+/// isolated 8-byte stores into the lattice, and the next sweep takes them from there (sweep_kernel).
 constexpr int KIND_MASK = 0x3f;
+constexpr int KIND_HANDOFF = 0x40;
 constexpr int KIND_PLANE = 0x80;
 
 struct Geo {
@@ -307,6 +311,8 @@ struct SweepArgs {
     double* partials;         ///< [gridDim.x][4] per-block partial sums
     unsigned int* ticket;     ///< arrival counter for the last-block reduction
     double* statsOut;         ///< [4] sum rhoBar, sum uSqr, max uSqr, cell count of this launch
+    const T* hbuf;            ///< completed populations of the handoff cells, [Q][hStride] by boundary record; nullptr: nothing to take over
+    long long hStride;
     const T* ext;             ///< MAIN == DYN_EXTERNAL: rhoBar [cells] followed by j_x, j_y, j_z [cells] each (extStride apart)
     long long extStride;
     int extBcFromFields;      ///< DYN_EXTERNAL_FUSED: the moments of cells with boundary dynamics are stored in the fields (else implied)

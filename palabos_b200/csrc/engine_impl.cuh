@@ -62,10 +62,13 @@ class LatticeImpl : public LatticeBase {
         size_t nItems = 0;
         unsigned int* dRimTicket = nullptr; ///< counts the rim tiles of a launch that signals a neighbouring rank
         int nReadPlanes0 = 0;              ///< the first nReadPlanes0 plane items of stage 0 are read by items of later stages
+        int nHandoff0 = 0;                 ///< the last nHandoff0 plane items of stage 0 are handoff cells (Item::c = 1)
+        T* dHbuf = nullptr; size_t hbufCap = 0;   ///< their completed populations between the plane pass and the next sweep, [Q][dBcsCap]
         bool bcAllInPasses = false;        ///< every owned cell with a boundary record is completed by a plane or finite-difference item
         bool valuesOnDevice = false;       ///< the records on the device hold newer u / rhoBar than `recs` (set_values_on_device)
         bool dirtyKind = true, dirtyBcIndex = true, dirtySched = true;
-        bool kindUnflagged = true;         ///< dKind was uploaded from hKind and carries no KIND_PLANE flags
+        bool kindUnflagged = true;         ///< dKind was uploaded from hKind and the flag bits it needs (KIND_PLANE, KIND_HANDOFF) are not set yet
+        bool kindHasFlags = false;         ///< dKind carries flag bits (of an earlier set-up, if kindUnflagged)
         int bcDirtyLo = 0, bcDirtyHi = 0;  ///< record range whose values must be re-uploaded
     };
 
@@ -117,6 +120,8 @@ class LatticeImpl : public LatticeBase {
     std::map<std::string, void*> ipcOpened_; ///< CUDA IPC mappings by handle (an allocation can be opened once per process)
     cudaStream_t sideStream_ = nullptr;      ///< the finite-difference stages beside the plane pass (run_processors)
     cudaEvent_t forkEvent_ = nullptr, joinEvent_ = nullptr;
+    bool handoffAllowed_ = true;             ///< PLB_B200_NO_HANDOFF=1 in the environment: the plane pass writes every cell back into the lattice (A/B tests)
+    bool handoff_ = false;                   ///< the handoff buffers hold the completed populations of their cells; the lattice holds the raw ones
     bool overlapStages_ = true;              ///< PLB_B200_SERIAL_STAGES=1 in the environment: one stream (A/B tests)
     cudaStream_t copyStream_ = nullptr;
     cudaEvent_t copied_[2] = {nullptr, nullptr}, transposed_[2] = {nullptr, nullptr};
@@ -135,6 +140,7 @@ public:
         if (const char* e = std::getenv("PLB_B200_HALO")) direct_ = !(std::strcmp(e, "nccl") == 0 || std::strcmp(e, "copy") == 0);
         if (const char* e = std::getenv("PLB_B200_EXT_EXPLICIT")) extFuse_ = !(e[0] == '1');
         if (const char* e = std::getenv("PLB_B200_SERIAL_STAGES")) overlapStages_ = !(e[0] == '1');
+        if (const char* e = std::getenv("PLB_B200_NO_HANDOFF")) handoffAllowed_ = !(e[0] == '1');
         add_dyn(d.dynamics, d.p1, d.p2);     // entry 0: the background dynamics
         for (int s = 0; s < d.slabsPerRank; ++s) {
             Slab sl;
@@ -173,7 +179,7 @@ public:
         cudaFree(dFlags_);
         for (Slab& sl : slabs_) {
             cudaFree(sl.F); cudaFree(sl.dExt); cudaFree(sl.dBcCells); cudaFree(sl.dKind); cudaFree(sl.dBcIdx); cudaFree(sl.dBcs); cudaFree(sl.dItems);
-            cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket); cudaFree(sl.dRimTicket);
+            cudaFree(sl.dPartials); cudaFree(sl.dStats); cudaFree(sl.dTicket); cudaFree(sl.dRimTicket); cudaFree(sl.dHbuf);
         }
         cudaFree(dDyns_); cudaFree(dStage_); cudaFree(dReduce_);
         if (comm_) NcclApi::get().CommDestroy(comm_);
@@ -375,7 +381,7 @@ public:
     void initialize_at_equilibrium(const int box[6], double rho, const double u[3]) override {
         check_box(box);
         ext_detach();
-        sync_setup();
+        sync_setup(); materialize();
         for (Slab& sl : slabs_) {
             BoxL b;
             if (!local_box(sl, box, b)) continue;
@@ -390,7 +396,7 @@ public:
         check_box(box);
         if (!ru) throw PlbError("null field");
         ext_detach();
-        sync_setup();
+        sync_setup(); materialize();
         const long long rowCells = (long long)(box[3] - box[2] + 1) * (box[5] - box[4] + 1);
         for (Slab& sl : slabs_) {
             BoxL b;
@@ -454,7 +460,7 @@ public:
         check_box(box);
         int b[6];
         if (!intersect(box, bulk_, b)) return;
-        sync_setup();
+        sync_setup(); materialize();
         const bool whole = std::memcmp(b, bulk_, sizeof b) == 0;
         if (!whole) ext_complete();            // the rest of the fields keeps its values
         rhobar_j_box(b);
@@ -474,7 +480,7 @@ public:
     /// store the implied part of the fields (only ever needed when somebody wants to see or change them)
     void ext_complete() {
         if (!ext_ || extComplete_) return;
-        sync_setup();
+        sync_setup(); materialize();
         if (extComplete_) return;              // sync_setup had to store them itself (set-up changes were outstanding)
         rhobar_j_box(bulk_);
         extComplete_ = true; extBcStored_ = true;
@@ -535,7 +541,7 @@ public:
     void density_velocity(const int box[6], void* out, size_t bytes) override {
         check_box(box);
         if (bytes != local_bytes(box) / Q * 4) throw PlbError("buffer size does not match the box");
-        sync_setup();
+        sync_setup(); materialize();
         char* host = (char*)out;
         for (Slab& sl : slabs_) {
             BoxL b;
@@ -582,6 +588,7 @@ public:
             // plane cells of the dynamics-based boundary managers complete at collision time: right before the sweep
             for (Slab& sl : slabs_) if (sl.nAuto > 0) launch_plane_stage(sl, 0, sl.nAuto, stream_);
             for (Slab& sl : slabs_) launch_sweep(sl);
+            handoff_ = false;                  // the sweep has taken the handoff cells' populations over
             swapped_ = !swapped_;
             if (direct_) wait_neighbours();
             else exchange_copies(stream_);
@@ -741,6 +748,7 @@ private:
         c.F = sl.F; c.kind = sl.dKind; c.bcIdx = sl.dBcIdx; c.dyns = dDyns_; c.bcs = sl.dBcs;
         c.g = geo(sl); c.swapped = swapped_;
         c.ext = storeBcMoments_ ? sl.dExt : nullptr; c.extStride = sl.cellsStore;
+        c.hbuf = sl.dHbuf; c.hStride = (long long)sl.hbufCap;
         return c;
     }
 
@@ -825,6 +833,7 @@ private:
             if (sl.dirtyKind || sl.dirtyBcIndex || sl.dirtySched || sl.bcDirtyHi > sl.bcDirtyLo || sl.kindUnflagged) return false;
         if (ext_ && !extComplete_ && !extBcStored_) {
             // the implied moments of the boundary cells are functions of the records about to change: store them first
+            materialize();
             for (Slab& sl : slabs_) {
                 if (sl.nBcCells == 0) continue;
                 rhobar_j_list_kernel<T, Q><<<(sl.nBcCells + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.dBcCells, sl.nBcCells, sl.dExt, sl.cellsStore);
@@ -946,7 +955,7 @@ private:
                     if (!sl.cellToRec.count(cell)) continue;
                     if (p.a == 1) {            // completes at collision time: no processor, no dependencies
                         Item it;
-                        it.cell = cell; it.bc = sl.cellToRec.at(cell); it.cls = (signed char)PROC_PLANE; it.a = 1; it.b = 0; it.c = 0;
+                        it.cell = cell; it.bc = sl.cellToRec.at(cell); it.cls = (signed char)PROC_PLANE; it.a = 1; it.b = 0; it.c = 0;   // (c: handoff flag, never for these)
                         items.push_back(it);
                         stageOf.push_back(-1);
                         continue;
@@ -984,7 +993,7 @@ private:
                 Item it;
                 it.cell = cell; it.cls = (signed char)p.cls; it.a = (signed char)p.a; it.b = (signed char)p.b; it.c = (signed char)p.c;
                 it.bc = -1;
-                if (p.cls == PROC_PLANE) it.bc = sl.cellToRec.at(cell);
+                if (p.cls == PROC_PLANE) { it.bc = sl.cellToRec.at(cell); it.c = 0; }     // (c: handoff flag, set when the items are sorted)
                 items.push_back(it);
                 stageOf.push_back(st);
             }
@@ -1001,14 +1010,28 @@ private:
         std::vector<int> cursor(count0.begin(), count0.begin() + nBuckets);
         // (the plane items of stage 0 whose cells a later item reads go first: run_processors can then let the rest of the plane
         // pass run beside the finite-difference stages)
-        sl.nReadPlanes0 = 0;
-        for (int pass = 0; pass < 2; ++pass)
+        // ... and the handoff cells last (KIND_HANDOFF, cell_io.cuh): plane cells of stage 0 that nothing else touches and that sit
+        // among at most 8 of their kind in the 32 cells a warp of the sweep covers (a z-face: one per row)
+        sl.nReadPlanes0 = 0; sl.nHandoff0 = 0;
+        auto plane0 = [&](size_t k) { return stageOf[k] == 0 && items[k].cls == PROC_PLANE; };
+        auto untouched = [&](size_t k) { return rd(items[k].cell) <= 0 && wr(items[k].cell) <= 0; };
+        std::unordered_map<int, int> perPiece;
+        if (handoffAllowed_ && !(ext_ && !extFuse_))
+            for (size_t k = 0; k < items.size(); ++k) if (plane0(k) && untouched(k)) ++perPiece[(items[k].cell - P_) / 32];
+        for (int pass = 0; pass < 3; ++pass)
             for (size_t k = 0; k < items.size(); ++k) {
-                const bool plane0 = stageOf[k] == 0 && items[k].cls == PROC_PLANE;
-                const bool readLater = plane0 && rd(items[k].cell) > 0;
-                if ((pass == 0) != (readLater || !plane0)) continue;
+                int cls = 0;                                   // 0: everything else and the plane items a later stage reads; 1: plain; 2: handoff
+                if (plane0(k)) {
+                    const bool readLater = rd(items[k].cell) > 0;
+                    auto pc = perPiece.find((items[k].cell - P_) / 32);
+                    const bool hand = !readLater && untouched(k) && pc != perPiece.end() && pc->second <= 8;
+                    cls = readLater ? 0 : (hand ? 2 : 1);
+                    if (pass == 0 && readLater) ++sl.nReadPlanes0;
+                    if (pass == 2 && hand) ++sl.nHandoff0;
+                    if (items[k].cls == PROC_PLANE) items[k].c = (signed char)(hand ? 1 : 0);
+                }
+                if (cls != pass) continue;
                 sorted[cursor[bucket(k)]++] = items[k];
-                if (readLater) ++sl.nReadPlanes0;
             }
         sl.nAuto = count0[1];
         // count[2*stage + (0|1)] as before
@@ -1046,10 +1069,25 @@ private:
         launched();
     }
 
+    /// The handoff buffers back into the lattice (handoff_scatter_kernel): before anything but the sweep reads or writes the
+    /// populations of those cells.
+    void materialize() {
+        if (!handoff_) return;
+        for (Slab& sl : slabs_) {
+            if (sl.nHandoff0 <= 0 || sl.stageOffsets.size() < 2) continue;
+            const int first = sl.stageSplit[0] - sl.nHandoff0, n = sl.nHandoff0;
+            if (swapped_) handoff_scatter_kernel<T, Q, true><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
+            else handoff_scatter_kernel<T, Q, false><<<(n + 127) / 128, 128, 0, stream_>>>(ctx(sl), sl.F, sl.dItems + first, n);
+            launched();
+        }
+        handoff_ = false;
+    }
+
     void sync_setup() {
         bool anyDirty = dirtyDyns_;
         for (Slab& sl : slabs_) anyDirty = anyDirty || sl.dirtyKind || sl.dirtyBcIndex || sl.dirtySched || sl.bcDirtyHi > sl.bcDirtyLo;
         if (!anyDirty) return;
+        materialize();                         // with the items and records the buffers were filled under
         pull_record_values();
         bool reflag = false;
         bool structural = false;               // (external-moment sweep) which cells read their moments from the fields may have changed
@@ -1081,7 +1119,7 @@ private:
                 PLB_CUDA(cudaMemcpyAsync(sl.dKind, sl.hKind.data(), (size_t)sl.cellsStore, cudaMemcpyHostToDevice, stream_));
                 PLB_CUDA(cudaStreamSynchronize(stream_));
                 sl.dirtyKind = false;
-                sl.kindUnflagged = true;
+                sl.kindUnflagged = true; sl.kindHasFlags = false;
             }
             if (sl.dirtyBcIndex) {
                 // records keep their position (dead ones are simply not indexed)
@@ -1131,18 +1169,32 @@ private:
             if (sl.dirtySched) { build_schedule(sl); sl.dirtySched = false; reflag = true; }
             if (sl.kindUnflagged) reflag = true;
         }
-        if (ext_ && (structural || reflag)) {
-            // KIND_PLANE (external-moment sweep): "boundary dynamics on top, or envelope layer" -- the cells whose moments are
-            // not those of a bulk cell
+        if (structural || reflag) {
             for (Slab& sl : slabs_) {
-                if (!sl.kindUnflagged) {   // drop the flags of an earlier set-up
+                if (sl.kindHasFlags) {     // drop the flags of an earlier set-up
                     PLB_CUDA(cudaMemcpyAsync(sl.dKind, sl.hKind.data(), (size_t)sl.cellsStore, cudaMemcpyHostToDevice, stream_));
                     PLB_CUDA(cudaStreamSynchronize(stream_));
                 }
-                BoxL lb;
-                if (!local_box(sl, bulk_, lb)) { lb.X0 = 1; lb.X1 = 0; lb.y0 = lb.z0 = 0; lb.y1 = lb.z1 = -1; }
-                flag_ext_cells_kernel<<<(unsigned)((sl.cellsStore + 255) / 256), 256, 0, stream_>>>(sl.dKind, sl.dBcIdx, geo(sl), lb, (int)sl.cellsStore);
-                launched();
+                if (ext_) {
+                    // KIND_PLANE (external-moment sweep): "boundary dynamics on top, or envelope layer" -- the cells whose moments
+                    // are not those of a bulk cell
+                    BoxL lb;
+                    if (!local_box(sl, bulk_, lb)) { lb.X0 = 1; lb.X1 = 0; lb.y0 = lb.z0 = 0; lb.y1 = lb.z1 = -1; }
+                    flag_ext_cells_kernel<<<(unsigned)((sl.cellsStore + 255) / 256), 256, 0, stream_>>>(sl.dKind, sl.dBcIdx, geo(sl), lb, (int)sl.cellsStore);
+                    launched();
+                }
+                if (sl.nHandoff0 > 0) {
+                    // KIND_HANDOFF, and the buffer that carries those cells' populations from the plane pass to the next sweep
+                    if (sl.hbufCap != sl.dBcsCap) {
+                        if (sl.dHbuf) { PLB_CUDA(cudaStreamSynchronize(stream_)); cudaFree(sl.dHbuf); devBytes_ -= sl.hbufCap * Q * sizeof(T); }
+                        sl.hbufCap = sl.dBcsCap;
+                        sl.dHbuf = (T*)dev_alloc(sl.hbufCap * Q * sizeof(T));
+                    }
+                    const int first = sl.stageSplit[0] - sl.nHandoff0;
+                    flag_handoff_cells_kernel<<<(sl.nHandoff0 + 255) / 256, 256, 0, stream_>>>(sl.dItems + first, sl.nHandoff0, sl.dKind);
+                    launched();
+                }
+                sl.kindHasFlags = sl.nHandoff0 > 0 || ext_;
             }
         }
         for (Slab& sl : slabs_) sl.kindUnflagged = false;
@@ -1235,6 +1287,7 @@ private:
         a.gatherStats = statsOn_ ? 1 : 0;
         a.partials = nullptr; a.ticket = sl.dTicket; a.statsOut = sl.dStats;
         a.ext = sl.dExt; a.extStride = sl.cellsStore; a.extBcFromFields = 1;
+        a.hbuf = (handoff_ && sl.nHandoff0 > 0) ? sl.dHbuf : nullptr; a.hStride = (long long)sl.hbufCap;
         if (ext_) {
             // the statistics of this mode are never evaluated by the reference's loop (executeInternalProcessors + incrementTime)
             a.gatherStats = 0;
@@ -1265,6 +1318,8 @@ private:
     }
 
     void run_processors() {
+        materialize();                         // processors run twice in a row (initialize() called again)
+        for (Slab& sl : slabs_) if (sl.nHandoff0 > 0) handoff_ = true;      // (the plane pass below fills the buffers)
         for (Slab& sl : slabs_) {
             const int nStages = (int)sl.stageOffsets.size() - 1;
             // The usual shape -- all plane items in stage 0, edges and corners behind them -- runs as a fork: the few plane cells
@@ -1527,7 +1582,7 @@ private:
         if (bytes != local_bytes(box)) throw PlbError("buffer size does not match the box");
         if (!data && bytes) throw PlbError("null buffer");
         if (up) ext_detach();
-        sync_setup();
+        sync_setup(); materialize();
         if (!copyStream_) {
             PLB_CUDA(cudaStreamCreateWithFlags(&copyStream_, cudaStreamNonBlocking));
             for (int k = 0; k < 2; ++k) {
@@ -1577,7 +1632,7 @@ private:
 
     double box_sum(const int box[6], int what) {
         check_box(box);
-        sync_setup();
+        sync_setup(); materialize();
         double total = 0.;
         for (Slab& sl : slabs_) {
             BoxL b;

@@ -53,6 +53,8 @@ struct CellCtx {
     const Bc<T>* bcs;
     Geo g;
     bool swapped;
+    T* hbuf;             ///< handoff buffer [Q][hStride] by boundary record (see KIND_HANDOFF)
+    long long hStride;
     T* ext;              ///< external-moment sweep: the rhoBar / j fields (rhoBar [cells] | j_x | j_y | j_z, extStride apart), else nullptr:
     long long extStride; ///< the boundary passes leave Dynamics::computeRhoBarJ of the cells they complete there (see plane_stage_kernel)
 };
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(128, 6) plane_stage_kernel(CellCtx<T> cx, T* F
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nItems) return;
     const int c = items[t].cell, bi = items[t].bc;
+    const bool handoff = items[t].c != 0;           // completed populations go to the handoff buffer, not back into the lattice
     if (bi < 0) return;
     const int kb = cx.kind[c];
     const Bc<T> b = cx.bcs[bi];
@@ -186,7 +189,12 @@ __global__ void __launch_bounds__(128, 6) plane_stage_kernel(CellCtx<T> cx, T* F
     CellIO<T, Q>::load(F, cx.g, n, c, SWAPPED, f);
     const Dyn<T> d = cx.dyns[kb & KIND_MASK];
     complete_by_face<T, Q>(d.type, b, f);
-    CellIO<T, Q>::store(F, cx.g, n, c, SWAPPED, f);
+    if (handoff) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) cx.hbuf[(long long)i * cx.hStride + bi] = f[i];
+    } else {
+        CellIO<T, Q>::store(F, cx.g, n, c, SWAPPED, f);
+    }
     if (cx.ext) {
         // BoxRhoBarJfunctional3D (level 3) of this cell, while its completed populations are at hand: the next external-moment
         // sweep reads the four values instead of recomputing them with one lane of a warp (a z-face has one such cell per row)
@@ -194,6 +202,29 @@ __global__ void __launch_bounds__(128, 6) plane_stage_kernel(CellCtx<T> cx, T* F
         LB<T, Q>::cell_rhoBar_j(d, true, b, f, rhoBar, j);
         cx.ext[c] = rhoBar; cx.ext[cx.extStride + c] = j[0]; cx.ext[2 * cx.extStride + c] = j[1]; cx.ext[3 * cx.extStride + c] = j[2];
     }
+}
+
+/// The handoff buffer back into the lattice: before anything but the sweep reads or writes the populations of those cells
+/// (downloads, reductions, re-initialisation, set-up changes, a second initialize()).
+template <class T, int Q, bool SWAPPED>
+__global__ void __launch_bounds__(128) handoff_scatter_kernel(CellCtx<T> cx, T* F, const Item* __restrict__ items, int nItems) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nItems) return;
+    const int c = items[t].cell, bi = items[t].bc;
+    if (bi < 0 || items[t].c == 0) return;
+    int X, y, z;
+    decode_cell(cx.g, c, X, y, z);
+    const Nbr n = make_nbr(cx.g, X, y, z);
+    T f[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) f[i] = cx.hbuf[(long long)i * cx.hStride + bi];
+    CellIO<T, Q>::store(F, cx.g, n, c, SWAPPED, f);
+}
+
+/// Mark the handoff cells in the kind bytes.
+static __global__ void flag_handoff_cells_kernel(const Item* items, int n, uint8_t* kind) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && items[t].c != 0) kind[items[t].cell] |= (uint8_t)KIND_HANDOFF;
 }
 
 template <class T, int Q>

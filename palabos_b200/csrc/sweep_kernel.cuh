@@ -275,6 +275,12 @@ __global__ void __launch_bounds__(sweep_threads(ODD), sweep_minblocks<T>(ODD)) s
                 }
             }
             k = a.kind[c];
+            if ((k & KIND_HANDOFF) && a.hbuf != nullptr) {
+                // a handoff cell: the plane pass has left its completed populations in the buffer (what was gathered is the raw set)
+                const T* h = a.hbuf + a.bcIdx[c];
+#pragma unroll
+                for (int i = 0; i < Q; ++i) f[i] = h[(long long)i * a.hStride];
+            }
         }
         p = next_piece();           // (the gather is in flight)
         if (active) collide_scatter(c, k, interior, X, n, f);
