@@ -173,6 +173,44 @@ static void addCorner(OnLatticeBoundaryCondition3D<T,D>& bc, MultiBlockLattice3D
 }
 
 template<template<typename U> class D>
+static void addInnerEdge(OnLatticeBoundaryCondition3D<T,D>& bc, MultiBlockLattice3D<T,D>& lat,
+                         int plane, int n1, int n2, Box3D box)
+{
+    int code = plane * 4 + (n1 > 0 ? 2 : 0) + (n2 > 0 ? 1 : 0);
+    switch (code) {
+        case 0:  bc.addInternalVelocityEdge0NN(box, lat); break;
+        case 1:  bc.addInternalVelocityEdge0NP(box, lat); break;
+        case 2:  bc.addInternalVelocityEdge0PN(box, lat); break;
+        case 3:  bc.addInternalVelocityEdge0PP(box, lat); break;
+        case 4:  bc.addInternalVelocityEdge1NN(box, lat); break;
+        case 5:  bc.addInternalVelocityEdge1NP(box, lat); break;
+        case 6:  bc.addInternalVelocityEdge1PN(box, lat); break;
+        case 7:  bc.addInternalVelocityEdge1PP(box, lat); break;
+        case 8:  bc.addInternalVelocityEdge2NN(box, lat); break;
+        case 9:  bc.addInternalVelocityEdge2NP(box, lat); break;
+        case 10: bc.addInternalVelocityEdge2PN(box, lat); break;
+        case 11: bc.addInternalVelocityEdge2PP(box, lat); break;
+    }
+}
+
+template<template<typename U> class D>
+static void addInnerCorner(OnLatticeBoundaryCondition3D<T,D>& bc, MultiBlockLattice3D<T,D>& lat,
+                           int nx, int ny, int nz, plint x, plint y, plint z)
+{
+    int code = (nx > 0 ? 4 : 0) + (ny > 0 ? 2 : 0) + (nz > 0 ? 1 : 0);
+    switch (code) {
+        case 0: bc.addInternalVelocityCornerNNN(x, y, z, lat); break;
+        case 1: bc.addInternalVelocityCornerNNP(x, y, z, lat); break;
+        case 2: bc.addInternalVelocityCornerNPN(x, y, z, lat); break;
+        case 3: bc.addInternalVelocityCornerNPP(x, y, z, lat); break;
+        case 4: bc.addInternalVelocityCornerPNN(x, y, z, lat); break;
+        case 5: bc.addInternalVelocityCornerPNP(x, y, z, lat); break;
+        case 6: bc.addInternalVelocityCornerPPN(x, y, z, lat); break;
+        case 7: bc.addInternalVelocityCornerPPP(x, y, z, lat); break;
+    }
+}
+
+template<template<typename U> class D>
 static int runScenario(std::vector<std::string> const& lines, size_t first,
                        plint nx, plint ny, plint nz, std::string dyn, double p1, double p2,
                        plint bx, plint by, plint bz)
@@ -289,6 +327,16 @@ static int runScenario(std::vector<std::string> const& lines, size_t first,
             std::string kind; int a, b, c; plint x, y, z; in >> kind >> a >> b >> c >> x >> y >> z;
             bcs.push_back(makeBC<D>(kind));
             addCorner<D>(*bcs.back(), lattice, a, b, c, x, y, z);
+        } else if (cmd == "bc_iedge") {
+            // inner (concave) edges and corners: RegularizedVelocityInnerEdge/CornerDynamics3D, regularizedBoundaryDynamics3D.hh:40-298
+            std::string kind; int plane, n1, n2; in >> kind >> plane >> n1 >> n2;
+            Box3D box = readBox(in);
+            bcs.push_back(makeBC<D>(kind));
+            addInnerEdge<D>(*bcs.back(), lattice, plane, n1, n2, box);
+        } else if (cmd == "bc_icorner") {
+            std::string kind; int a, b, c; plint x, y, z; in >> kind >> a >> b >> c >> x >> y >> z;
+            bcs.push_back(makeBC<D>(kind));
+            addInnerCorner<D>(*bcs.back(), lattice, a, b, c, x, y, z);
         } else if (cmd == "set_velocity") {
             Box3D box = readBox(in); double u[3]; in >> u[0] >> u[1] >> u[2];
             setBoundaryVelocity(lattice, box, Array<T,3>((T)u[0], (T)u[1], (T)u[2]));
