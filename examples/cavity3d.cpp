@@ -31,6 +31,34 @@ int run(plint nx, plint ny, plint nz, plint steps, const char* dump) {
                             : (model == "equilibrium" ? createEquilibriumBoundaryCondition3D<T, DESCRIPTOR>()
                                : (model == "interp" ? createInterpBoundaryCondition3D<T, DESCRIPTOR>() : createLocalBoundaryCondition3D<T, DESCRIPTOR>()));
     bc->setVelocityConditionOnBlockBoundaries(lattice);
+    if (std::getenv("CAVITY3D_BLOCK")) {
+        // a solid block inside the cavity: its faces are velocity planes, its edges and corners the CONCAVE ones of the boundary
+        // condition (addInternalVelocityEdge* / addInternalVelocityCorner*); normals point from the fluid into the solid
+        const plint x0 = nx / 3, x1 = nx / 3 + 3, y0 = ny / 3, y1 = ny / 3 + 3, z0 = nz / 3, z1 = nz / 3 + 2;
+        defineDynamics(lattice, Box3D(x0 + 1, x1 - 1, y0 + 1, y1 - 1, z0 + 1, z1 - 1), new BounceBack<T, DESCRIPTOR>((T)1.));
+        bc->addVelocityBoundary0P(Box3D(x0, x0, y0 + 1, y1 - 1, z0 + 1, z1 - 1), lattice);
+        bc->addVelocityBoundary0N(Box3D(x1, x1, y0 + 1, y1 - 1, z0 + 1, z1 - 1), lattice);
+        bc->addVelocityBoundary1P(Box3D(x0 + 1, x1 - 1, y0, y0, z0 + 1, z1 - 1), lattice);
+        bc->addVelocityBoundary1N(Box3D(x0 + 1, x1 - 1, y1, y1, z0 + 1, z1 - 1), lattice);
+        bc->addVelocityBoundary2P(Box3D(x0 + 1, x1 - 1, y0 + 1, y1 - 1, z0, z0), lattice);
+        bc->addVelocityBoundary2N(Box3D(x0 + 1, x1 - 1, y0 + 1, y1 - 1, z1, z1), lattice);
+        bc->addInternalVelocityEdge0PP(Box3D(x0 + 1, x1 - 1, y0, y0, z0, z0), lattice);
+        bc->addInternalVelocityEdge0PN(Box3D(x0 + 1, x1 - 1, y0, y0, z1, z1), lattice);
+        bc->addInternalVelocityEdge0NP(Box3D(x0 + 1, x1 - 1, y1, y1, z0, z0), lattice);
+        bc->addInternalVelocityEdge0NN(Box3D(x0 + 1, x1 - 1, y1, y1, z1, z1), lattice);
+        bc->addInternalVelocityEdge1PP(Box3D(x0, x0, y0 + 1, y1 - 1, z0, z0), lattice);
+        bc->addInternalVelocityEdge1PN(Box3D(x1, x1, y0 + 1, y1 - 1, z0, z0), lattice);
+        bc->addInternalVelocityEdge1NP(Box3D(x0, x0, y0 + 1, y1 - 1, z1, z1), lattice);
+        bc->addInternalVelocityEdge1NN(Box3D(x1, x1, y0 + 1, y1 - 1, z1, z1), lattice);
+        bc->addInternalVelocityEdge2PP(Box3D(x0, x0, y0, y0, z0 + 1, z1 - 1), lattice);
+        bc->addInternalVelocityEdge2PN(Box3D(x0, x0, y1, y1, z0 + 1, z1 - 1), lattice);
+        bc->addInternalVelocityEdge2NP(Box3D(x1, x1, y0, y0, z0 + 1, z1 - 1), lattice);
+        bc->addInternalVelocityEdge2NN(Box3D(x1, x1, y1, y1, z0 + 1, z1 - 1), lattice);
+        bc->addInternalVelocityCornerPPP(x0, y0, z0, lattice); bc->addInternalVelocityCornerPPN(x0, y0, z1, lattice);
+        bc->addInternalVelocityCornerPNP(x0, y1, z0, lattice); bc->addInternalVelocityCornerPNN(x0, y1, z1, lattice);
+        bc->addInternalVelocityCornerNPP(x1, y0, z0, lattice); bc->addInternalVelocityCornerNPN(x1, y0, z1, lattice);
+        bc->addInternalVelocityCornerNNP(x1, y1, z0, lattice); bc->addInternalVelocityCornerNNN(x1, y1, z1, lattice);
+    }
     setBoundaryVelocity(lattice, lattice.getBoundingBox(), Array<T, 3>(0., 0., 0.));
     setBoundaryVelocity(lattice, Box3D(1, nx - 2, 1, ny - 2, nz - 1, nz - 1), Array<T, 3>(uMax, 0., 0.));
     initializeAtEquilibrium(lattice, lattice.getBoundingBox(), (T)1., Array<T, 3>(0., 0., 0.));

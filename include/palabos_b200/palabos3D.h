@@ -569,6 +569,21 @@ public:
     PLB_B200_CORNER(+1, -1, -1, PNN) PLB_B200_CORNER(+1, -1, +1, PNP) PLB_B200_CORNER(+1, +1, -1, PPN) PLB_B200_CORNER(+1, +1, +1, PPP)
 #undef PLB_B200_CORNER
 
+    // the concave edges and corners (boundaryCondition3D.h:123-206)
+#define PLB_B200_IEDGE(PLANE, N1, N2, SUFFIX)                                                                         \
+    void addInternalVelocityEdge##SUFFIX(Box3D domain, Lattice& lattice, boundary::BcType = boundary::dirichlet) {      \
+        detail::CBox b(domain); detail::check(plb_b200_add_internal_velocity_edge(lattice.b200Handle(), model, PLANE, N1, N2, b.v)); }
+    PLB_B200_IEDGE(0, -1, -1, 0NN) PLB_B200_IEDGE(0, -1, +1, 0NP) PLB_B200_IEDGE(0, +1, -1, 0PN) PLB_B200_IEDGE(0, +1, +1, 0PP)
+    PLB_B200_IEDGE(1, -1, -1, 1NN) PLB_B200_IEDGE(1, -1, +1, 1NP) PLB_B200_IEDGE(1, +1, -1, 1PN) PLB_B200_IEDGE(1, +1, +1, 1PP)
+    PLB_B200_IEDGE(2, -1, -1, 2NN) PLB_B200_IEDGE(2, -1, +1, 2NP) PLB_B200_IEDGE(2, +1, -1, 2PN) PLB_B200_IEDGE(2, +1, +1, 2PP)
+#undef PLB_B200_IEDGE
+#define PLB_B200_ICORNER(XN, YN, ZN, SUFFIX)                                                                                    \
+    void addInternalVelocityCorner##SUFFIX(plint x, plint y, plint z, Lattice& lattice, boundary::BcType = boundary::dirichlet) {  \
+        detail::check(plb_b200_add_internal_velocity_corner(lattice.b200Handle(), model, XN, YN, ZN, (int)x, (int)y, (int)z)); }
+    PLB_B200_ICORNER(-1, -1, -1, NNN) PLB_B200_ICORNER(-1, -1, +1, NNP) PLB_B200_ICORNER(-1, +1, -1, NPN) PLB_B200_ICORNER(-1, +1, +1, NPP)
+    PLB_B200_ICORNER(+1, -1, -1, PNN) PLB_B200_ICORNER(+1, -1, +1, PNP) PLB_B200_ICORNER(+1, +1, -1, PPN) PLB_B200_ICORNER(+1, +1, +1, PPP)
+#undef PLB_B200_ICORNER
+
     /// boundaryCondition3D.h:416-434 (three overloads), implementation boundaryCondition3D.hh:64-162
     void setVelocityConditionOnBlockBoundaries(Lattice& lattice, boundary::BcType bcType = boundary::dirichlet) {
         setVelocityConditionOnBlockBoundaries(lattice, lattice.getBoundingBox(), lattice.getBoundingBox(), bcType);

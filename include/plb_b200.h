@@ -120,6 +120,13 @@ int plb_b200_add_pressure_boundary(plb_b200_lattice* L, int model, int direction
  * boundaryCondition3D.hh:861-915 */
 int plb_b200_add_external_velocity_edge(plb_b200_lattice* L, int model, int plane, int normal1, int normal2, const int box[6]);
 int plb_b200_add_external_velocity_corner(plb_b200_lattice* L, int model, int xn, int yn, int zn, int x, int y, int z);
+/* addInternalVelocityEdge{0,1,2}{N,P}{N,P}(box, lattice) / addInternalVelocityCorner{N,P}{N,P}{N,P}(x, y, z, lattice)
+ * boundaryCondition3D.h:123-206: the CONCAVE edges and corners of a wall (a solid block inside the fluid, a backward-facing
+ * step): RegularizedVelocityInnerEdgeDynamics3D / RegularizedVelocityInnerCornerDynamics3D, regularizedBoundaryDynamics3D.hh:40-298.
+ * Normals as for the external ones (from the fluid into the solid); completed by a processor under models 0 and 1, at
+ * collision time under 2, 3 and 4, as in the reference's managers. */
+int plb_b200_add_internal_velocity_edge(plb_b200_lattice* L, int model, int plane, int normal1, int normal2, const int box[6]);
+int plb_b200_add_internal_velocity_corner(plb_b200_lattice* L, int model, int xn, int yn, int zn, int x, int y, int z);
 /* OnLatticeBoundaryCondition3D::setVelocityConditionOnBlockBoundaries(lattice, block, applicationDomain)
  * boundaryCondition3D.hh:64-162 */
 int plb_b200_set_velocity_condition_on_block_boundaries(plb_b200_lattice* L, int model, const int block[6], const int app[6]);

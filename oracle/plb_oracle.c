@@ -14,7 +14,7 @@
 #include "plb_oracle.h"
 
 #define MAX_DYN 128
-enum { BC_VEL_REG = 0, BC_RHO_REG = 1, BC_VEL_ZH = 2, BC_RHO_ZH = 3, BC_STORE_VEL = 4 };
+enum { BC_VEL_REG = 0, BC_RHO_REG = 1, BC_VEL_ZH = 2, BC_RHO_ZH = 3, BC_STORE_VEL = 4, BC_INNER_EDGE = 5, BC_INNER_CORNER = 6 };
 enum { PROC_PLANE = 0, PROC_EDGE = 1, PROC_CORNER = 2, PROC_PLANE_FD = 3 };
 typedef struct { int cls; int box[6]; int a, b, c; } Proc;
 
@@ -187,6 +187,28 @@ int plbo_add_external_velocity_corner(plbo_lattice* L, int model, int xn, int yn
     if (!box_ok(L, box)) return fail("corner outside the lattice");
     if (!add_bc(L, BC_STORE_VEL, 0, 0, box)) return 0;
     add_proc(L, PROC_CORNER, box, xn, yn, zn);
+    return 1;
+}
+
+/* addInternalVelocityEdge / Corner (boundaryInstantiator3D.h; managers boundaryCondition3D.hh:770-820 and its wrapped / Zou-He /
+ * equilibrium / interpolation counterparts): RegularizedVelocityInnerEdge/CornerDynamics3D on the cells; the wrapped managers
+ * (local, Zou-He) add the WrappedLocalBoundaryFunctional3D processor, the others leave automaticPrepareCollision on. */
+int plbo_add_internal_velocity_edge(plbo_lattice* L, int model, int plane, int n1, int n2, const int box[6]) {
+    if (!box_ok(L, box)) return fail("box outside the lattice");
+    if (plane < 0 || plane > 2 || (n1 != 1 && n1 != -1) || (n2 != 1 && n2 != -1)) return fail("bad plane / normals");
+    if (model < 0 || model > PLBO_BC_INTERP) return fail("unknown boundary condition model");
+    if (!add_bc(L, BC_INNER_EDGE, plane, (n1 > 0 ? 2 : 0) + (n2 > 0 ? 1 : 0), box)) return 0;
+    if (model >= PLBO_BC_DYNLOCAL) { if (L->prec == 8) mark_auto_f64(L->d, box); else mark_auto_f32(L->s, box); }
+    else add_proc(L, PROC_PLANE, box, 0, 0, 0);
+    return 1;
+}
+int plbo_add_internal_velocity_corner(plbo_lattice* L, int model, int xn, int yn, int zn, int x, int y, int z) {
+    int box[6] = { x, x, y, y, z, z };
+    if (!box_ok(L, box)) return fail("corner outside the lattice");
+    if (model < 0 || model > PLBO_BC_INTERP) return fail("unknown boundary condition model");
+    if (!add_bc(L, BC_INNER_CORNER, 0, (xn > 0 ? 4 : 0) + (yn > 0 ? 2 : 0) + (zn > 0 ? 1 : 0), box)) return 0;
+    if (model >= PLBO_BC_DYNLOCAL) { if (L->prec == 8) mark_auto_f64(L->d, box); else mark_auto_f32(L->s, box); }
+    else add_proc(L, PROC_PLANE, box, 0, 0, 0);
     return 1;
 }
 

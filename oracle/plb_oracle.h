@@ -43,6 +43,9 @@ int plbo_add_velocity_boundary(plbo_lattice* L, int model, int direction, int or
 int plbo_add_pressure_boundary(plbo_lattice* L, int model, int direction, int orientation, const int box[6]);
 int plbo_add_external_velocity_edge(plbo_lattice* L, int model, int plane, int normal1, int normal2, const int box[6]);
 int plbo_add_external_velocity_corner(plbo_lattice* L, int model, int xn, int yn, int zn, int x, int y, int z);
+/* addInternalVelocityEdge{0,1,2}{N,P}{N,P} / addInternalVelocityCorner{N,P}{N,P}{N,P}: the concave edges and corners */
+int plbo_add_internal_velocity_edge(plbo_lattice* L, int model, int plane, int normal1, int normal2, const int box[6]);
+int plbo_add_internal_velocity_corner(plbo_lattice* L, int model, int xn, int yn, int zn, int x, int y, int z);
 int plbo_set_velocity_condition_on_block_boundaries(plbo_lattice* L, int model, const int block[6], const int app[6]);
 int plbo_set_boundary_velocity(plbo_lattice* L, const int box[6], const double u[3]);
 int plbo_set_boundary_density(plbo_lattice* L, const int box[6], double rho);

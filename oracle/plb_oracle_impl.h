@@ -588,6 +588,48 @@ static void SFX(plane_rhoBar_j)(const SFX(Lat)* L, const SFX(Bc)* b, const REAL*
     }
 }
 
+/* RegularizedVelocityInnerEdgeDynamics3D<plane,normal1,normal2> / RegularizedVelocityInnerCornerDynamics3D<xN,yN,zN>
+ * (boundaryCondition/regularizedBoundaryDynamics3D.h:40-140, .hh:40-298): composites of two / three velocity-Dirichlet plane
+ * dynamics that share the stored velocity.  Bc encoding: edge  dir = plane, ori = 2*(normal1 > 0) + (normal2 > 0), with
+ * direction1 = (plane+1)%3, direction2 = (plane+2)%3;  corner  ori = 4*(xN > 0) + 2*(yN > 0) + (zN > 0). */
+static int SFX(inner_parts)(const SFX(Bc)* b, SFX(Bc) part[3]) {
+    int n, k;
+    if (b->kind == BC_INNER_EDGE) {
+        n = 2;
+        part[0] = *b; part[0].kind = BC_VEL_REG; part[0].dir = (b->dir + 1) % 3; part[0].ori = (b->ori & 2) ? 1 : -1;
+        part[1] = *b; part[1].kind = BC_VEL_REG; part[1].dir = (b->dir + 2) % 3; part[1].ori = (b->ori & 1) ? 1 : -1;
+    } else {
+        n = 3;
+        for (k = 0; k < 3; ++k) { part[k] = *b; part[k].kind = BC_VEL_REG; part[k].dir = k; part[k].ori = (b->ori & (4 >> k)) ? 1 : -1; }
+    }
+    return n;
+}
+/* computeRhoBar: (rhoBar1 + rhoBar2) / 2, (x + y + z) / 3   regularizedBoundaryDynamics3D.hh:95-101, :237-245 */
+static REAL SFX(inner_rhoBar)(const SFX(Lat)* L, const SFX(Bc)* b, const REAL* f, int velIsJ) {
+    SFX(Bc) part[3];
+    int n = SFX(inner_parts)(b, part);
+    if (n == 2) return (SFX(veldir_rhoBar)(L, &part[0], f, velIsJ) + SFX(veldir_rhoBar)(L, &part[1], f, velIsJ) ) / (REAL)2;
+    return (SFX(veldir_rhoBar)(L, &part[0], f, velIsJ) +
+            SFX(veldir_rhoBar)(L, &part[1], f, velIsJ) +
+            SFX(veldir_rhoBar)(L, &part[2], f, velIsJ)) / (REAL)3;
+}
+/* computeDensity: the mean of the parts' densities  :86-92, :225-234 */
+static REAL SFX(inner_density)(const SFX(Lat)* L, const SFX(Bc)* b, const REAL* f, int velIsJ) {
+    SFX(Bc) part[3];
+    int n = SFX(inner_parts)(b, part);
+    if (n == 2) return (FULLRHO(SFX(veldir_rhoBar)(L, &part[0], f, velIsJ)) + FULLRHO(SFX(veldir_rhoBar)(L, &part[1], f, velIsJ)) ) / (REAL)2;
+    return (FULLRHO(SFX(veldir_rhoBar)(L, &part[0], f, velIsJ)) +
+            FULLRHO(SFX(veldir_rhoBar)(L, &part[1], f, velIsJ)) +
+            FULLRHO(SFX(veldir_rhoBar)(L, &part[2], f, velIsJ))) / (REAL)3;
+}
+/* computeRhoBarJ: rhoBar as above, j = velocity (of the first part: all parts store the same), times rho unless velIsJ  :104-116, :248-260 */
+static void SFX(inner_rhoBar_j)(const SFX(Lat)* L, const SFX(Bc)* b, const REAL* f, REAL* rhoBar, REAL j[3], int velIsJ) {
+    REAL rho; int d;
+    *rhoBar = SFX(inner_rhoBar)(L, b, f, velIsJ);
+    rho = FULLRHO(*rhoBar);
+    for (d = 0; d < 3; ++d) { j[d] = b->u[d]; if (!velIsJ) j[d] *= rho; }
+}
+
 /* boundaryTemplates<..>::compute_PiNeq boundaryCondition/boundaryTemplates.h:45-87 */
 static void SFX(boundary_PiNeq)(const SFX(Lat)* L, const SFX(Dyn)* base, const SFX(Bc)* b, const REAL* f,
                                 REAL rhoBar, const REAL j[3], REAL jSqr, REAL PiNeq[6])
@@ -656,6 +698,34 @@ static void SFX(complete_populations)(const SFX(Lat)* L, const SFX(Dyn)* base, c
         SFX(regularize)(L, base, f, rhoBar, j, jSqr, PiNeq);
     } else if (b->kind == BC_VEL_ZH || b->kind == BC_RHO_ZH) {
         SFX(zouhe_closure)(L, base, b, f);
+    } else if (b->kind == BC_INNER_EDGE || b->kind == BC_INNER_CORNER) {
+        /* regularizedBoundaryDynamics3D.hh:138-162 (edge), :276-298 (corner): bounce-back of off-equilibrium on the unknown
+         * populations -- those that leave the solid along both (all three) normals --, then regularize ALL populations with
+         * the base dynamics' PiNeq of the cell (IsoThermalBulkDynamics::computePiNeq isoThermalDynamics.hh:78-85: moments of
+         * the populations themselves) around the boundary's own rhoBar and j */
+        SFX(Bc) part[3];
+        REAL rhoBar, j[3], jSqr, cellRhoBar, cellJ[3], PiNeq[6];
+        int n = SFX(inner_parts)(b, part), i, k;
+        SFX(inner_rhoBar_j)(L, b, f, &rhoBar, j, VEL_IS_J(base));
+        jSqr = j[0]*j[0] + j[1]*j[1] + j[2]*j[2];
+        for (i = 0; i < L->q; ++i) {
+            int unknown = 1;
+            for (k = 0; k < n; ++k) if (L->c[i][part[k].dir] != -part[k].ori) unknown = 0;
+            if (unknown) {
+                int h = (L->q - 1) / 2;
+                int opp = (i == 0) ? 0 : (i <= h ? i + h : i - h);
+                f[i] = f[opp]
+                    - SFX(computeEquilibrium)(L, base, opp, rhoBar, j, jSqr)
+                    + SFX(computeEquilibrium)(L, base, i, rhoBar, j, jSqr);
+            }
+        }
+        if (base->type == PLBO_DYN_BOUNCEBACK || base->type == PLBO_DYN_NODYNAMICS) {
+            for (i = 0; i < 6; ++i) PiNeq[i] = (REAL)0;            /* core/dynamics.hh:837-842, :1017-1022 */
+        } else {
+            SFX(get_rhoBar_j)(L->q, f, &cellRhoBar, cellJ);
+            SFX(compute_PiNeq)(L->q, f, L->cs2, cellRhoBar, cellJ, PiNeq);
+        }
+        SFX(regularize)(L, base, f, rhoBar, j, jSqr, PiNeq);
     }
     /* BC_STORE_VEL: StoreVelocityDynamics inherits the empty completePopulations
      * (boundaryDynamics.hh:185-187) */
@@ -679,6 +749,7 @@ static REAL SFX(cell_density)(const SFX(Lat)* L, size_t cell) {
         const SFX(Bc)* b = &L->bcs[bi];
         if (b->kind == BC_VEL_REG || b->kind == BC_VEL_ZH) return FULLRHO(SFX(veldir_rhoBar)(L, b, f, VEL_IS_J(d)));
         if (b->kind == BC_RHO_REG || b->kind == BC_RHO_ZH) return FULLRHO(b->rhoBar);
+        if (b->kind == BC_INNER_EDGE || b->kind == BC_INNER_CORNER) return SFX(inner_density)(L, b, f, VEL_IS_J(d));
     }
     if (d->type == PLBO_DYN_BOUNCEBACK || d->type == PLBO_DYN_NODYNAMICS) return d->rho;
     return FULLRHO(SFX(get_rhoBar)(L->q, f));
@@ -731,6 +802,7 @@ static REAL SFX(cell_rhoBar)(const SFX(Lat)* L, size_t cell) {
         const SFX(Bc)* b = &L->bcs[bi];
         if (b->kind == BC_VEL_REG || b->kind == BC_VEL_ZH) return SFX(veldir_rhoBar)(L, b, f, VEL_IS_J(d));
         if (b->kind == BC_RHO_REG || b->kind == BC_RHO_ZH) return b->rhoBar;
+        if (b->kind == BC_INNER_EDGE || b->kind == BC_INNER_CORNER) return SFX(inner_rhoBar)(L, b, f, VEL_IS_J(d));
         { REAL rho = SFX(cell_density)(L, cell); return RHOBAR(rho); }
     }
     if (d->type == PLBO_DYN_BOUNCEBACK || d->type == PLBO_DYN_NODYNAMICS) return RHOBAR(d->rho);
@@ -752,6 +824,8 @@ static void SFX(cell_rhoBar_j)(const SFX(Lat)* L, size_t cell, REAL* rhoBar, REA
             REAL rho = SFX(cell_density)(L, cell);
             *rhoBar = RHOBAR(rho);
             for (k = 0; k < 3; ++k) j[k] = rho * (b->u[k] - 0.5*(REAL)0);
+        } else if (b->kind == BC_INNER_EDGE || b->kind == BC_INNER_CORNER) {
+            SFX(inner_rhoBar_j)(L, b, f, rhoBar, j, VEL_IS_J(d));
         } else {
             SFX(plane_rhoBar_j)(L, b, f, rhoBar, j, VEL_IS_J(d));
         }

@@ -31,7 +31,8 @@ SYMBOLS = [
     "plb_b200_set_stream", "plb_b200_set_periodicity", "plb_b200_toggle_internal_statistics",
     "plb_b200_define_dynamics_box", "plb_b200_define_dynamics_mask", "plb_b200_add_velocity_boundary",
     "plb_b200_add_pressure_boundary", "plb_b200_add_external_velocity_edge",
-    "plb_b200_add_external_velocity_corner", "plb_b200_set_velocity_condition_on_block_boundaries",
+    "plb_b200_add_external_velocity_corner", "plb_b200_add_internal_velocity_edge", "plb_b200_add_internal_velocity_corner",
+    "plb_b200_set_velocity_condition_on_block_boundaries",
     "plb_b200_set_boundary_velocity", "plb_b200_set_boundary_density", "plb_b200_initialize_at_equilibrium",
     "plb_b200_initialize_at_equilibrium_field", "plb_b200_initialize", "plb_b200_upload", "plb_b200_download",
     "plb_b200_local_bytes", "plb_b200_collide_and_stream", "plb_b200_synchronize",
@@ -96,6 +97,8 @@ def lib():
         L.plb_b200_add_pressure_boundary.argtypes = [vp, ci, ci, ci, vp]
         L.plb_b200_add_external_velocity_edge.argtypes = [vp, ci, ci, ci, ci, vp]
         L.plb_b200_add_external_velocity_corner.argtypes = [vp] + [ci] * 7
+        L.plb_b200_add_internal_velocity_edge.argtypes = [vp, ci, ci, ci, ci, vp]
+        L.plb_b200_add_internal_velocity_corner.argtypes = [vp] + [ci] * 7
         L.plb_b200_set_velocity_condition_on_block_boundaries.argtypes = [vp, ci, vp, vp]
         L.plb_b200_set_boundary_velocity.argtypes = [vp, vp, vp]
         L.plb_b200_set_boundary_density.argtypes = [vp, vp, cd]
@@ -267,6 +270,12 @@ class Lattice:
 
     def add_external_velocity_corner(self, model, xn, yn, zn, x, y, z):
         self._ck(self.lib.plb_b200_add_external_velocity_corner(self.h, BC[model], xn, yn, zn, x, y, z))
+
+    def add_internal_velocity_edge(self, model, plane, n1, n2, box):
+        self._ck(self.lib.plb_b200_add_internal_velocity_edge(self.h, BC[model], plane, n1, n2, _box(box)))
+
+    def add_internal_velocity_corner(self, model, xn, yn, zn, x, y, z):
+        self._ck(self.lib.plb_b200_add_internal_velocity_corner(self.h, BC[model], xn, yn, zn, x, y, z))
 
     def set_boundary_velocity(self, box, u):
         self._ck(self.lib.plb_b200_set_boundary_velocity(self.h, _box(box), _vec(u)))

@@ -488,6 +488,12 @@ int plb_b200_add_external_velocity_edge(plb_b200_lattice* L, int model, int plan
 int plb_b200_add_external_velocity_corner(plb_b200_lattice* L, int model, int xn, int yn, int zn, int x, int y, int z) {
     PLB_TRY(L, L->impl->add_external_velocity_corner(model, xn, yn, zn, x + L->off[0], y + L->off[1], z + L->off[2]))
 }
+int plb_b200_add_internal_velocity_edge(plb_b200_lattice* L, int model, int plane, int n1, int n2, const int box[6]) {
+    PLB_TRY(L, L->impl->add_internal_velocity_edge(model, plane, n1, n2, SBox(L, box)))
+}
+int plb_b200_add_internal_velocity_corner(plb_b200_lattice* L, int model, int xn, int yn, int zn, int x, int y, int z) {
+    PLB_TRY(L, L->impl->add_internal_velocity_corner(model, xn, yn, zn, x + L->off[0], y + L->off[1], z + L->off[2]))
+}
 int plb_b200_set_velocity_condition_on_block_boundaries(plb_b200_lattice* L, int model, const int block[6], const int app[6]) {
     PLB_TRY(L, L->impl->set_velocity_condition_on_block_boundaries(model, SBox(L, block), SBox(L, app)))
 }

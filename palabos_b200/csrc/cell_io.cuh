@@ -346,8 +346,15 @@ __device__ __forceinline__ void complete_by_face_as(int baseType, Bc<T> b, T* f)
     default: b.dir = 2; b.ori = +1; L::template complete_populations<INC>(baseType, b, f); break;
     }
 }
+/// the concave edges and corners out of line: rare, and their loops over the composing planes are run-time
+template <class T, int Q>
+__device__ __noinline__ void complete_inner_cell(int baseType, const Bc<T>& b, T* f) {
+    if (baseType == DYN_INCBGK) LB<T, Q>::template complete_inner<true>(baseType, b, f);
+    else LB<T, Q>::template complete_inner<false>(baseType, b, f);
+}
 template <class T, int Q>
 __device__ __forceinline__ void complete_by_face(int baseType, const Bc<T>& b, T* f) {
+    if (LB<T, Q>::is_inner(b.kind)) { complete_inner_cell<T, Q>(baseType, b, f); return; }
     // IncBGK as base dynamics (velIsJ, invRho0) is its own instantiation: the usual one stays as lean as it was
     if (baseType == DYN_INCBGK) complete_by_face_as<T, Q, true>(baseType, b, f);
     else complete_by_face_as<T, Q, false>(baseType, b, f);

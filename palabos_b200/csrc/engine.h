@@ -41,6 +41,8 @@ public:
     virtual void add_pressure_boundary(int model, int dir, int ori, const int box[6]) = 0;
     virtual void add_external_velocity_edge(int model, int plane, int n1, int n2, const int box[6]) = 0;
     virtual void add_external_velocity_corner(int model, int xn, int yn, int zn, int x, int y, int z) = 0;
+    virtual void add_internal_velocity_edge(int model, int plane, int n1, int n2, const int box[6]) = 0;
+    virtual void add_internal_velocity_corner(int model, int xn, int yn, int zn, int x, int y, int z) = 0;
     virtual void set_velocity_condition_on_block_boundaries(int model, const int block[6], const int app[6]) = 0;
     virtual void set_boundary_velocity(const int box[6], const double u[3]) = 0;
     virtual void set_boundary_density(const int box[6], double rho) = 0;

@@ -322,6 +322,31 @@ public:
         add_proc(PROC_CORNER, box, xn, yn, zn);
     }
 
+    /// addInternalVelocityEdge / Corner (the concave ones): RegularizedVelocityInnerEdge/CornerDynamics3D on the cells
+    /// (regularizedBoundaryDynamics3D.hh:40-298); the wrapped managers (local, Zou-He) add WrappedLocalBoundaryFunctional3D -- a
+    /// plane item here --, all others leave automaticPrepareCollision on (boundaryCondition3D.hh:770-820, 883-935, 998-1046, 1109-1157)
+    int inner_auto(int model) {
+        if (model < 0 || model > 4) throw PlbError("unknown boundary condition model");
+        if (model >= 2 && ext_) throw PlbError("dynamics-based boundary conditions are not available with the external-moment sweep");
+        if (model >= 2) autoPlanes_ = true;
+        return model >= 2 ? 1 : 0;
+    }
+    void add_internal_velocity_edge(int model, int plane, int n1, int n2, const int box[6]) override {
+        check_box(box);
+        if (plane < 0 || plane > 2 || (n1 != 1 && n1 != -1) || (n2 != 1 && n2 != -1)) throw PlbError("bad edge plane/normals");
+        const int autoPrep = inner_auto(model);
+        add_bc(BC_INNER_EDGE, plane, (n1 > 0 ? 2 : 0) + (n2 > 0 ? 1 : 0), box);
+        add_proc(PROC_PLANE, box, autoPrep, 0, 0);
+    }
+    void add_internal_velocity_corner(int model, int xn, int yn, int zn, int x, int y, int z) override {
+        const int box[6] = {x, x, y, y, z, z};
+        check_box(box);
+        if ((xn != 1 && xn != -1) || (yn != 1 && yn != -1) || (zn != 1 && zn != -1)) throw PlbError("bad corner normals");
+        const int autoPrep = inner_auto(model);
+        add_bc(BC_INNER_CORNER, 0, (xn > 0 ? 4 : 0) + (yn > 0 ? 2 : 0) + (zn > 0 ? 1 : 0), box);
+        add_proc(PROC_PLANE, box, autoPrep, 0, 0);
+    }
+
     /// OnLatticeBoundaryCondition3D::setVelocityConditionOnBlockBoundaries boundaryCondition3D.hh:64-162
     /// with BlockSurface3D(block, 1) (core/blockSurface3D.cpp:38-200): 6 faces, 12 edges, 8 corners, in that order.
     void set_velocity_condition_on_block_boundaries(int model, const int d[6], const int app[6]) override {

@@ -18,7 +18,10 @@ enum DynType : int { DYN_BGK = 0, DYN_RLB = 1, DYN_TRT = 2, DYN_SMAGO = 3, DYN_B
 constexpr int DYN_EXTERNAL = 100;
 /// ... and the form that takes them from the fields only where they are not a function of the cell's own populations
 constexpr int DYN_EXTERNAL_FUSED = 101;
-enum BcKind : int { BC_VEL_REG = 0, BC_RHO_REG = 1, BC_VEL_ZH = 2, BC_RHO_ZH = 3, BC_STORE_VEL = 4 };
+/// BC_INNER_EDGE / BC_INNER_CORNER: RegularizedVelocityInnerEdgeDynamics3D<plane,normal1,normal2> / ...InnerCornerDynamics3D<xN,yN,zN>
+/// (boundaryCondition/regularizedBoundaryDynamics3D.h:40-140).  Record encoding: edge  dir = plane, ori = 2*(normal1 > 0) + (normal2 > 0),
+/// with direction1 = (plane+1)%3, direction2 = (plane+2)%3;  corner  ori = 4*(xN > 0) + 2*(yN > 0) + (zN > 0).
+enum BcKind : int { BC_VEL_REG = 0, BC_RHO_REG = 1, BC_VEL_ZH = 2, BC_RHO_ZH = 3, BC_STORE_VEL = 4, BC_INNER_EDGE = 5, BC_INNER_CORNER = 6 };
 enum ProcClass : int { PROC_PLANE = 0, PROC_EDGE = 1, PROC_CORNER = 2, PROC_PLANE_FD = 3 };
 
 /// One entry of the per-lattice dynamics table (a cell stores the 1-byte index of its entry).
@@ -646,6 +649,69 @@ struct LB {
         }
     }
 
+    // ------------------------------------------------- concave (internal) edges and corners
+
+    PLB_HD static bool is_inner(int kind) { return kind == BC_INNER_EDGE || kind == BC_INNER_CORNER; }
+    /// the velocity-Dirichlet plane dynamics an inner edge (two) or corner (three) is composed of; all share the stored velocity
+    PLB_HD static int inner_parts(const Bc<T>& b, Bc<T> part[3]) {
+        if (b.kind == BC_INNER_EDGE) {
+            part[0] = b; part[0].kind = BC_VEL_REG; part[0].dir = (b.dir + 1) % 3; part[0].ori = (b.ori & 2) ? 1 : -1;
+            part[1] = b; part[1].kind = BC_VEL_REG; part[1].dir = (b.dir + 2) % 3; part[1].ori = (b.ori & 1) ? 1 : -1;
+            part[2] = part[1];
+            return 2;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { part[k] = b; part[k].kind = BC_VEL_REG; part[k].dir = k; part[k].ori = (b.ori & (4 >> k)) ? 1 : -1; }
+        return 3;
+    }
+    /// computeRhoBar regularizedBoundaryDynamics3D.hh:95-101 (edge), :237-245 (corner)
+    PLB_HD static T inner_rhoBar(const Bc<T>& b, const T* f, bool velIsJ) {
+        Bc<T> part[3];
+        if (inner_parts(b, part) == 2) return (veldir_rhoBar(part[0], f, velIsJ) + veldir_rhoBar(part[1], f, velIsJ)) / (T)2;
+        return (veldir_rhoBar(part[0], f, velIsJ) + veldir_rhoBar(part[1], f, velIsJ) + veldir_rhoBar(part[2], f, velIsJ)) / (T)3;
+    }
+    /// computeDensity :86-92, :225-234: the mean of the parts' densities
+    PLB_HD static T inner_density(const Bc<T>& b, const T* f, bool velIsJ) {
+        Bc<T> part[3];
+        if (inner_parts(b, part) == 2) return (fullRho(veldir_rhoBar(part[0], f, velIsJ)) + fullRho(veldir_rhoBar(part[1], f, velIsJ))) / (T)2;
+        return (fullRho(veldir_rhoBar(part[0], f, velIsJ)) + fullRho(veldir_rhoBar(part[1], f, velIsJ)) + fullRho(veldir_rhoBar(part[2], f, velIsJ))) / (T)3;
+    }
+    /// computeRhoBarJ :104-116, :248-260: j = stored velocity, times rho unless velIsJ
+    PLB_HD static void inner_rhoBar_j(const Bc<T>& b, const T* f, T& rhoBar, T j[3], bool velIsJ) {
+        rhoBar = inner_rhoBar(b, f, velIsJ);
+        const T rho = fullRho(rhoBar);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { j[d] = b.u[d]; if (!velIsJ) j[d] *= rho; }
+    }
+    /// completePopulations :138-162 (edge), :276-298 (corner): bounce-back of off-equilibrium on the populations that leave the solid
+    /// along both (all three) normals, then regularize ALL populations with the base dynamics' PiNeq of the cell
+    /// (IsoThermalBulkDynamics::computePiNeq isoThermalDynamics.hh:78-85) around the boundary's own rhoBar and j
+    template <bool INC>
+    PLB_HD static void complete_inner(int baseType, const Bc<T>& b, T* f) {
+        Bc<T> part[3];
+        const int n = inner_parts(b, part);
+        T rhoBar, j[3], PiNeq[6];
+        inner_rhoBar_j(b, f, rhoBar, j, INC);
+        const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            bool unknown = cdir(i, part[0].dir) == -part[0].ori && cdir(i, part[1].dir) == -part[1].ori;
+            if (n == 3) unknown = unknown && cdir(i, part[2].dir) == -part[2].ori;
+            if (unknown)
+                f[i] = f[opp(i)] - computeEquilibriumT<INC>(baseType, opp(i), rhoBar, j, jSqr)
+                                 + computeEquilibriumT<INC>(baseType, i, rhoBar, j, jSqr);
+        }
+        if (is_inert(baseType)) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) PiNeq[k] = (T)0;           // core/dynamics.hh:837-842, :1017-1022
+        } else {
+            T cellRhoBar, cellJ[3];
+            get_rhoBar_j(f, cellRhoBar, cellJ);
+            compute_PiNeq(f, cellRhoBar, cellJ, PiNeq);
+        }
+        regularizeT<INC>(baseType, f, rhoBar, j, jSqr, PiNeq);
+    }
+
     /// boundaryTemplates<..>::compute_PiNeq boundaryCondition/boundaryTemplates.h:45-87
     template <bool INC>
     PLB_HD static void boundary_PiNeq(int baseType, const Bc<T>& b, const T* f, T rhoBar, const T j[3], T jSqr, T PiNeq[6]) {
@@ -724,6 +790,8 @@ struct LB {
             regularizeT<INC>(baseType, f, rhoBar, j, jSqr, PiNeq);
         } else if (b.kind == BC_VEL_ZH || b.kind == BC_RHO_ZH) {
             zouhe_closure<INC>(baseType, b, f);
+        } else if (is_inner(b.kind)) {
+            complete_inner<INC>(baseType, b, f);
         }
     }
 
@@ -737,6 +805,7 @@ struct LB {
         if (hasBc) {
             if (is_vel_plane(b.kind)) return fullRho(veldir_rhoBar(b, f, vel_is_j(d.type)));
             if (is_rho_plane(b.kind)) return fullRho(b.rhoBar);
+            if (is_inner(b.kind)) return inner_density(b, f, vel_is_j(d.type));
         }
         if (is_inert(d.type)) return d.rho;
         return fullRho(get_rhoBar(f));
@@ -744,7 +813,7 @@ struct LB {
     /// True when cell_density needs the populations of the cell.
     PLB_HD static bool density_reads_pops(int dynType, bool hasBc, int bcKind) {
         if (hasBc) {
-            if (is_vel_plane(bcKind)) return true;
+            if (is_vel_plane(bcKind) || is_inner(bcKind)) return true;
             if (is_rho_plane(bcKind)) return false;
         }
         return !is_inert(dynType);
@@ -787,6 +856,7 @@ struct LB {
         if (hasBc) {
             if (is_vel_plane(b.kind)) return veldir_rhoBar(b, f, vel_is_j(d.type));
             if (is_rho_plane(b.kind)) return b.rhoBar;
+            if (is_inner(b.kind)) return inner_rhoBar(b, f, vel_is_j(d.type));
             return rhoBarOf(cell_density(d, hasBc, b, f));
         }
         if (is_inert(d.type)) return rhoBarOf(d.rho);
@@ -804,6 +874,8 @@ struct LB {
                 rhoBar = rhoBarOf(rho);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) j[k] = rho * (b.u[k] - 0.5 * (T)0);
+            } else if (is_inner(b.kind)) {
+                inner_rhoBar_j(b, f, rhoBar, j, vel_is_j(d.type));
             } else {
                 plane_rhoBar_j(b, f, rhoBar, j, vel_is_j(d.type));
             }

@@ -338,6 +338,49 @@ def cavity_eraser(nx, ny, nz, steps, model="local", q=19, prec="f64"):
 
 
 # name -> (builder, how to store the reference outcome: "full" dumps, or "probe" = sha256 + sampled cells)
+def cavity_block(nx, ny, nz, steps, model="local", dyn="BGK", q=19, prec="f64", outer="local", u_block=(0.0, 0.0, 0.0)):
+    """Lid-driven cavity with a solid block inside: the block's faces are velocity planes seen from the fluid around it, its
+    twelve edges and eight corners are the CONCAVE (internal) edges and corners of the boundary condition
+    (addInternalVelocityEdge* / addInternalVelocityCorner*, RegularizedVelocityInnerEdge/CornerDynamics3D), its inside is
+    BounceBack.  Normals point from the fluid into the solid, as for every wall."""
+    u_max, re = 0.02, 100.0
+    omega = 1.0 / (3 * u_max * ny / re + 0.5)
+    sc = Scenario(q, prec, nx, ny, nz, dyn, omega, 0.14 if dyn == "SMAGO" else 0.0)
+    sc.bc_box(outer)
+    x0, x1, y0, y1, z0, z1 = nx // 3, nx // 3 + 3, ny // 3, ny // 3 + 3, nz // 3, nz // 3 + 2
+    lo, hi = (x0, y0, z0), (x1, y1, z1)
+    sc.dynamics((x0 + 1, x1 - 1, y0 + 1, y1 - 1, z0 + 1, z1 - 1), "BB", 1.0)
+    for d in range(3):                                   # faces: the block's low face has its solid at +d, i.e. orientation +1
+        for ori, at in ((+1, lo[d]), (-1, hi[d])):
+            b = [lo[0] + 1, hi[0] - 1, lo[1] + 1, hi[1] - 1, lo[2] + 1, hi[2] - 1]
+            b[2 * d] = b[2 * d + 1] = at
+            sc.bc_vel(model, d, ori, tuple(b))
+    for plane in range(3):                               # edges parallel to `plane`: normals along (plane+1)%3 and (plane+2)%3
+        d1, d2 = (plane + 1) % 3, (plane + 2) % 3
+        for n1, a1 in ((+1, lo[d1]), (-1, hi[d1])):
+            for n2, a2 in ((+1, lo[d2]), (-1, hi[d2])):
+                b = [0] * 6
+                b[2 * plane], b[2 * plane + 1] = lo[plane] + 1, hi[plane] - 1
+                b[2 * d1] = b[2 * d1 + 1] = a1
+                b[2 * d2] = b[2 * d2 + 1] = a2
+                sc.bc_iedge(model, plane, n1, n2, tuple(b))
+    for xn, x in ((+1, x0), (-1, x1)):
+        for yn, y in ((+1, y0), (-1, y1)):
+            for zn, z in ((+1, z0), (-1, z1)):
+                sc.bc_icorner(model, xn, yn, zn, x, y, z)
+    sc.set_velocity(sc.box, (0, 0, 0))
+    sc.set_velocity((1, nx - 2, 1, ny - 2, nz - 1, nz - 1), (u_max, 0, 0))
+    sc.set_velocity((x0, x1, y0, y1, z0, z1), u_block)
+    sc.init_eq(sc.box, 1.0, (0, 0, 0))
+    sc.initialize()
+    sc.dump("f_init")
+    sc.run(steps // 2).stats()
+    sc.set_velocity((x0, x1, y0, y1, z0, z1), tuple(0.5 * v for v in u_block))
+    sc.run(steps - steps // 2).stats()
+    sc.dump("f_end").dump_rho_u("rho_u_end")
+    return sc
+
+
 CASES = {
     # configs[0]-style cavity, all dynamics on the path
     "cavity_bgk_10x9x8":        (lambda: cavity(10, 9, 8, 60, every=20), "full"),
@@ -347,6 +390,12 @@ CASES = {
     "cavity_bgk_f32_10x9x8":    (lambda: cavity(10, 9, 8, 40, prec="f32"), "full"),
     "cavity_bgk_q27_8x8x9":     (lambda: cavity(8, 8, 9, 30, q=27), "full"),
     "cavity_zouhe_10x9x8":      (lambda: cavity(10, 9, 8, 40, model="zouhe"), "full"),
+    # concave (internal) edges and corners: a solid block inside the cavity
+    "block_local_13x12x11":     (lambda: cavity_block(13, 12, 11, 30, u_block=(0.004, -0.002, 0.003)), "full"),
+    "block_local_q27_12x12x11": (lambda: cavity_block(12, 12, 11, 24, q=27, u_block=(0.003, 0.002, -0.002)), "full"),
+    "block_zouhe_f32_13x11x12": (lambda: cavity_block(13, 11, 12, 24, model="zouhe", outer="zouhe", prec="f32"), "full"),
+    "block_dynlocal_rlb_12x12x12": (lambda: cavity_block(12, 12, 12, 24, model="dynlocal", dyn="RLB", u_block=(0.0, 0.003, 0.0)), "full"),
+    "block_incbgk_12x13x11":    (lambda: cavity_block(12, 13, 11, 24, dyn="INCBGK", u_block=(0.002, 0.0, 0.001)), "full"),
     # the reference's own known-answer sizes (test_cylinder.py:85-97), 30 steps
     "cavity_bgk_20":            (lambda: cavity(20, 20, 20, 30), "probe"),
     "cavity_bgk_39":            (lambda: cavity(39, 39, 39, 30), "probe"),

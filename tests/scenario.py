@@ -82,6 +82,13 @@ class Scenario:
     def bc_corner(self, model, xn, yn, zn, x, y, z):
         return self._add("bc_corner", model, xn, yn, zn, x, y, z)
 
+    def bc_iedge(self, model, plane, n1, n2, box):
+        """addInternalVelocityEdge<plane><n1><n2>: a concave edge"""
+        return self._add("bc_iedge", model, plane, n1, n2, tuple(box))
+
+    def bc_icorner(self, model, xn, yn, zn, x, y, z):
+        return self._add("bc_icorner", model, xn, yn, zn, x, y, z)
+
     def set_velocity(self, box, u):
         return self._add("set_velocity", tuple(box), tuple(float(v) for v in u))
 
@@ -185,6 +192,10 @@ def run_reference(sc: Scenario, timed_steps=None):
                 lines.append("bc_edge %s %d %d %d %s" % (op[1], op[2], op[3], op[4], fmt(op[5])))
             elif k == "bc_corner":
                 lines.append("bc_corner %s %s" % (op[1], fmt(op[2:])))
+            elif k == "bc_iedge":
+                lines.append("bc_iedge %s %d %d %d %s" % (op[1], op[2], op[3], op[4], fmt(op[5])))
+            elif k == "bc_icorner":
+                lines.append("bc_icorner %s %s" % (op[1], fmt(op[2:])))
             elif k == "set_velocity":
                 lines.append("set_velocity %s %s" % (fmt(op[1]), fmt(op[2])))
             elif k == "set_density":
@@ -328,6 +339,12 @@ class OracleEngine:
     def add_external_velocity_corner(self, model, xn, yn, zn, x, y, z):
         self._ck(self.lib.plbo_add_external_velocity_corner(self.h, BC[model], xn, yn, zn, x, y, z))
 
+    def add_internal_velocity_edge(self, model, plane, n1, n2, box):
+        self._ck(self.lib.plbo_add_internal_velocity_edge(self.h, BC[model], plane, n1, n2, _box(box)))
+
+    def add_internal_velocity_corner(self, model, xn, yn, zn, x, y, z):
+        self._ck(self.lib.plbo_add_internal_velocity_corner(self.h, BC[model], xn, yn, zn, x, y, z))
+
     def set_boundary_velocity(self, box, u):
         self._ck(self.lib.plbo_set_boundary_velocity(self.h, _box(box), _vec(u)))
 
@@ -441,6 +458,10 @@ def replay(sc: Scenario, engine):
             engine.add_external_velocity_edge(op[1], op[2], op[3], op[4], op[5])
         elif k == "bc_corner":
             engine.add_external_velocity_corner(*op[1:])
+        elif k == "bc_iedge":
+            engine.add_internal_velocity_edge(op[1], op[2], op[3], op[4], op[5])
+        elif k == "bc_icorner":
+            engine.add_internal_velocity_corner(*op[1:])
         elif k == "set_velocity":
             engine.set_boundary_velocity(op[1], op[2])
         elif k == "set_density":
@@ -533,6 +554,12 @@ class EnvelopedOracle:
 
     def add_external_velocity_corner(self, model, xn, yn, zn, x, y, z):
         self.inner.add_external_velocity_corner(model, xn, yn, zn, x + self.off[0], y + self.off[1], z + self.off[2])
+
+    def add_internal_velocity_edge(self, model, plane, n1, n2, box):
+        self.inner.add_internal_velocity_edge(model, plane, n1, n2, self._b(box))
+
+    def add_internal_velocity_corner(self, model, xn, yn, zn, x, y, z):
+        self.inner.add_internal_velocity_corner(model, xn, yn, zn, x + self.off[0], y + self.off[1], z + self.off[2])
 
     def set_boundary_velocity(self, box, u):
         self.inner.set_boundary_velocity(self._b(box), u)

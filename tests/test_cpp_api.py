@@ -52,6 +52,22 @@ def test_cavity3d_cpp_matches_oracle(shape, q):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("q", [19, 27])
+def test_cavity3d_cpp_with_a_block_matches_oracle(q):
+    """CAVITY3D_BLOCK=1: a solid block in the cavity through the mirror's addVelocityBoundary* / addInternalVelocityEdge* /
+    addInternalVelocityCorner* (the concave edges and corners)"""
+    from cases import cavity_block
+    nx, ny, nz = 13, 12, 11
+    with tempfile.TemporaryDirectory() as tmp:
+        dump = os.path.join(tmp, "f.bin")
+        subprocess.run([_exe("cavity3d"), str(nx), str(ny), str(nz), "30", dump] + (["D3Q27"] if q == 27 else []),
+                       check=True, capture_output=True, text=True, env=dict(os.environ, CAVITY3D_BLOCK="1"))
+        got = np.fromfile(dump, dtype=np.float64).reshape(nx, ny, nz, q)
+    want = run_oracle(cavity_block(nx, ny, nz, 30, q=q))
+    assert np.array_equal(got, want["f_end"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("model,prec", [("trt", "f64"), ("smago27", "f32"), ("incbgk", "f64")])
 def test_channel3d_cpp_matches_oracle(model, prec):
     out = subprocess.run([_exe("channel3d"), "16", "12", "10", "40", model, prec], check=True, capture_output=True, text=True).stdout

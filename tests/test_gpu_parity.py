@@ -109,6 +109,8 @@ SLAB_CASES = {
     "cavity_interp_10x9x8": 3,
     "cavity_eraser_10x9x8": 3,
     "cavity_eraser_zouhe_q27": 2,
+    "block_local_13x12x11": 2,
+    "block_dynlocal_rlb_12x12x12": 3,
 }
 
 
