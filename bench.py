@@ -185,6 +185,29 @@ class ClockSampler:
         return out
 
 
+def bind_near_gpu(torch, local):
+    """Multi-rank runs: keep this process (and with it the pinned host buffers it allocates -- the e2e leg moves 20 GB per rank
+    each way) on the CPU cores, hence the NUMA node, next to its GPU.  Round 1's e2e leg fell from 52 GB/s per GPU at N = 1 to
+    14 GB/s at N = 8 with all ranks' buffers wherever the launcher had put the processes.  Best effort: any failure leaves the
+    affinity as it was.  Returns what it did, for the JSON line."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        cpus = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if not ids:
+            return None
+        os.sched_setaffinity(0, ids)
+        node = open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip()
+        return {"gpu": bdf, "numa_node": int(node), "cpus": cpus}
+    except Exception as e:          # noqa: BLE001
+        return {"error": str(e)[:120]}
+
+
 def nccl_parity_check(pb, dist, torch, rank, world):
     """Untimed prologue of the N > 1 runs (the driver's test box has one GPU, its bench boxes have N): a small lid-driven cavity
     stepped over the N-rank lattice -- the very exchange path the timed steps use -- must give, bit for bit, the populations of
@@ -249,6 +272,7 @@ def our_arm(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the engine has no CPU fallback"
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(torch, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -431,7 +455,7 @@ def our_arm(args):
         e2e = {"value": cells_global * k2 / dt / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": (nbytes * world) / k2 + 48 * world,
                "d2h_bytes_per_step": (nbytes * world) / k2 + 32 * world,
-               "steps": k2, "seconds": dt, "pinned_host": pinned,
+               "steps": k2, "seconds": dt, "pinned_host": pinned, "cpu_binding": numa,
                # where the time goes (max over ranks each): the two PCIe transfers of the whole lattice, and the time loop whose
                # every step changes the lid velocity on the device (set_bc_values_kernel), sweeps, and reads the statistics back
                "h2d_s": h2d_s, "d2h_s": d2h_s, "loop_s": loop_s, "step_ms": loop_s / k2 * 1e3,
