@@ -212,31 +212,31 @@ struct LB {
     PLB_HD static void bgk_ma2_equilibria(T rhoBar, T invRho, const T j[3], T jSqr, T* eq) {
         constexpr int h = H;
         const T t0 = t(0), t1 = t(1), t4 = t(4);
-        const T kx = (T)3 * j[0], ky = (T)3 * j[1], kz = (T)3 * j[2];
-        const T kxSqr_ = invRho / (T)2 * kx * kx;
-        const T kySqr_ = invRho / (T)2 * ky * ky;
-        const T kzSqr_ = invRho / (T)2 * kz * kz;
-        const T kxky_ = invRho * kx * ky;
-        const T kxkz_ = invRho * kx * kz;
-        const T kykz_ = invRho * ky * kz;
-        const T C1 = rhoBar + invRho * (T)3 * jSqr;
-        T C2, C3;
-        C3 = -kxSqr_ - kySqr_ - kzSqr_;           eq[0] = t0 * (C1 + C3);
-        C2 = -kx;       C3 = -kySqr_ - kzSqr_;    eq[1] = t1 * (C1 + C2 + C3); eq[1 + h] = t1 * (C1 - C2 + C3);
-        C2 = -ky;       C3 = -kxSqr_ - kzSqr_;    eq[2] = t1 * (C1 + C2 + C3); eq[2 + h] = t1 * (C1 - C2 + C3);
-        C2 = -kz;       C3 = -kxSqr_ - kySqr_;    eq[3] = t1 * (C1 + C2 + C3); eq[3 + h] = t1 * (C1 - C2 + C3);
-        C2 = -kx - ky;  C3 = kxky_ - kzSqr_;      eq[4] = t4 * (C1 + C2 + C3); eq[4 + h] = t4 * (C1 - C2 + C3);
-        C2 = -kx + ky;  C3 = -kxky_ - kzSqr_;     eq[5] = t4 * (C1 + C2 + C3); eq[5 + h] = t4 * (C1 - C2 + C3);
-        C2 = -kx - kz;  C3 = kxkz_ - kySqr_;      eq[6] = t4 * (C1 + C2 + C3); eq[6 + h] = t4 * (C1 - C2 + C3);
-        C2 = -kx + kz;  C3 = -kxkz_ - kySqr_;     eq[7] = t4 * (C1 + C2 + C3); eq[7 + h] = t4 * (C1 - C2 + C3);
-        C2 = -ky - kz;  C3 = kykz_ - kxSqr_;      eq[8] = t4 * (C1 + C2 + C3); eq[8 + h] = t4 * (C1 - C2 + C3);
-        C2 = -ky + kz;  C3 = -kykz_ - kxSqr_;     eq[9] = t4 * (C1 + C2 + C3); eq[9 + h] = t4 * (C1 - C2 + C3);
+        const T ax = (T)3 * j[0], ay = (T)3 * j[1], az = (T)3 * j[2];
+        const T qxx = invRho / (T)2 * ax * ax;
+        const T qyy = invRho / (T)2 * ay * ay;
+        const T qzz = invRho / (T)2 * az * az;
+        const T qxy = invRho * ax * ay;
+        const T qxz = invRho * ax * az;
+        const T qyz = invRho * ay * az;
+        const T iso = rhoBar + invRho * (T)3 * jSqr;
+        T lin, quad;
+        quad = -qxx - qyy - qzz;           eq[0] = t0 * (iso + quad);
+        lin = -ax;       quad = -qyy - qzz;    eq[1] = t1 * (iso + lin + quad); eq[1 + h] = t1 * (iso - lin + quad);
+        lin = -ay;       quad = -qxx - qzz;    eq[2] = t1 * (iso + lin + quad); eq[2 + h] = t1 * (iso - lin + quad);
+        lin = -az;       quad = -qxx - qyy;    eq[3] = t1 * (iso + lin + quad); eq[3 + h] = t1 * (iso - lin + quad);
+        lin = -ax - ay;  quad = qxy - qzz;      eq[4] = t4 * (iso + lin + quad); eq[4 + h] = t4 * (iso - lin + quad);
+        lin = -ax + ay;  quad = -qxy - qzz;     eq[5] = t4 * (iso + lin + quad); eq[5 + h] = t4 * (iso - lin + quad);
+        lin = -ax - az;  quad = qxz - qyy;      eq[6] = t4 * (iso + lin + quad); eq[6 + h] = t4 * (iso - lin + quad);
+        lin = -ax + az;  quad = -qxz - qyy;     eq[7] = t4 * (iso + lin + quad); eq[7 + h] = t4 * (iso - lin + quad);
+        lin = -ay - az;  quad = qyz - qxx;      eq[8] = t4 * (iso + lin + quad); eq[8 + h] = t4 * (iso - lin + quad);
+        lin = -ay + az;  quad = -qyz - qxx;     eq[9] = t4 * (iso + lin + quad); eq[9 + h] = t4 * (iso - lin + quad);
         if constexpr (Q == 27) {
             const T t10 = t(10);
-            C2 = -kx - ky - kz;  C3 = kxky_ + kxkz_ + kykz_;   eq[10] = t10 * (C1 + C2 + C3); eq[23] = t10 * (C1 - C2 + C3);
-            C2 = -kx - ky + kz;  C3 = kxky_ - kxkz_ - kykz_;   eq[11] = t10 * (C1 + C2 + C3); eq[24] = t10 * (C1 - C2 + C3);
-            C2 = -kx + ky - kz;  C3 = -kxky_ + kxkz_ - kykz_;  eq[12] = t10 * (C1 + C2 + C3); eq[25] = t10 * (C1 - C2 + C3);
-            C2 = -kx + ky + kz;  C3 = -kxky_ - kxkz_ + kykz_;  eq[13] = t10 * (C1 + C2 + C3); eq[26] = t10 * (C1 - C2 + C3);
+            lin = -ax - ay - az;  quad = qxy + qxz + qyz;   eq[10] = t10 * (iso + lin + quad); eq[23] = t10 * (iso - lin + quad);
+            lin = -ax - ay + az;  quad = qxy - qxz - qyz;   eq[11] = t10 * (iso + lin + quad); eq[24] = t10 * (iso - lin + quad);
+            lin = -ax + ay - az;  quad = -qxy + qxz - qyz;  eq[12] = t10 * (iso + lin + quad); eq[25] = t10 * (iso - lin + quad);
+            lin = -ax + ay + az;  quad = -qxy - qxz + qyz;  eq[13] = t10 * (iso + lin + quad); eq[26] = t10 * (iso - lin + quad);
         }
     }
 
@@ -247,52 +247,8 @@ struct LB {
     PLB_HD static T bgk_ma2_collision(T* f, T rhoBar, const T j[3], T omega) {
         const T invRho = invRhoOf(rhoBar);
         if constexpr (Q == 19) {
-            const T one_m_omega = (T)1 - omega;
-            const T t0_omega = t(0) * omega;
-            const T t1_omega = t(1) * omega;
-            const T t4_omega = t(4) * omega;
-            const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
-            const T kx = (T)3 * j[0];
-            const T ky = (T)3 * j[1];
-            const T kz = (T)3 * j[2];
-            const T kxSqr_ = invRho / (T)2 * kx * kx;
-            const T kySqr_ = invRho / (T)2 * ky * ky;
-            const T kzSqr_ = invRho / (T)2 * kz * kz;
-            const T kxky_ = invRho * kx * ky;
-            const T kxkz_ = invRho * kx * kz;
-            const T kykz_ = invRho * ky * kz;
-            const T C1 = rhoBar + invRho * (T)3 * jSqr;
-            T C2, C3;
-            C3 = -kxSqr_ - kySqr_ - kzSqr_;
-            f[0] *= one_m_omega; f[0] += t0_omega * (C1 + C3);
-            C2 = -kx;  C3 = -kySqr_ - kzSqr_;
-            f[1]  *= one_m_omega; f[1]  += t1_omega * (C1 + C2 + C3);
-            f[10] *= one_m_omega; f[10] += t1_omega * (C1 - C2 + C3);
-            C2 = -ky;  C3 = -kxSqr_ - kzSqr_;
-            f[2]  *= one_m_omega; f[2]  += t1_omega * (C1 + C2 + C3);
-            f[11] *= one_m_omega; f[11] += t1_omega * (C1 - C2 + C3);
-            C2 = -kz;  C3 = -kxSqr_ - kySqr_;
-            f[3]  *= one_m_omega; f[3]  += t1_omega * (C1 + C2 + C3);
-            f[12] *= one_m_omega; f[12] += t1_omega * (C1 - C2 + C3);
-            C2 = -kx - ky;  C3 = kxky_ - kzSqr_;
-            f[4]  *= one_m_omega; f[4]  += t4_omega * (C1 + C2 + C3);
-            f[13] *= one_m_omega; f[13] += t4_omega * (C1 - C2 + C3);
-            C2 = -kx + ky;  C3 = -kxky_ - kzSqr_;
-            f[5]  *= one_m_omega; f[5]  += t4_omega * (C1 + C2 + C3);
-            f[14] *= one_m_omega; f[14] += t4_omega * (C1 - C2 + C3);
-            C2 = -kx - kz;  C3 = kxkz_ - kySqr_;
-            f[6]  *= one_m_omega; f[6]  += t4_omega * (C1 + C2 + C3);
-            f[15] *= one_m_omega; f[15] += t4_omega * (C1 - C2 + C3);
-            C2 = -kx + kz;  C3 = -kxkz_ - kySqr_;
-            f[7]  *= one_m_omega; f[7]  += t4_omega * (C1 + C2 + C3);
-            f[16] *= one_m_omega; f[16] += t4_omega * (C1 - C2 + C3);
-            C2 = -ky - kz;  C3 = kykz_ - kxSqr_;
-            f[8]  *= one_m_omega; f[8]  += t4_omega * (C1 + C2 + C3);
-            f[17] *= one_m_omega; f[17] += t4_omega * (C1 - C2 + C3);
-            C2 = -ky + kz;  C3 = -kykz_ - kxSqr_;
-            f[9]  *= one_m_omega; f[9]  += t4_omega * (C1 + C2 + C3);
-            f[18] *= one_m_omega; f[18] += t4_omega * (C1 - C2 + C3);
-            return invRho * invRho * jSqr;
+            // the reference's D3Q19 specialisation IS the explicit-invRho form called with 1/rho (dynamicsTemplates3D.h:2476-2478)
+            return bgk_ma2_collision_base(f, rhoBar, j, omega, invRho);
         } else {
             const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
 #pragma unroll
@@ -308,40 +264,40 @@ struct LB {
     /// with an explicit invRho, used by bgk_inc_collision (:2480-2482, :1680-1682) with invRho0.  Returns invRho^2 * jSqr.
     PLB_HD static T bgk_ma2_collision_base(T* f, T rhoBar, const T j[3], T omega, T invRho) {
         constexpr int h = H;
-        const T one_m_omega = (T)1 - omega;
-        const T t0_omega = t(0) * omega;
-        const T t1_omega = t(1) * omega;
-        const T t4_omega = t(4) * omega;
+        const T keep = (T)1 - omega;
+        const T w0 = t(0) * omega;
+        const T w1 = t(1) * omega;
+        const T w4 = t(4) * omega;
         const T jSqr = j[0] * j[0] + j[1] * j[1] + j[2] * j[2];
-        const T kx = (T)3 * j[0];
-        const T ky = (T)3 * j[1];
-        const T kz = (T)3 * j[2];
-        const T kxSqr_ = invRho / (T)2 * kx * kx;
-        const T kySqr_ = invRho / (T)2 * ky * ky;
-        const T kzSqr_ = invRho / (T)2 * kz * kz;
-        const T kxky_ = invRho * kx * ky;
-        const T kxkz_ = invRho * kx * kz;
-        const T kykz_ = invRho * ky * kz;
-        const T C1 = rhoBar + invRho * (T)3 * jSqr;
-        T C2, C3;
-        C3 = -kxSqr_ - kySqr_ - kzSqr_;
-        f[0] *= one_m_omega; f[0] += t0_omega * (C1 + C3);
-#define PLB_PAIR(I, TW) f[I] *= one_m_omega; f[I] += TW * (C1 + C2 + C3); f[I + h] *= one_m_omega; f[I + h] += TW * (C1 - C2 + C3);
-        C2 = -kx;       C3 = -kySqr_ - kzSqr_;   PLB_PAIR(1, t1_omega)
-        C2 = -ky;       C3 = -kxSqr_ - kzSqr_;   PLB_PAIR(2, t1_omega)
-        C2 = -kz;       C3 = -kxSqr_ - kySqr_;   PLB_PAIR(3, t1_omega)
-        C2 = -kx - ky;  C3 = kxky_ - kzSqr_;     PLB_PAIR(4, t4_omega)
-        C2 = -kx + ky;  C3 = -kxky_ - kzSqr_;    PLB_PAIR(5, t4_omega)
-        C2 = -kx - kz;  C3 = kxkz_ - kySqr_;     PLB_PAIR(6, t4_omega)
-        C2 = -kx + kz;  C3 = -kxkz_ - kySqr_;    PLB_PAIR(7, t4_omega)
-        C2 = -ky - kz;  C3 = kykz_ - kxSqr_;     PLB_PAIR(8, t4_omega)
-        C2 = -ky + kz;  C3 = -kykz_ - kxSqr_;    PLB_PAIR(9, t4_omega)
+        const T ax = (T)3 * j[0];
+        const T ay = (T)3 * j[1];
+        const T az = (T)3 * j[2];
+        const T qxx = invRho / (T)2 * ax * ax;
+        const T qyy = invRho / (T)2 * ay * ay;
+        const T qzz = invRho / (T)2 * az * az;
+        const T qxy = invRho * ax * ay;
+        const T qxz = invRho * ax * az;
+        const T qyz = invRho * ay * az;
+        const T iso = rhoBar + invRho * (T)3 * jSqr;
+        T lin, quad;
+        quad = -qxx - qyy - qzz;
+        f[0] *= keep; f[0] += w0 * (iso + quad);
+#define PLB_PAIR(I, TW) f[I] *= keep; f[I] += TW * (iso + lin + quad); f[I + h] *= keep; f[I + h] += TW * (iso - lin + quad);
+        lin = -ax;       quad = -qyy - qzz;   PLB_PAIR(1, w1)
+        lin = -ay;       quad = -qxx - qzz;   PLB_PAIR(2, w1)
+        lin = -az;       quad = -qxx - qyy;   PLB_PAIR(3, w1)
+        lin = -ax - ay;  quad = qxy - qzz;     PLB_PAIR(4, w4)
+        lin = -ax + ay;  quad = -qxy - qzz;    PLB_PAIR(5, w4)
+        lin = -ax - az;  quad = qxz - qyy;     PLB_PAIR(6, w4)
+        lin = -ax + az;  quad = -qxz - qyy;    PLB_PAIR(7, w4)
+        lin = -ay - az;  quad = qyz - qxx;     PLB_PAIR(8, w4)
+        lin = -ay + az;  quad = -qyz - qxx;    PLB_PAIR(9, w4)
         if constexpr (Q == 27) {
-            const T t10_omega = t(10) * omega;
-            C2 = -kx - ky - kz;  C3 = kxky_ + kxkz_ + kykz_;    PLB_PAIR(10, t10_omega)
-            C2 = -kx - ky + kz;  C3 = kxky_ - kxkz_ - kykz_;    PLB_PAIR(11, t10_omega)
-            C2 = -kx + ky - kz;  C3 = -kxky_ + kxkz_ - kykz_;   PLB_PAIR(12, t10_omega)
-            C2 = -kx + ky + kz;  C3 = -kxky_ - kxkz_ + kykz_;   PLB_PAIR(13, t10_omega)
+            const T w10 = t(10) * omega;
+            lin = -ax - ay - az;  quad = qxy + qxz + qyz;    PLB_PAIR(10, w10)
+            lin = -ax - ay + az;  quad = qxy - qxz - qyz;    PLB_PAIR(11, w10)
+            lin = -ax + ay - az;  quad = -qxy + qxz - qyz;   PLB_PAIR(12, w10)
+            lin = -ax + ay + az;  quad = -qxy - qxz + qyz;   PLB_PAIR(13, w10)
         }
 #undef PLB_PAIR
         return invRho * invRho * jSqr;
