@@ -1,5 +1,6 @@
-"""development tool: what each kind of boundary face costs the step at 512^3 (D3Q19 BGK fp64), fused vs eager plane completion
-usage: python tools/face_cost.py [n]      (env PLB_B200_EAGER_PLANES selects the mode)"""
+"""development tool: what each kind of boundary face costs the step at 512^3 (D3Q19 BGK fp64)
+usage: python tools/face_cost.py [n [cases]]      (PLB_B200_NO_HANDOFF=1: the plane pass writes every cell back into the lattice;
+FC_BLOCK=1: the "xyz" case uses setVelocityConditionOnBlockBoundaries, i.e. with edges and corners)"""
 import os, sys, json
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import torch
@@ -29,5 +30,5 @@ for name in sel:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); lat.collide_and_stream(K); e1.record(); torch.cuda.synchronize()
     sw, sn = lat.profile_read()
-    print("%-5s eager=%s  ms/step %.3f  sweep %.3f ms/step  launches/step %.1f" % (name, os.environ.get("PLB_B200_EAGER_PLANES", "0"), e0.elapsed_time(e1) / K, sw / K, (lat.launch_count() - l0) / K), flush=True)
+    print("%-5s no_handoff=%s  ms/step %.3f  sweep %.3f ms/step  launches/step %.1f" % (name, os.environ.get("PLB_B200_NO_HANDOFF", "0"), e0.elapsed_time(e1) / K, sw / K, (lat.launch_count() - l0) / K), flush=True)
     lat.close()
