@@ -7,7 +7,9 @@
 Workload (config.workload): BASELINE.json configs[1] -- 3D lid-driven cavity, D3Q19 BGK fp64, 512^3
 per GPU, regularized velocity boundaries on all faces / edges / corners (Palabos cavity3d), synthetic
 initial state rho=1, u=0.  With N GPUs the cavity is (512 N) x 512 x 512, one x-slab per rank
-(weak scaling, NCCL send/recv of the face-crossing populations between neighbours).
+(weak scaling; the rim cells of the sweep store the face-crossing populations straight into the neighbouring rank's slab
+over NVLink, NCCL send/recv is the fallback).  Multi-rank runs start with an untimed parity check of that transport
+("parity_check": small lattices stepped over the N ranks against a one-slab run).
 
 One JSON line on rank 0:
   value     whole-job MLUPS, state resident in HBM, CUDA events, max over ranks
