@@ -827,8 +827,8 @@ private:
     /// in this fork both managers, :712-747 and :940-974, hand out the regularized dynamics WITHOUT a data processor): the
     /// plane dynamics keep automaticPrepareCollision = true and complete the populations at the beginning of collide()
     /// (CompositeDynamics::collide core/dynamics.hh:470-475) -- nothing runs after streaming, the cell holds raw
-    /// populations between two steps.  Here: a plane "processor" entry with a = 1, never executed; the sweep completes such
-    /// cells on load (the machinery of the lazy completion, permanently on, without the on-the-fly completion for readers).
+    /// populations between two steps.  Here: a plane "processor" entry with a = 1, never executed as a stage after the step:
+    /// plane_stage_kernel completes such cells right before the sweep that collides them (advance_steps).
     int auto_model(int model) {
         if (model < 0 || model > 4) throw PlbError("unknown boundary condition model");
         // model 4 = createInterpBoundaryCondition3D (boundaryCondition3D.hh:1049-1085): plain Velocity / DensityDirichletBoundaryDynamics
@@ -849,8 +849,8 @@ private:
 
     /// The time loop's form of setBoundaryVelocity / setBoundaryDensity: when the set-up on the device is current (no dynamics,
     /// boundary or schedule change outstanding) the values are changed THERE, by one small kernel over the box -- no walk over
-    /// the host records, no upload, and the pending plane completion stays pending (it answers with the previous values,
-    /// Bc::stamp).  The host records are refreshed from the device before they are needed again (pull_record_values).
+    /// the host records, no upload (the plane completion of the step before has run with the previous values: nothing of it
+    /// is outstanding).  The host records are refreshed from the device before they are needed again (pull_record_values).
     bool set_values_on_device(const int box[6], int what, const T u[3], T rhoBar) {
         if (!stepped_ && !ext_) return false;                 // set-up phase: the host path batches everything into one upload
         if (dirtyDyns_) return false;

@@ -141,3 +141,15 @@ def test_save_state_load_state_cpp(slabs, tmp_path):
     assert (tmp_path / "restart.xml").read_text() == want
     ref = g["plb"].tobytes().decode()
     assert (tmp_path / "ckpt00000005_0.plb").read_text() == ref[:ref.index("        <DynamicsDict>")] + "    </Data>\n</Block3D>\n"
+
+
+def test_file_name_helpers_of_the_mirror_match_the_reference(tmp_path):
+    """CPU: plb::FileName / createFileName of include/palabos_b200/palabos3D.h against the output of the same probe compiled with the
+    reference's io/plbFiles.h + io/imageWriter.h (tests/golden/filename_probe.txt, made in the build container with
+    g++ -DUSE_REF -DPLB_USE_POSIX -I/root/reference/src ... tests/cpp/filename_probe.cpp oracle/_ref/libplb.a)"""
+    exe = tmp_path / "probe"
+    subprocess.run(["g++", "-std=c++11", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(HERE, "cpp", "filename_probe.cpp"),
+                    "-L" + os.path.join(ROOT, "palabos_b200"), "-lplb_b200", "-Wl,-rpath," + os.path.join(ROOT, "palabos_b200"), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out == open(os.path.join(HERE, "golden", "filename_probe.txt")).read()
