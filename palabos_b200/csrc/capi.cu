@@ -2,6 +2,8 @@
 // Every entry point catches C++ exceptions and returns 1/0 like the reference's CoProcessor3D
 // methods (coProcessors/coProcessor3D.h:77,93,103,115).
 #include <cstdio>
+#include <fcntl.h>
+#include <unistd.h>
 #include <algorithm>
 #include <cstring>
 #include <functional>
@@ -313,15 +315,17 @@ std::string trimmed(const std::string& t) {
 int plb_b200_parallel_save(plb_b200_lattice* L, const char* base_path, const char* data_file_entry, int global_id) {
     if (!L || !L->impl) return fail("null lattice handle");
     FILE* fp = nullptr;
+    int fd = -1;
     try {
         if (!base_path) throw PlbError("null path");
         const CreateDesc& d = L->desc;
         const std::string base(base_path), dat = base + ".dat";
         const std::vector<Component> comps = slab_components(L);
-        // every rank writes the bulks of its own slabs at their offsets (the reference: writeRawData, MPI-IO or gathered)
-        fp = std::fopen(dat.c_str(), d.rank == 0 ? "wb" : "r+b");
-        if (!fp && d.rank != 0) fp = std::fopen(dat.c_str(), "wb");
-        if (!fp) throw PlbError("Could not open file " + dat + " for saving");
+        // every rank writes the bulks of its own slabs at their offsets (the reference: writeRawData, MPI-IO or gathered).  Nobody
+        // truncates on opening -- the ranks arrive in any order --; rank 0 cuts the file to its final length at the end, which
+        // removes the tail of an older, longer file and never touches what another rank has written
+        fd = ::open(dat.c_str(), O_CREAT | O_WRONLY, 0644);
+        if (fd < 0) throw PlbError("Could not open file " + dat + " for saving");
         const size_t planeBytes = (size_t)d.ny * d.nz * d.q * d.prec;
         const int planes = (int)std::max<size_t>(1, (size_t(64) << 20) / planeBytes);
         std::vector<unsigned char> buf;
@@ -333,12 +337,17 @@ int plb_b200_parallel_save(plb_b200_lattice* L, const char* base_path, const cha
                 if (bytes != (size_t)(box[1] - box[0] + 1) * planeBytes) throw PlbError("a slab is split over ranks");
                 buf.resize(bytes);
                 L->impl->download(SBox(L, box), buf.data(), bytes);
-                if (fseeko(fp, (off_t)(c.begin + (long long)(x - c.box[0]) * (long long)planeBytes), SEEK_SET) != 0 ||
-                    std::fwrite(buf.data(), 1, bytes, fp) != bytes) throw PlbError("write error on " + dat);
+                off_t at = (off_t)(c.begin + (long long)(x - c.box[0]) * (long long)planeBytes);
+                for (size_t done = 0; done < bytes;) {
+                    const ssize_t w = ::pwrite(fd, buf.data() + done, bytes - done, at + (off_t)done);
+                    if (w <= 0) throw PlbError("write error on " + dat);
+                    done += (size_t)w;
+                }
             }
         }
-        if (std::fclose(fp) != 0) { fp = nullptr; throw PlbError("write error on " + dat); }
-        fp = nullptr;
+        if (d.rank == 0 && ::ftruncate(fd, (off_t)(comps.empty() ? 0 : comps.back().end)) != 0) throw PlbError("write error on " + dat);
+        if (::close(fd) != 0) { fd = -1; throw PlbError("write error on " + dat); }
+        fd = -1;
         if (d.rank == 0) {
             // writeXmlSpec io/multiBlockWriter3D.cpp:52-142, without the dynamics dictionary and the processor list: both are
             // optional to the reader (multiBlockReader3D.cpp:66-120) and describe the set-up, which lives in the program here
@@ -364,7 +373,7 @@ int plb_b200_parallel_save(plb_b200_lattice* L, const char* base_path, const cha
             if (std::fclose(fp) != 0) { fp = nullptr; throw PlbError("write error on " + plb); }
         }
         return 1;
-    } catch (const std::exception& e) { if (fp) std::fclose(fp); return fail(e.what()); }
+    } catch (const std::exception& e) { if (fp) std::fclose(fp); if (fd >= 0) ::close(fd); return fail(e.what()); }
 }
 
 int plb_b200_parallel_load(plb_b200_lattice* L, const char* base_path) {
